@@ -1,0 +1,172 @@
+/*
+ * pv_b200.h -- C ABI of the B200-native phase-vocoder engine (libpv_b200.so).
+ *
+ * This is the drop-in boundary for the analysis -> processing -> resynthesis path of
+ * davispolito/Phase-Vocoder.  Every entry point names the reference interface it replaces
+ * (paths relative to the reference checkout).  Plain pointers and sizes only; no C++ or
+ * torch types.  All functions return PV_OK (0) or a negative pv_status and record a
+ * message retrievable with pv_last_error() (the reference prints and exit()s instead:
+ * checkCUDAError_, src/io.cpp:115-124 -- the C++ shim host/phaseVocoder.h restores that).
+ *
+ * There is no CPU fallback: every call needs a CUDA device of compute capability 10.x and
+ * fails with PV_ERR_CUDA otherwise.
+ *
+ * Modes
+ *   PV_MODE_COMPAT     bit-for-intent reproduction of the reference pipeline, including its
+ *                      four defects (atanf quadrant loss, overwritten-x polar->rect, size-N
+ *                      C2R on a 2N spectrum, no OLA gain normalisation) -- SURVEY 3.2.
+ *   PV_MODE_CORRECTED  true phase vocoder: atan2, phase-difference unwrapping to true bin
+ *                      frequency, pitch / time scaling, fixed-point phase accumulation,
+ *                      WOLA gain.  Not implemented by the reference (parity unpinned).
+ */
+#ifndef PV_B200_H
+#define PV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PV_MAX_VOICES 8
+#define PV_MIN_WINDOW 64
+#define PV_MAX_WINDOW 4096
+
+typedef enum pv_status {
+    PV_OK = 0,
+    PV_ERR_PARAM = -1,       /* invalid argument                                   */
+    PV_ERR_CUDA = -2,        /* CUDA runtime / launch failure or no usable device  */
+    PV_ERR_ALLOC = -3,       /* allocation failure                                 */
+    PV_ERR_UNSUPPORTED = -4  /* valid but not available in this build              */
+} pv_status;
+
+typedef enum pv_mode { PV_MODE_COMPAT = 0, PV_MODE_CORRECTED = 1 } pv_mode;
+
+/* Window tables -- PhaseVocoder ctor, src/phaseVocoder.h:62-69 and :84-94. */
+typedef enum pv_window_type {
+    PV_WIN_HAMMING = 0,       /* 0.54-0.46cos(2 pi i/(N-1))   HEAD, phaseVocoder.h:85-89        */
+    PV_WIN_HANN_SYM = 1,      /* 0.5(1-cos(2 pi i/(N-1)))     commented line phaseVocoder.h:87  */
+    PV_WIN_HANN_PERIODIC = 2  /* 0.5(1-cos(2 pi i/N))         1-arg ctor :64-66, kernel.cu:85-91 */
+} pv_window_type;
+
+enum { PV_FLAG_NAN_COMPAT = 1 /* keep atanf(0/0)=NaN of kernel.cu:108 (default: phase 0) */ };
+
+/* Parameter carrier = the fields of class PhaseVocoder (src/phaseVocoder.h:25-30) plus the
+ * knobs the reference hard-codes.                                                         */
+typedef struct pv_params {
+    int32_t window;                 /* N  = PhaseVocoder::nSamps, power of two 64..4096       */
+    int32_t hop_in;                 /* Ha = PhaseVocoder::hopSize (= N / hop divisor, :79)    */
+    int32_t hop_out;                /* Hs = PhaseVocoder::outHopSize (= scale*hopSize, :104)  */
+    int32_t mode;                   /* pv_mode                                                */
+    int32_t window_type;            /* pv_window_type                                         */
+    int32_t n_voices;               /* corrected mode: pitch voices per stream (1..8); compat: 1 */
+    float pitch[PV_MAX_VOICES];     /* corrected mode: pitch ratio per voice (1.0 = none)     */
+    int32_t flags;
+    int32_t device;                 /* CUDA ordinal, -1 = current device                      */
+} pv_params;
+
+typedef struct pv_handle pv_handle;
+
+/* Last error message of the calling thread ("" if none). */
+const char *pv_last_error(void);
+
+/* Library / build description: "pv_b200 <version> sm_100a ..." */
+const char *pv_version(void);
+
+/* Replaces PhaseVocoder::PhaseVocoder(int,Effect,float,int) (src/phaseVocoder.h:79-116):
+ * validates parameters, builds the window table on the host exactly as the reference does
+ * (float arithmetic) and uploads it with the twiddle tables.                               */
+int pv_create(const pv_params *params, pv_handle **out);
+
+/* Replaces PhaseVocoder::~PhaseVocoder (src/phaseVocoder.h:128-130). */
+void pv_destroy(pv_handle *h);
+
+int pv_get_params(const pv_handle *h, pv_params *out);
+
+/* Copies the N-entry window table (PhaseVocoder::imp, src/phaseVocoder.h:16,85-89) to host. */
+int pv_window_table(const pv_handle *h, float *host_out);
+
+/* Reference frame schedule for a stream of num_samples (src/main.cpp:231 and :266).        */
+int pv_reference_schedule(const pv_handle *h, int64_t num_samples, int64_t *n_analysed,
+                          int64_t *n_synth);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-frame entry points: the reference's own granularity.  Pointers must be device
+ * accessible (device or managed memory), exactly as the reference requires.  Synchronous.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Replaces PhaseVocoder::analysis_CUFFT (src/phaseVocoder.cpp:25-33) ->
+ * CudaPhase::pv_analysis_CUFFT (karnel/kernel.cu:299-348): in[N] -> out float2[2N] {mag,phase}.
+ * Unlike the reference the output buffer need not be pre-zeroed and no scratch is needed.  */
+int pv_analysis(pv_handle *h, const float *in, float *out_magphase);
+
+/* Replaces PhaseVocoder::resynthesis_CUFFT (src/phaseVocoder.cpp:60-76) ->
+ * CudaPhase::resynthesis_CUFFT (karnel/kernel.cu:352-432): back[N], front float2[2N] -> out[N].
+ * front is NOT modified (the reference rewrites it in place, kernel.cu:354).               */
+int pv_resynthesis(pv_handle *h, const float *back, const float *front_magphase, float *out);
+
+/* Replaces PhaseVocoder::test_overlap_add (src/phaseVocoder.cpp:20-23, kernel.cu:289-298):
+ * window -> half swap -> half swap -> window -> overlap-add, no FFT.                        */
+int pv_test_overlap_add(pv_handle *h, const float *in, const float *back, float *out);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched entry points (device pointers, asynchronous on `cuda_stream`, a cudaStream_t
+ * passed as void*; NULL = default stream).
+ * ---------------------------------------------------------------------------------------- */
+
+/* The analysis loop of src/main.cpp:228-250 in one launch: frame k (0 <= k < n_frames) reads
+ * in[k*Ha .. k*Ha+N) (samples at index >= n_in read as 0) and writes
+ * out_magphase[k][2N] {mag, phase}.                                                         */
+int pv_analysis_batch(pv_handle *h, const float *in, int64_t n_in, int64_t n_frames,
+                      float *out_magphase, void *cuda_stream);
+
+/* The resynthesis loop of src/main.cpp:264-297 in one launch: consumes spectra[k][2N],
+ * carries back[N] (in/out, main.cpp:253-258,279) and writes out[k*Hs .. (k+1)*Hs).           */
+int pv_resynthesis_batch(pv_handle *h, const float *spectra, int64_t n_frames, float *back,
+                         float *out, void *cuda_stream);
+
+/* Bytes of per-stream carried state (compat: the accumulated frame `back`, N floats;
+ * corrected: previous analysis phase, phase accumulators and OLA accumulators per voice).    */
+size_t pv_state_bytes(const pv_handle *h);
+
+/* THE HOT PATH: fused analysis -> processing -> resynthesis/overlap-add over a batch of
+ * independent streams (channels), replacing both host loops of src/main.cpp:228-297 and every
+ * kernel / cuFFT call under them.
+ *
+ *   in          n_streams rows of n_in samples, row pitch in_stride (floats)
+ *   n_analysed  compat: frames k >= n_analysed are zero spectra (main.cpp:216,231); pass
+ *               n_frames for "all".  corrected: ignored.
+ *   n_frames    frames synthesised per stream; frame k reads in[k*Ha .. k*Ha+N), zero past n_in
+ *   out         [stream][voice][n_frames*Hs]: out + s*out_stream_stride + v*out_voice_stride
+ *   state       NULL, or n_streams * pv_state_bytes(h) bytes: read as the carry-in when
+ *               (flags & PV_PROCESS_CARRY_IN), written as the carry-out when
+ *               (flags & PV_PROCESS_CARRY_OUT).
+ * Long streams are split into frame-range segments processed concurrently (the (N-Hs) OLA
+ * halo is recomputed, so the result does not depend on the split).                            */
+enum { PV_PROCESS_CARRY_IN = 1, PV_PROCESS_CARRY_OUT = 2 };
+
+int pv_process_device(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride,
+                      int64_t n_in, int64_t n_analysed, int64_t n_frames, float *out,
+                      int64_t out_stream_stride, int64_t out_voice_stride, void *state,
+                      int32_t flags, void *cuda_stream);
+
+/* Same with HOST buffers (pinned or pageable): H2D, kernel, D2H, synchronise.  This is the
+ * call the C++ PhaseVocoder shim and the CLI make, and what bench.py times as `e2e`.         */
+int pv_process_host(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride,
+                    int64_t n_in, int64_t n_analysed, int64_t n_frames, float *out,
+                    int64_t out_stream_stride, int64_t out_voice_stride, void *state,
+                    int32_t flags);
+
+/* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
+int64_t pv_launch_count(const pv_handle *h);
+
+/* Average device time in ms of the fused kernel launches issued since the last call of
+ * pv_timing_reset (CUDA events recorded on the launching stream); 0 if none.               */
+int pv_timing_enable(pv_handle *h, int32_t on);
+int pv_timing_read(pv_handle *h, double *total_ms, int64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PV_B200_H */

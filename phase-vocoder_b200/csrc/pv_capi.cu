@@ -1,0 +1,516 @@
+// pv_capi.cu -- implementation of the C ABI declared in include/pv_b200.h.
+// Host-side only: parameter validation, table construction, segment planning, launches.
+#include <cmath>
+#include <cstdarg>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "pv_internal.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+struct pv_handle {
+    pv_params p;
+    int device;
+    int sm_count;
+    PvDev dev;
+    // owned device memory
+    float *d_win = nullptr;
+    float2 *d_tw = nullptr;
+    uint32_t *d_nomA = nullptr;
+    int32_t *d_alo = nullptr, *d_ahi = nullptr;
+    uint64_t *d_nomS = nullptr;
+    std::vector<float> h_win;
+    // segment plan cache
+    PvSegment *d_segs = nullptr;
+    size_t segs_cap = 0;
+    int32_t n_segs = 0;
+    int64_t plan_streams = -1, plan_frames = -1;
+    int32_t plan_flags = -1;
+    // staging for the host-pointer entry point
+    float *d_in = nullptr, *d_out = nullptr;
+    size_t in_cap = 0, out_cap = 0;
+    void *d_state = nullptr;
+    size_t state_cap = 0;
+    cudaStream_t copy_stream = nullptr;
+    // accounting
+    int64_t launches = 0;
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define PV_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(PV_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int ilog2(int n)
+{
+    int l = 0;
+    while ((1 << l) < n) ++l;
+    return l;
+}
+
+// Window tables, float arithmetic on the host as the reference does (src/phaseVocoder.h:62-69,
+// 84-94): omega is a float, the cosine is the float overload.
+void make_window(int type, int N, std::vector<float> &w)
+{
+    w.resize(N);
+    if (type == PV_WIN_HANN_PERIODIC) {
+        for (int i = 0; i < N; i++) w[i] = 0.5f * (1.f - cosf((float)(2.f * M_PI * i / N)));
+        return;
+    }
+    const float omega = (float)(2.f * M_PI / (N - 1));
+    for (int i = 0; i < N; i++) {
+        const float c = cosf(omega * (float)i);
+        w[i] = (type == PV_WIN_HAMMING) ? (0.54f - 0.46f * c) : (0.5f * (1.f - c));
+    }
+}
+
+template <class T>
+int upload(T **dst, const std::vector<T> &src)
+{
+    PV_CUDA(cudaMalloc((void **)dst, sizeof(T) * src.size()));
+    PV_CUDA(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
+    return PV_OK;
+}
+
+// Integer tables of the corrected mode (DESIGN.md "corrected mode"; same definitions as
+// oracle/pv_oracle.h, implemented independently).
+void corrected_tables(int N, int Ha, int Hs, double beta, uint64_t *Rq, int32_t *a_lo, int32_t *a_hi,
+                      uint64_t *nomS)
+{
+    const int h = N / 2, nb = h + 1, lg = ilog2(N);
+    const uint64_t bq = (uint64_t)llround(beta * 4294967296.0);
+    *Rq = (bq * (uint64_t)Hs + (uint64_t)(Ha / 2)) / (uint64_t)Ha;
+    for (int s = 0; s < nb; s++) { a_lo[s] = 1; a_hi[s] = 0; }
+    for (int a = 0; a < nb; a++) {
+        const uint64_t s = ((uint64_t)a * bq + 0x80000000ull) >> 32;
+        if (s > (uint64_t)h) break;
+        if (a_lo[s] > a_hi[s]) a_lo[s] = a;
+        a_hi[s] = a;
+    }
+    for (int s = 0; s < nb; s++)
+        nomS[s] = (a_lo[s] > a_hi[s]) ? 0 : ((bq * (uint64_t)a_hi[s] * (uint64_t)Hs) << (32 - lg));
+}
+
+// Splits every stream into frame-range segments so that the grid fills the machine.
+// The (R-1)-frame OLA halo in front of each segment is recomputed (compat frames are
+// independent), so the output does not depend on the split.
+int plan_segments(pv_handle *h, int64_t n_streams, int64_t n_frames, int32_t flags, cudaStream_t st)
+{
+    if (h->plan_streams == n_streams && h->plan_frames == n_frames && h->plan_flags == flags) return PV_OK;
+    const int N = h->p.window, Hs = h->p.hop_out;
+    const int64_t halo = (N - 1) / Hs;                     // frames k' < k that still overlap frame k
+    const int64_t target = (int64_t)h->sm_count * 8;
+    int64_t per_stream = (target + n_streams - 1) / n_streams;
+    if (per_stream < 1) per_stream = 1;
+    int64_t seg_len = (n_frames + per_stream - 1) / per_stream;
+    const int64_t min_len = std::max<int64_t>(8 * halo, 8);
+    if (seg_len < min_len) seg_len = min_len;
+    std::vector<PvSegment> segs;
+    for (int64_t s = 0; s < n_streams; s++) {
+        for (int64_t k0 = 0; k0 < n_frames; k0 += seg_len) {
+            PvSegment g{};
+            g.stream = (int32_t)s;
+            g.k_emit = k0;
+            g.k_end = std::min(n_frames, k0 + seg_len);
+            g.k_begin = std::max<int64_t>(0, k0 - halo);
+            g.carry_in = (k0 == 0 && (flags & PV_PROCESS_CARRY_IN)) ? 1 : 0;
+            g.carry_out = (g.k_end == n_frames && (flags & PV_PROCESS_CARRY_OUT)) ? 1 : 0;
+            segs.push_back(g);
+        }
+    }
+    if (segs.size() > h->segs_cap) {
+        if (h->d_segs) cudaFree(h->d_segs);
+        h->d_segs = nullptr;
+        PV_CUDA(cudaMalloc((void **)&h->d_segs, sizeof(PvSegment) * segs.size()));
+        h->segs_cap = segs.size();
+    }
+    // pageable source: the runtime stages it before returning, so `segs` may die afterwards
+    PV_CUDA(cudaMemcpyAsync(h->d_segs, segs.data(), sizeof(PvSegment) * segs.size(), cudaMemcpyHostToDevice, st));
+    PV_CUDA(cudaStreamSynchronize(st));
+    h->n_segs = (int32_t)segs.size();
+    h->plan_streams = n_streams;
+    h->plan_frames = n_frames;
+    h->plan_flags = flags;
+    return PV_OK;
+}
+
+int ensure(float **buf, size_t *cap, size_t need)
+{
+    if (need <= *cap) return PV_OK;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc((void **)buf, need * sizeof(float));
+    if (e != cudaSuccess) return fail(PV_ERR_ALLOC, "cudaMalloc(%zu floats) failed: %s", need, cudaGetErrorString(e));
+    *cap = need;
+    return PV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *pv_last_error(void) { return g_err.c_str(); }
+
+const char *pv_version(void) { return "pv_b200 0.1 (sm_100a; in-kernel FFT, no cuFFT, no CPU fallback)"; }
+
+int pv_create(const pv_params *params, pv_handle **out)
+{
+    if (!params || !out) return fail(PV_ERR_PARAM, "pv_create: null argument");
+    *out = nullptr;
+    const pv_params &p = *params;
+    const int N = p.window;
+    if (N < PV_MIN_WINDOW || N > PV_MAX_WINDOW || (N & (N - 1)))
+        return fail(PV_ERR_PARAM, "window must be a power of two in [%d, %d], got %d", PV_MIN_WINDOW, PV_MAX_WINDOW, N);
+    if (p.hop_in < 1) return fail(PV_ERR_PARAM, "hop_in must be >= 1, got %d", p.hop_in);
+    if (p.hop_out < 1 || p.hop_out > N)
+        return fail(PV_ERR_PARAM, "hop_out must be in [1, window], got %d", p.hop_out);
+    if (p.mode != PV_MODE_COMPAT && p.mode != PV_MODE_CORRECTED) return fail(PV_ERR_PARAM, "bad mode %d", p.mode);
+    if (p.window_type < PV_WIN_HAMMING || p.window_type > PV_WIN_HANN_PERIODIC)
+        return fail(PV_ERR_PARAM, "bad window_type %d", p.window_type);
+    int V = p.n_voices;
+    if (p.mode == PV_MODE_COMPAT) {
+        if (V != 0 && V != 1) return fail(PV_ERR_PARAM, "compat mode has exactly one voice");
+        V = 1;
+    } else {
+        if (V < 1 || V > PV_MAX_VOICES) return fail(PV_ERR_PARAM, "n_voices must be in [1, %d]", PV_MAX_VOICES);
+        for (int v = 0; v < V; v++)
+            if (!(p.pitch[v] >= 0.25f && p.pitch[v] <= 4.0f))
+                return fail(PV_ERR_PARAM, "pitch[%d] = %g outside [0.25, 4]", v, (double)p.pitch[v]);
+    }
+    int device = p.device;
+    if (device < 0) PV_CUDA(cudaGetDevice(&device));
+    cudaDeviceProp prop;
+    PV_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(PV_ERR_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major,
+                    prop.minor);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(PV_ERR_CUDA, "cannot select device %d", device);
+
+    pv_handle *h = new pv_handle();
+    h->p = p;
+    h->p.n_voices = V;
+    h->p.device = device;
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    make_window(p.window_type, N, h->h_win);
+    std::vector<float2> tw(N);
+    for (int k = 0; k < N; k++) {
+        const double a = -M_PI * (double)k / (double)N;
+        tw[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    int rc = upload(&h->d_win, h->h_win);
+    if (rc == PV_OK) rc = upload(&h->d_tw, tw);
+    PvDev &d = h->dev;
+    memset(&d, 0, sizeof d);
+    d.N = N;
+    d.lgN = ilog2(N);
+    d.Ha = p.hop_in;
+    d.Hs = p.hop_out;
+    d.flags = p.flags;
+    d.inv_N = 1.0f / (float)N;
+    d.V = V;
+    if (rc == PV_OK && p.mode == PV_MODE_CORRECTED) {
+        const int nb = N / 2 + 1, lg = d.lgN;
+        std::vector<uint32_t> nomA(nb);
+        for (int b = 0; b < nb; b++) nomA[b] = (uint32_t)(((uint64_t)b * (uint64_t)p.hop_in) << (32 - lg));
+        std::vector<int32_t> alo((size_t)V * nb), ahi((size_t)V * nb);
+        std::vector<uint64_t> nomS((size_t)V * nb);
+        for (int v = 0; v < V; v++)
+            corrected_tables(N, p.hop_in, p.hop_out, (double)p.pitch[v], &d.Rq[v], &alo[(size_t)v * nb],
+                             &ahi[(size_t)v * nb], &nomS[(size_t)v * nb]);
+        double s2 = 0;
+        for (int i = 0; i < N; i++) s2 += (double)h->h_win[i] * (double)h->h_win[i];
+        d.gain = (float)((double)p.hop_out / s2);
+        rc = upload(&h->d_nomA, nomA);
+        if (rc == PV_OK) rc = upload(&h->d_alo, alo);
+        if (rc == PV_OK) rc = upload(&h->d_ahi, ahi);
+        if (rc == PV_OK) rc = upload(&h->d_nomS, nomS);
+    }
+    if (rc != PV_OK) {
+        pv_destroy(h);
+        return rc;
+    }
+    d.win = h->d_win;
+    d.tw = h->d_tw;
+    d.nomA = h->d_nomA;
+    d.a_lo = h->d_alo;
+    d.a_hi = h->d_ahi;
+    d.nomS = h->d_nomS;
+    *out = h;
+    return PV_OK;
+}
+
+void pv_destroy(pv_handle *h)
+{
+    if (!h) return;
+    DeviceGuard guard(h->device);
+    cudaFree(h->d_win);
+    cudaFree(h->d_tw);
+    cudaFree(h->d_nomA);
+    cudaFree(h->d_alo);
+    cudaFree(h->d_ahi);
+    cudaFree(h->d_nomS);
+    cudaFree(h->d_segs);
+    cudaFree(h->d_in);
+    cudaFree(h->d_out);
+    cudaFree(h->d_state);
+    for (auto &e : h->events) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    delete h;
+}
+
+int pv_get_params(const pv_handle *h, pv_params *out)
+{
+    if (!h || !out) return fail(PV_ERR_PARAM, "null argument");
+    *out = h->p;
+    return PV_OK;
+}
+
+int pv_window_table(const pv_handle *h, float *host_out)
+{
+    if (!h || !host_out) return fail(PV_ERR_PARAM, "null argument");
+    memcpy(host_out, h->h_win.data(), sizeof(float) * h->h_win.size());
+    return PV_OK;
+}
+
+int pv_reference_schedule(const pv_handle *h, int64_t num_samples, int64_t *n_analysed, int64_t *n_synth)
+{
+    if (!h) return fail(PV_ERR_PARAM, "null handle");
+    const int64_t Ha = h->p.hop_in, Hs = h->p.hop_out;
+    // for (i = 0; i < numSamples - hop; i += hop)   src/main.cpp:231
+    int64_t na = 0;
+    if (num_samples - Ha > 0) na = (num_samples - Ha + Ha - 1) / Ha;
+    if (n_analysed) *n_analysed = na;
+    if (n_synth) *n_synth = num_samples / Hs;     // src/main.cpp:266
+    return PV_OK;
+}
+
+size_t pv_state_bytes(const pv_handle *h)
+{
+    if (!h) return 0;
+    const size_t N = (size_t)h->p.window, nb = N / 2 + 1, V = (size_t)h->p.n_voices;
+    if (h->p.mode == PV_MODE_COMPAT) return N * sizeof(float);
+    // [have_prev u32 + pad][P_prev u32 nb (padded to 8)][psi u64 V*nb][acc f32 V*N]
+    return 8 + ((nb * 4 + 7) / 8) * 8 + V * nb * 8 + V * N * 4;
+}
+
+#define PV_COMPAT_ONLY(h, what)                                                                 \
+    if ((h)->p.mode != PV_MODE_COMPAT)                                                          \
+        return fail(PV_ERR_PARAM, what " is the reference's per-frame contract and exists in compat mode only")
+
+int pv_analysis(pv_handle *h, const float *in, float *out_magphase)
+{
+    if (!h || !in || !out_magphase) return fail(PV_ERR_PARAM, "pv_analysis: null argument");
+    PV_COMPAT_ONLY(h, "pv_analysis");
+    DeviceGuard guard(h->device);
+    PV_CUDA(pv_launch_analysis_batch(h->dev, in, h->p.window, 1, out_magphase, nullptr));
+    h->launches++;
+    PV_CUDA(cudaStreamSynchronize(nullptr));     // phaseVocoder.cpp:30
+    return PV_OK;
+}
+
+int pv_resynthesis(pv_handle *h, const float *back, const float *front_magphase, float *out)
+{
+    if (!h || !back || !front_magphase || !out) return fail(PV_ERR_PARAM, "pv_resynthesis: null argument");
+    PV_COMPAT_ONLY(h, "pv_resynthesis");
+    DeviceGuard guard(h->device);
+    PV_CUDA(pv_launch_resynthesis_frame(h->dev, back, front_magphase, out, nullptr));
+    h->launches++;
+    PV_CUDA(cudaStreamSynchronize(nullptr));     // phaseVocoder.cpp:75
+    return PV_OK;
+}
+
+int pv_test_overlap_add(pv_handle *h, const float *in, const float *back, float *out)
+{
+    if (!h || !in || !back || !out) return fail(PV_ERR_PARAM, "pv_test_overlap_add: null argument");
+    DeviceGuard guard(h->device);
+    PV_CUDA(pv_launch_test_overlap_add(h->dev, in, back, out, nullptr));
+    h->launches++;
+    PV_CUDA(cudaStreamSynchronize(nullptr));     // phaseVocoder.cpp:22
+    return PV_OK;
+}
+
+int pv_analysis_batch(pv_handle *h, const float *in, int64_t n_in, int64_t n_frames, float *out_magphase,
+                      void *cuda_stream)
+{
+    if (!h || !in || !out_magphase || n_in < 0 || n_frames < 0)
+        return fail(PV_ERR_PARAM, "pv_analysis_batch: bad argument");
+    PV_COMPAT_ONLY(h, "pv_analysis_batch");
+    if (n_frames > 0x7fffffffLL) return fail(PV_ERR_PARAM, "too many frames for one launch");
+    DeviceGuard guard(h->device);
+    PV_CUDA(pv_launch_analysis_batch(h->dev, in, n_in, n_frames, out_magphase, (cudaStream_t)cuda_stream));
+    if (n_frames) h->launches++;
+    return PV_OK;
+}
+
+int pv_resynthesis_batch(pv_handle *h, const float *spectra, int64_t n_frames, float *back, float *out,
+                         void *cuda_stream)
+{
+    if (!h || !spectra || !back || !out || n_frames < 0) return fail(PV_ERR_PARAM, "pv_resynthesis_batch: bad argument");
+    PV_COMPAT_ONLY(h, "pv_resynthesis_batch");
+    DeviceGuard guard(h->device);
+    PV_CUDA(pv_launch_resynthesis_batch(h->dev, spectra, n_frames, back, out, (cudaStream_t)cuda_stream));
+    if (n_frames) h->launches++;
+    return PV_OK;
+}
+
+int pv_process_device(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride, int64_t n_in,
+                      int64_t n_analysed, int64_t n_frames, float *out, int64_t out_stream_stride,
+                      int64_t out_voice_stride, void *state, int32_t flags, void *cuda_stream)
+{
+    if (!h || !in || !out) return fail(PV_ERR_PARAM, "pv_process: null argument");
+    if (n_streams < 0 || n_in < 0 || n_frames < 0 || in_stride < n_in)
+        return fail(PV_ERR_PARAM, "pv_process: bad sizes (n_streams=%lld n_in=%lld n_frames=%lld in_stride=%lld)",
+                    (long long)n_streams, (long long)n_in, (long long)n_frames, (long long)in_stride);
+    if (n_streams > 0x7fffffffLL) return fail(PV_ERR_PARAM, "too many streams");
+    if (out_stream_stride < n_frames * h->p.hop_out * (int64_t)h->p.n_voices && n_streams > 1)
+        return fail(PV_ERR_PARAM, "pv_process: out_stream_stride too small");
+    if ((flags & (PV_PROCESS_CARRY_IN | PV_PROCESS_CARRY_OUT)) && !state)
+        return fail(PV_ERR_PARAM, "pv_process: carry requested without a state buffer");
+    if (n_streams == 0 || n_frames == 0) return PV_OK;
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (h->p.mode != PV_MODE_COMPAT)
+        return fail(PV_ERR_UNSUPPORTED, "corrected mode is not available in this build yet");
+    int rc = plan_segments(h, n_streams, n_frames, flags, st);
+    if (rc != PV_OK) return rc;
+    PvProcessArgs a{};
+    a.in = in;
+    a.in_stride = in_stride;
+    a.n_in = n_in;
+    a.n_analysed = n_analysed;
+    a.n_frames = n_frames;
+    a.out = out;
+    a.out_stream_stride = out_stream_stride;
+    a.out_voice_stride = out_voice_stride;
+    a.state = (float *)state;
+    a.state_stride = (int64_t)(pv_state_bytes(h) / sizeof(float));
+    a.segs = h->d_segs;
+    a.n_segs = h->n_segs;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->timing) {
+        PV_CUDA(cudaEventCreate(&e0));
+        PV_CUDA(cudaEventCreate(&e1));
+        PV_CUDA(cudaEventRecord(e0, st));
+    }
+    PV_CUDA(pv_launch_compat_generic(h->dev, a, st));
+    h->launches++;
+    if (h->timing) {
+        PV_CUDA(cudaEventRecord(e1, st));
+        h->events.emplace_back(e0, e1);
+    }
+    return PV_OK;
+}
+
+int pv_process_host(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride, int64_t n_in,
+                    int64_t n_analysed, int64_t n_frames, float *out, int64_t out_stream_stride,
+                    int64_t out_voice_stride, void *state, int32_t flags)
+{
+    if (!h || !in || !out) return fail(PV_ERR_PARAM, "pv_process_host: null argument");
+    if (n_streams <= 0 || n_frames <= 0) return PV_OK;
+    DeviceGuard guard(h->device);
+    const int64_t V = h->p.n_voices, n_out = n_frames * h->p.hop_out;
+    int rc = ensure(&h->d_in, &h->in_cap, (size_t)(n_streams * n_in));
+    if (rc == PV_OK) rc = ensure(&h->d_out, &h->out_cap, (size_t)(n_streams * V * n_out));
+    if (rc != PV_OK) return rc;
+    const size_t sb = pv_state_bytes(h);
+    if (state) {
+        if ((size_t)n_streams * sb > h->state_cap) {
+            cudaFree(h->d_state);
+            h->d_state = nullptr;
+            PV_CUDA(cudaMalloc(&h->d_state, (size_t)n_streams * sb));
+            h->state_cap = (size_t)n_streams * sb;
+        }
+        if (flags & PV_PROCESS_CARRY_IN)
+            PV_CUDA(cudaMemcpyAsync(h->d_state, state, (size_t)n_streams * sb, cudaMemcpyHostToDevice, nullptr));
+    }
+    PV_CUDA(cudaMemcpy2DAsync(h->d_in, sizeof(float) * n_in, in, sizeof(float) * in_stride, sizeof(float) * n_in,
+                              (size_t)n_streams, cudaMemcpyHostToDevice, nullptr));
+    rc = pv_process_device(h, h->d_in, n_streams, n_in, n_in, n_analysed, n_frames, h->d_out, V * n_out, n_out,
+                           state ? h->d_state : nullptr, flags, nullptr);
+    if (rc != PV_OK) return rc;
+    for (int64_t v = 0; v < V; v++)
+        PV_CUDA(cudaMemcpy2DAsync(out + v * out_voice_stride, sizeof(float) * out_stream_stride, h->d_out + v * n_out,
+                                  sizeof(float) * V * n_out, sizeof(float) * n_out, (size_t)n_streams,
+                                  cudaMemcpyDeviceToHost, nullptr));
+    if (state && (flags & PV_PROCESS_CARRY_OUT))
+        PV_CUDA(cudaMemcpyAsync(state, h->d_state, (size_t)n_streams * sb, cudaMemcpyDeviceToHost, nullptr));
+    PV_CUDA(cudaStreamSynchronize(nullptr));
+    return PV_OK;
+}
+
+int64_t pv_launch_count(const pv_handle *h) { return h ? h->launches : 0; }
+
+int pv_timing_enable(pv_handle *h, int32_t on)
+{
+    if (!h) return fail(PV_ERR_PARAM, "null handle");
+    h->timing = on != 0;
+    return PV_OK;
+}
+
+int pv_timing_read(pv_handle *h, double *total_ms, int64_t *launches)
+{
+    if (!h) return fail(PV_ERR_PARAM, "null handle");
+    DeviceGuard guard(h->device);
+    double tot = 0;
+    int64_t n = 0;
+    for (auto &e : h->events) {
+        PV_CUDA(cudaEventSynchronize(e.second));
+        float ms = 0;
+        PV_CUDA(cudaEventElapsedTime(&ms, e.first, e.second));
+        tot += ms;
+        n++;
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    h->events.clear();
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = n;
+    return PV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,318 @@
+// pv_generic_kernels.cu -- shape-generic sm_100a kernels.
+//
+// These cover (a) the reference's per-frame entry points (analysis / resynthesis /
+// test_overlap_add), which by contract read and write the full 2N-bin {mag, phase} buffers
+// and are therefore HBM-bound on those buffers, and (b) a fused compat-mode stream kernel
+// that accepts ANY power-of-two window and any hop pair.  The tuned fused kernels for the
+// benchmarked shapes live in pv_fused_kernels.cu; pv_capi.cu picks between them.
+//
+// Transform layout (both kernel families): a real sequence of length 2M is packed into M
+// complex points, c[n] = x[2n] + j x[2n+1]; one M-point complex FFT plus a split step gives the
+// non-redundant half of the real spectrum.  Reference steps:
+//   A window              karnel/kernel.cu:68-74
+//   B zero-phase + pad    karnel/kernel.cu:25-32     (folded into the load index)
+//   C 2N-point DFT        karnel/kernel.cu:324-326   (cuFFT in the reference; in-kernel here)
+//   D {mag, atanf}        karnel/kernel.cu:101-109
+//   E polar->rect (D2)    karnel/kernel.cu:121-129
+//   F N-point C2R         karnel/kernel.cu:363-366
+//   G /N, half swap, win  karnel/kernel.cu:130-138, 51-59, 75-81
+//   H overlap-add         karnel/kernel.cu:111-119
+//   I emit hop            src/main.cpp:281-295
+#include "pv_internal.h"
+
+namespace {
+
+constexpr int kGenericThreads = 128;
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// Stockham radix-2 autosort FFT of M points held in shared memory (ping-pong x <-> y).
+// e^{-2 pi i k / M} = tw[k * tws] with tw the 2N-th roots table.  Returns the result buffer.
+__device__ float2 *fft_stockham(float2 *x, float2 *y, int M, int tws, const float2 *__restrict__ tw,
+                                bool inverse)
+{
+    int lg_s = 0;
+    for (int n = M; n > 1; n >>= 1, ++lg_s) {
+        const int m = n >> 1, s = 1 << lg_s;
+        for (int idx = threadIdx.x; idx < (M >> 1); idx += blockDim.x) {
+            const int p = idx >> lg_s, q = idx & (s - 1);
+            float2 w = tw[(p << lg_s) * tws];
+            if (inverse) w.y = -w.y;
+            const float2 a = x[q + s * p], b = x[q + s * (p + m)];
+            y[q + s * (2 * p)] = make_float2(a.x + b.x, a.y + b.y);
+            y[q + s * (2 * p + 1)] = cmul(make_float2(a.x - b.x, a.y - b.y), w);
+        }
+        __syncthreads();
+        float2 *t = x; x = y; y = t;
+    }
+    return x;
+}
+
+// Steps A+B: window, zero-phase shift, zero pad to 2N, packed as N complex points.
+__device__ void load_frame_compat(float2 *c, const float *__restrict__ in, int64_t base, int64_t n_in,
+                                  const PvDev &d)
+{
+    const int N = d.N, q = N >> 2;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        float2 v = make_float2(0.f, 0.f);
+        int i = -1;
+        if (n < q) i = (N >> 1) + 2 * n;
+        else if (n >= 3 * q) i = 2 * (n - 3 * q);
+        if (i >= 0) {
+            const int64_t g = base + i;
+            const float x0 = (g < n_in) ? in[g] : 0.f;
+            const float x1 = (g + 1 < n_in) ? in[g + 1] : 0.f;
+            v = make_float2(x0 * d.win[i], x1 * d.win[i + 1]);
+        }
+        c[n] = v;
+    }
+}
+
+// Bin k (0 <= k < N) of the 2N-point real spectrum from the packed N-point transform C.
+__device__ __forceinline__ float2 split_bin(const float2 *C, int k, const PvDev &d)
+{
+    const int N = d.N;
+    const float2 a = C[k];
+    float2 b = C[(N - k) & (N - 1)];
+    b.y = -b.y;
+    const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
+    const float2 dd = make_float2(a.x - b.x, a.y - b.y);
+    const float2 o = make_float2(0.5f * dd.y, -0.5f * dd.x);      // (a-b)/(2j)
+    const float2 t = cmul(d.tw[k], o);
+    return make_float2(e.x + t.x, e.y + t.y);
+}
+
+// Step D exactly as cudaMagFreq (kernel.cu:101-109).
+__device__ __forceinline__ float2 mag_phase(float2 X, int flags)
+{
+    const float mag = sqrtf(X.x * X.x + X.y * X.y);
+    float ph;
+    if (X.x == 0.f && X.y == 0.f && !(flags & PV_FLAG_NAN_COMPAT)) ph = 0.f;
+    else ph = atanf(X.y / X.x);
+    return make_float2(mag, ph);
+}
+
+// Step E exactly as cudaTimeScale with timeScale = 1 (kernel.cu:121-129, defect D2).
+__device__ __forceinline__ float2 polar_to_rect_d2(float2 mp)
+{
+    const float xr = mp.x * cosf(mp.y);
+    const float xi = xr * sinf(mp.y);
+    return make_float2(xr, xi);
+}
+
+// Pre-twiddle of the packed Hermitian inverse (N real outputs from N/2 complex points):
+// Z[k] = (Yk + conj(Ym)) + j * w * (Yk - conj(Ym)),  w = e^{+2 pi i k / N}, Ym = Y[N/2-k].
+__device__ __forceinline__ float2 herm_pack(float2 yk, float2 ym, float2 w)
+{
+    const float2 s = make_float2(yk.x + ym.x, yk.y - ym.y);
+    const float2 df = make_float2(yk.x - ym.x, yk.y + ym.y);
+    const float2 t = cmul(w, df);
+    return make_float2(s.x - t.y, s.y + t.x);
+}
+
+// Steps F (pre-twiddle) for all bins: reads Y via functor, writes Z[0..N/2) into z.
+template <class YF>
+__device__ void build_inverse_input(float2 *z, YF Y, const PvDev &d)
+{
+    const int N = d.N, h = N >> 1, q = N >> 2;
+    for (int k = threadIdx.x; k <= q; k += blockDim.x) {
+        float2 yk = Y(k), ym = Y(h - k);
+        if (k == 0) { yk.y = 0.f; ym.y = 0.f; }    // C2R ignores Im of bins 0 and N/2
+        const float2 t = d.tw[2 * k];               // e^{-2 pi i k / N}
+        z[k] = herm_pack(yk, ym, make_float2(t.x, -t.y));
+        if (k != 0 && k != q) z[h - k] = herm_pack(ym, yk, make_float2(-t.x, -t.y));
+    }
+}
+
+// Steps G+H for one frame: r = unnormalised packed inverse output, acc = OLA ring of N floats.
+__device__ void ola_accumulate(float *acc, const float2 *r, int pos0, bool zero_frame, const PvDev &d)
+{
+    const int N = d.N, h = N >> 1, keep = N - d.Hs;
+    for (int n = threadIdx.x; n < h; n += blockDim.x) {
+        const float2 v = zero_frame ? make_float2(0.f, 0.f) : r[n];
+        const int i = (2 * n + h) & (N - 1);        // half swap: y'[i] = y[(i+N/2) mod N]
+        const float y0 = (v.x / (float)N) * d.win[i];
+        const float y1 = (v.y / (float)N) * d.win[i + 1];
+        const int p0 = (pos0 + i) & (N - 1), p1 = (pos0 + i + 1) & (N - 1);
+        acc[p0] = (i < keep ? acc[p0] : 0.f) + y0;
+        acc[p1] = (i + 1 < keep ? acc[p1] : 0.f) + y1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-frame API kernels
+// ---------------------------------------------------------------------------------------------
+
+// One CTA per frame: steps A-D, all 2N bins written as {mag, phase}.
+__global__ void __launch_bounds__(kGenericThreads)
+analysis_batch_kernel(PvDev d, const float *__restrict__ in, int64_t n_in, float2 *__restrict__ out)
+{
+    extern __shared__ float2 sm[];
+    const int N = d.N;
+    float2 *a = sm, *b = sm + N;
+    const int64_t k = blockIdx.x;
+    load_frame_compat(a, in, k * (int64_t)d.Ha, n_in, d);
+    __syncthreads();
+    const float2 *C = fft_stockham(a, b, N, 2, d.tw, false);
+    float2 *o = out + k * 2 * (int64_t)N;
+    for (int kk = threadIdx.x; kk <= N; kk += blockDim.x) {
+        float2 X;
+        if (kk == N) X = make_float2(C[0].x - C[0].y, 0.f);
+        else X = split_bin(C, kk, d);
+        o[kk] = mag_phase(X, d.flags);
+        if (kk > 0 && kk < N) o[2 * N - kk] = mag_phase(make_float2(X.x, -X.y), d.flags);
+    }
+}
+
+// One CTA walks the frames of one spectra batch sequentially: steps E-I.
+// full_frame_out != nullptr: additionally dump the whole accumulated frame of the LAST frame
+// (the per-frame API returns all N samples, kernel.cu:352).
+__global__ void __launch_bounds__(kGenericThreads)
+resynthesis_batch_kernel(PvDev d, const float2 *__restrict__ spectra, int64_t n_frames,
+                         const float *__restrict__ back_in, float *__restrict__ back_out,
+                         float *__restrict__ out, float *__restrict__ full_frame_out)
+{
+    extern __shared__ float2 sm[];
+    const int N = d.N, h = N >> 1;
+    float2 *a = sm, *b = sm + h;
+    float *acc = reinterpret_cast<float *>(sm + N);
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+        acc[i] = (back_in != nullptr && i + d.Hs < N) ? back_in[i + d.Hs] : 0.f;
+    __syncthreads();
+    int pos0 = 0;
+    for (int64_t k = 0; k < n_frames; ++k) {
+        const float2 *sp = spectra + k * 2 * (int64_t)N;
+        build_inverse_input(a, [&](int kk) { return polar_to_rect_d2(sp[kk]); }, d);
+        __syncthreads();
+        const float2 *r = fft_stockham(a, b, h, 4, d.tw, true);
+        ola_accumulate(acc, r, pos0, false, d);
+        __syncthreads();
+        if (out != nullptr)
+            for (int j = threadIdx.x; j < d.Hs; j += blockDim.x)
+                out[k * (int64_t)d.Hs + j] = acc[(pos0 + j) & (N - 1)];
+        if (k + 1 == n_frames) {
+            for (int i = threadIdx.x; i < N; i += blockDim.x) {
+                const float v = acc[(pos0 + i) & (N - 1)];
+                if (back_out != nullptr) back_out[i] = v;
+                if (full_frame_out != nullptr) full_frame_out[i] = v;
+            }
+        }
+        __syncthreads();
+        pos0 = (pos0 + d.Hs) & (N - 1);
+    }
+}
+
+// test_overlap_add (kernel.cu:289-298): the two half swaps cancel.
+__global__ void test_overlap_add_kernel(PvDev d, const float *__restrict__ in,
+                                        const float *__restrict__ back, float *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.N) return;
+    float v = (in[i] * d.win[i]) * d.win[i];
+    if (i + d.Hs < d.N) v += back[i + d.Hs];
+    out[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic fused compat stream kernel: one CTA per frame-range segment
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGenericThreads)
+compat_generic_kernel(PvDev d, PvProcessArgs a)
+{
+    extern __shared__ float2 sm[];
+    const int N = d.N, h = N >> 1;
+    float2 *bufA = sm, *bufB = sm + N;
+    float *acc = reinterpret_cast<float *>(sm + 2 * N);
+    const PvSegment seg = a.segs[blockIdx.x];
+    const float *in = a.in + seg.stream * a.in_stride;
+    float *out = a.out + seg.stream * a.out_stream_stride;
+    float *state = a.state ? a.state + seg.stream * a.state_stride : nullptr;
+
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+        acc[i] = (seg.carry_in && state && i + d.Hs < N) ? state[i + d.Hs] : 0.f;
+    __syncthreads();
+
+    int pos0 = 0;
+    for (int64_t k = seg.k_begin; k < seg.k_end; ++k) {
+        const bool analysed = k < a.n_analysed;
+        const float2 *r = nullptr;
+        if (analysed) {
+            load_frame_compat(bufA, in, k * (int64_t)d.Ha, a.n_in, d);
+            __syncthreads();
+            float2 *C = fft_stockham(bufA, bufB, N, 2, d.tw, false);
+            float2 *Z = (C == bufA) ? bufB : bufA;
+            build_inverse_input(Z, [&](int kk) {
+                return polar_to_rect_d2(mag_phase(split_bin(C, kk, d), d.flags)); }, d);
+            __syncthreads();
+            r = fft_stockham(Z, C, h, 4, d.tw, true);
+        }
+        ola_accumulate(acc, r, pos0, !analysed, d);
+        __syncthreads();
+        if (k >= seg.k_emit)
+            for (int j = threadIdx.x; j < d.Hs; j += blockDim.x)
+                out[k * (int64_t)d.Hs + j] = acc[(pos0 + j) & (N - 1)];
+        if (seg.carry_out && state && k + 1 == seg.k_end)
+            for (int i = threadIdx.x; i < N; i += blockDim.x)
+                state[i] = acc[(pos0 + i) & (N - 1)];
+        __syncthreads();
+        pos0 = (pos0 + d.Hs) & (N - 1);
+    }
+}
+
+}  // namespace
+
+cudaError_t pv_launch_analysis_batch(const PvDev &d, const float *in, int64_t n_in, int64_t n_frames,
+                                     float *out_magphase, cudaStream_t st)
+{
+    if (n_frames <= 0) return cudaSuccess;
+    const size_t smem = sizeof(float2) * 2 * (size_t)d.N;
+    cudaError_t e = cudaFuncSetAttribute(analysis_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    analysis_batch_kernel<<<(unsigned)n_frames, kGenericThreads, smem, st>>>(
+        d, in, n_in, reinterpret_cast<float2 *>(out_magphase));
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_resynth(const PvDev &d, const float *spectra, int64_t n_frames, const float *back_in,
+                                  float *back_out, float *out, float *full, cudaStream_t st)
+{
+    const size_t smem = sizeof(float2) * (size_t)d.N + sizeof(float) * (size_t)d.N;
+    cudaError_t e = cudaFuncSetAttribute(resynthesis_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    resynthesis_batch_kernel<<<1, kGenericThreads, smem, st>>>(d, reinterpret_cast<const float2 *>(spectra), n_frames,
+                                                             back_in, back_out, out, full);
+    return cudaGetLastError();
+}
+
+cudaError_t pv_launch_resynthesis_batch(const PvDev &d, const float *spectra, int64_t n_frames, float *back,
+                                        float *out, cudaStream_t st)
+{
+    if (n_frames <= 0) return cudaSuccess;
+    return launch_resynth(d, spectra, n_frames, back, back, out, nullptr, st);
+}
+
+cudaError_t pv_launch_resynthesis_frame(const PvDev &d, const float *back, const float *front, float *out,
+                                        cudaStream_t st)
+{
+    return launch_resynth(d, front, 1, back, nullptr, nullptr, out, st);
+}
+
+cudaError_t pv_launch_test_overlap_add(const PvDev &d, const float *in, const float *back, float *out,
+                                       cudaStream_t st)
+{
+    test_overlap_add_kernel<<<(d.N + 255) / 256, 256, 0, st>>>(d, in, back, out);
+    return cudaGetLastError();
+}
+
+cudaError_t pv_launch_compat_generic(const PvDev &d, const PvProcessArgs &a, cudaStream_t st)
+{
+    if (a.n_segs <= 0) return cudaSuccess;
+    const size_t smem = sizeof(float2) * 2 * (size_t)d.N + sizeof(float) * (size_t)d.N;
+    cudaError_t e = cudaFuncSetAttribute(compat_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    compat_generic_kernel<<<a.n_segs, kGenericThreads, smem, st>>>(d, a);
+    return cudaGetLastError();
+}

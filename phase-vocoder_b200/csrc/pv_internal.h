@@ -1,0 +1,59 @@
+// pv_internal.h -- shared declarations of the engine (not part of the public ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pv_b200.h"
+
+// Immutable per-handle tables, passed to kernels by value.
+struct PvDev {
+    const float *win;     // N        window (PhaseVocoder::imp)
+    const float2 *tw;     // N        tw[k] = exp(-j*pi*k/N): the 2N-th roots of unity, k < N
+    int N;                // window length
+    int lgN;
+    int Ha, Hs;
+    int flags;
+    float inv_N;
+    // corrected mode
+    int V;
+    float gain;           // Hs / sum(w^2)
+    const uint32_t *nomA; // nb
+    const int32_t *a_lo;  // V*nb
+    const int32_t *a_hi;  // V*nb
+    const uint64_t *nomS; // V*nb
+    uint64_t Rq[PV_MAX_VOICES];
+};
+
+// A frame-range segment of one stream: frames [k_begin, k_end) are computed, frames
+// [k_emit, k_end) are written to the output; k_begin < k_emit are the recomputed OLA halo.
+struct PvSegment {
+    int32_t stream;
+    int32_t carry_in;     // 1: k_begin == 0 and the accumulator starts from the stream state
+    int32_t carry_out;    // 1: this segment holds the last frame and writes the stream state
+    int32_t pad;
+    int64_t k_begin, k_emit, k_end;
+};
+
+struct PvProcessArgs {
+    const float *in;
+    int64_t in_stride, n_in, n_analysed, n_frames;
+    float *out;
+    int64_t out_stream_stride, out_voice_stride;
+    float *state;         // per-stream state (floats), stride state_stride
+    int64_t state_stride;
+    const PvSegment *segs;
+    int32_t n_segs;
+};
+
+// ---- launchers (defined in the .cu files) ----
+cudaError_t pv_launch_analysis_batch(const PvDev &d, const float *in, int64_t n_in, int64_t n_frames,
+                                     float *out_magphase, cudaStream_t st);
+cudaError_t pv_launch_resynthesis_batch(const PvDev &d, const float *spectra, int64_t n_frames,
+                                        float *back, float *out, cudaStream_t st);
+cudaError_t pv_launch_resynthesis_frame(const PvDev &d, const float *back, const float *front, float *out,
+                                        cudaStream_t st);
+cudaError_t pv_launch_test_overlap_add(const PvDev &d, const float *in, const float *back, float *out,
+                                       cudaStream_t st);
+// generic (any N / hop) fused compat path
+cudaError_t pv_launch_compat_generic(const PvDev &d, const PvProcessArgs &a, cudaStream_t st);

@@ -1,0 +1,208 @@
+"""pvb200 -- thin ctypes binding of libpv_b200.so (C ABI: include/pv_b200.h).
+
+Used by the tests and bench.py.  There is no Python or CPU implementation behind it: if the
+CUDA library is missing, or no sm_100 device is present, the calls raise.
+Tensors are torch CUDA tensors (device entry points) or numpy arrays (host entry points);
+torch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_DIR, "libpv_b200.so")
+
+MODE_COMPAT, MODE_CORRECTED = 0, 1
+WIN_HAMMING, WIN_HANN_SYM, WIN_HANN_PERIODIC = 0, 1, 2
+FLAG_NAN_COMPAT = 1
+CARRY_IN, CARRY_OUT = 1, 2
+MAX_VOICES = 8
+
+EXPORTS = [
+    "pv_last_error", "pv_version", "pv_create", "pv_destroy", "pv_get_params", "pv_window_table",
+    "pv_reference_schedule", "pv_analysis", "pv_resynthesis", "pv_test_overlap_add", "pv_analysis_batch",
+    "pv_resynthesis_batch", "pv_state_bytes", "pv_process_device", "pv_process_host", "pv_launch_count",
+    "pv_timing_enable", "pv_timing_read",
+]
+
+
+class PvError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("window", C.c_int32), ("hop_in", C.c_int32), ("hop_out", C.c_int32), ("mode", C.c_int32),
+                ("window_type", C.c_int32), ("n_voices", C.c_int32), ("pitch", C.c_float * MAX_VOICES),
+                ("flags", C.c_int32), ("device", C.c_int32)]
+
+
+_lib = None
+
+
+def load():
+    """Loads libpv_b200.so; raises PvError if it has not been built (no fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PvError(f"{LIB_PATH} is missing: build it with `make -C {_DIR}` (or __graft_entry__.build()); "
+                      "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    L.pv_last_error.restype = C.c_char_p
+    L.pv_version.restype = C.c_char_p
+    L.pv_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    L.pv_destroy.argtypes = [vp]
+    L.pv_destroy.restype = None
+    L.pv_get_params.argtypes = [vp, C.POINTER(Params)]
+    L.pv_window_table.argtypes = [vp, vp]
+    L.pv_reference_schedule.argtypes = [vp, i64, C.POINTER(i64), C.POINTER(i64)]
+    L.pv_analysis.argtypes = [vp, vp, vp]
+    L.pv_resynthesis.argtypes = [vp, vp, vp, vp]
+    L.pv_test_overlap_add.argtypes = [vp, vp, vp, vp]
+    L.pv_analysis_batch.argtypes = [vp, vp, i64, i64, vp, vp]
+    L.pv_resynthesis_batch.argtypes = [vp, vp, i64, vp, vp, vp]
+    L.pv_state_bytes.argtypes = [vp]
+    L.pv_state_bytes.restype = C.c_size_t
+    L.pv_process_device.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, i64, i64, vp, i32, vp]
+    L.pv_process_host.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, i64, i64, vp, i32]
+    L.pv_launch_count.argtypes = [vp]
+    L.pv_launch_count.restype = i64
+    L.pv_timing_enable.argtypes = [vp, i32]
+    L.pv_timing_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise PvError(f"pv_b200 error {rc}: {load().pv_last_error().decode()}")
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+def _cuda_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+class PhaseVocoder:
+    """Host-side mirror of the reference's `class PhaseVocoder` (src/phaseVocoder.h:9-139) over the
+    C ABI.  `PhaseVocoder(samples, effect, scale, hop)` keeps the reference meaning: window =
+    samples, hopSize = samples // hop (:79), outHopSize = int(scale * hopSize) (:104).  Explicit
+    hop_in / hop_out override that derivation (the golden 1000hzout.wav needs Ha=1, Hs=128)."""
+
+    def __init__(self, samples, effect="t", scale=1.0, hop=2, *, hop_in=None, hop_out=None, mode=MODE_COMPAT,
+                 window_type=WIN_HAMMING, pitch=(1.0,), flags=0, device=-1):
+        self.nSamps = int(samples)
+        self.hopSize = int(samples) // int(hop) if hop_in is None else int(hop_in)
+        self.timeScale = float(scale)
+        self.outHopSize = int(float(scale) * self.hopSize) if hop_out is None else int(hop_out)
+        self.effect = effect
+        p = Params()
+        p.window, p.hop_in, p.hop_out = self.nSamps, self.hopSize, self.outHopSize
+        p.mode, p.window_type, p.flags, p.device = mode, window_type, flags, device
+        p.n_voices = len(pitch) if mode == MODE_CORRECTED else 1
+        for i, b in enumerate(pitch[:MAX_VOICES]):
+            p.pitch[i] = float(b)
+        self.mode, self.n_voices = mode, p.n_voices
+        self._h = C.c_void_p()
+        _check(load().pv_create(C.byref(p), C.byref(self._h)))
+        self.imp = np.empty(self.nSamps, np.float32)        # the window table, as PhaseVocoder::imp
+        _check(load().pv_window_table(self._h, self.imp.ctypes.data))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            load().pv_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    # ---- reference granularity (device tensors) ----
+    def analysis_CUFFT(self, input, output):
+        """PhaseVocoder::analysis_CUFFT (src/phaseVocoder.cpp:25-33): input[N] -> output[2N,2]."""
+        _check(load().pv_analysis(self._h, _ptr(input), _ptr(output)))
+
+    analysis = analysis_CUFFT
+
+    def resynthesis_CUFFT(self, backFrame, frontFrame, output):
+        """PhaseVocoder::resynthesis_CUFFT (src/phaseVocoder.cpp:60-76)."""
+        _check(load().pv_resynthesis(self._h, _ptr(backFrame), _ptr(frontFrame), _ptr(output)))
+
+    resynthesis = resynthesis_CUFFT
+
+    def test_overlap_add(self, input, back, output):
+        _check(load().pv_test_overlap_add(self._h, _ptr(input), _ptr(back), _ptr(output)))
+
+    # ---- batched ----
+    def reference_schedule(self, num_samples):
+        na, ns = C.c_int64(), C.c_int64()
+        _check(load().pv_reference_schedule(self._h, num_samples, C.byref(na), C.byref(ns)))
+        return na.value, ns.value
+
+    def analysis_batch(self, x, n_frames, out=None):
+        import torch
+        N = self.nSamps
+        if out is None:
+            out = torch.empty((n_frames, 2 * N, 2), dtype=torch.float32, device=x.device)
+        _check(load().pv_analysis_batch(self._h, _ptr(x), x.numel(), n_frames, _ptr(out), _cuda_stream()))
+        return out
+
+    def resynthesis_batch(self, spectra, back, out=None):
+        import torch
+        n_frames = spectra.shape[0]
+        if out is None:
+            out = torch.empty(n_frames * self.outHopSize, dtype=torch.float32, device=spectra.device)
+        _check(load().pv_resynthesis_batch(self._h, _ptr(spectra), n_frames, _ptr(back), _ptr(out), _cuda_stream()))
+        return out
+
+    def state_bytes(self):
+        return load().pv_state_bytes(self._h)
+
+    def process(self, x, n_frames, n_analysed=None, out=None, state=None, flags=0):
+        """Fused hot path on device tensors.  x: [streams, n_in] float32 CUDA -> out [streams, V, n_frames*Hs]."""
+        import torch
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+        S, n_in = x.shape
+        n_out = n_frames * self.outHopSize
+        if out is None:
+            out = torch.empty((S, self.n_voices, n_out), dtype=torch.float32, device=x.device)
+        na = n_frames if n_analysed is None else n_analysed
+        _check(load().pv_process_device(self._h, _ptr(x), S, x.stride(0), n_in, na, n_frames, _ptr(out),
+                                        out.stride(0), out.stride(1), _ptr(state), flags, _cuda_stream()))
+        return out
+
+    def process_host(self, x, n_frames, n_analysed=None, out=None, state=None, flags=0):
+        """Same through host buffers (numpy arrays or pinned CPU torch tensors): H2D + kernel + D2H."""
+        S, n_in = x.shape
+        n_out = n_frames * self.outHopSize
+        if out is None:
+            out = np.empty((S, self.n_voices, n_out), np.float32)
+        na = n_frames if n_analysed is None else n_analysed
+        if isinstance(x, np.ndarray):
+            in_stride, os_, ov = x.strides[0] // 4, out.strides[0] // 4, out.strides[1] // 4
+        else:
+            in_stride, os_, ov = x.stride(0), out.stride(0), out.stride(1)
+        _check(load().pv_process_host(self._h, _ptr(x), S, in_stride, n_in, na, n_frames, _ptr(out), os_, ov,
+                                      _ptr(state), flags))
+        return out
+
+    def launch_count(self):
+        return load().pv_launch_count(self._h)
+
+    def timing(self, on=True):
+        _check(load().pv_timing_enable(self._h, 1 if on else 0))
+
+    def timing_read(self):
+        ms, n = C.c_double(), C.c_int64()
+        _check(load().pv_timing_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
