@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "pv_internal.h"
+#include "pv_fused_tables.h"
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
@@ -28,6 +29,11 @@ struct pv_handle {
     int32_t *d_alo = nullptr, *d_ahi = nullptr;
     uint64_t *d_nomS = nullptr;
     std::vector<float> h_win;
+    // fused-kernel tables
+    bool fused = false;
+    int capacity = 0;
+    PvFusedTables ft;
+    float2 *d_ft[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     // segment plan cache
     PvSegment *d_segs = nullptr;
     size_t segs_cap = 0;
@@ -139,11 +145,13 @@ int plan_segments(pv_handle *h, int64_t n_streams, int64_t n_frames, int32_t fla
     if (h->plan_streams == n_streams && h->plan_frames == n_frames && h->plan_flags == flags) return PV_OK;
     const int N = h->p.window, Hs = h->p.hop_out;
     const int64_t halo = (N - 1) / Hs;                     // frames k' < k that still overlap frame k
-    const int64_t target = (int64_t)h->sm_count * 8;
+    // aim at ~8 waves of resident groups so that the tail wave is small, but keep the halo
+    // recompute below ~3 % of a segment
+    const int64_t target = (int64_t)h->capacity * 8;
     int64_t per_stream = (target + n_streams - 1) / n_streams;
     if (per_stream < 1) per_stream = 1;
     int64_t seg_len = (n_frames + per_stream - 1) / per_stream;
-    const int64_t min_len = std::max<int64_t>(8 * halo, 8);
+    const int64_t min_len = std::max<int64_t>(32 * halo, 32);
     if (seg_len < min_len) seg_len = min_len;
     std::vector<PvSegment> segs;
     for (int64_t s = 0; s < n_streams; s++) {
@@ -268,6 +276,20 @@ int pv_create(const pv_params *params, pv_handle **out)
         if (rc == PV_OK) rc = upload(&h->d_ahi, ahi);
         if (rc == PV_OK) rc = upload(&h->d_nomS, nomS);
     }
+    h->capacity = h->sm_count * 8;
+    if (rc == PV_OK && p.mode == PV_MODE_COMPAT && pv_fused_compat_supported(N, p.hop_out)) {
+        HostTables ht;
+        build_tables(d.lgN, ht);
+        const std::vector<float2> *src[5] = {&ht.tw1, &ht.tw2, &ht.tw2n, &ht.itw1, &ht.itw2};
+        for (int i = 0; i < 5 && rc == PV_OK; i++) rc = upload(&h->d_ft[i], *src[i]);
+        h->ft.tw1 = h->d_ft[0];
+        h->ft.tw2 = h->d_ft[1];
+        h->ft.tw2n = h->d_ft[2];
+        h->ft.itw1 = h->d_ft[3];
+        h->ft.itw2 = h->d_ft[4];
+        h->fused = rc == PV_OK;
+        if (h->fused) h->capacity = pv_fused_compat_capacity(N, h->sm_count);
+    }
     if (rc != PV_OK) {
         pv_destroy(h);
         return rc;
@@ -292,6 +314,7 @@ void pv_destroy(pv_handle *h)
     cudaFree(h->d_alo);
     cudaFree(h->d_ahi);
     cudaFree(h->d_nomS);
+    for (auto p : h->d_ft) cudaFree(p);
     cudaFree(h->d_segs);
     cudaFree(h->d_in);
     cudaFree(h->d_out);
@@ -437,7 +460,8 @@ int pv_process_device(pv_handle *h, const float *in, int64_t n_streams, int64_t 
         PV_CUDA(cudaEventCreate(&e1));
         PV_CUDA(cudaEventRecord(e0, st));
     }
-    PV_CUDA(pv_launch_compat_generic(h->dev, a, st));
+    if (h->fused && !getenv("PV_FORCE_GENERIC")) PV_CUDA(pv_launch_compat_fused(h->dev, h->ft, a, st));
+    else PV_CUDA(pv_launch_compat_generic(h->dev, a, st));
     h->launches++;
     if (h->timing) {
         PV_CUDA(cudaEventRecord(e1, st));

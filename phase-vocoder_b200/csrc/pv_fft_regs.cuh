@@ -1,0 +1,109 @@
+// pv_fft_regs.cuh -- register-resident radix-2/4/8/16 DFTs and complex helpers.
+//
+// Compiles as CUDA device code and, with PV_HOST_EMUL defined, as plain C++ so that the
+// fused kernel's index algebra can be executed on the CPU by tests/emul (one std::thread per
+// CUDA thread, std::barrier for __syncthreads).  The emulation is a TEST harness: the product
+// only ever runs the CUDA build.
+#pragma once
+
+#ifdef PV_HOST_EMUL
+#include <cmath>
+#include <cstdint>
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+#define PV_DEV inline
+#define PV_LDG(p) (*(p))
+#else
+#include <cuda_runtime.h>
+#define PV_DEV __device__ __forceinline__
+#define PV_LDG(p) __ldg(p)
+#endif
+
+namespace pvfft {
+
+PV_DEV float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+PV_DEV float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+PV_DEV float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+PV_DEV float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+// a * (+j) and a * (-j)
+PV_DEV float2 mul_pj(float2 a) { return make_float2(-a.y, a.x); }
+PV_DEV float2 mul_mj(float2 a) { return make_float2(a.y, -a.x); }
+
+// a * exp(DIR * j * 2*pi * K / 16), K and DIR compile-time (DIR = -1 forward, +1 inverse)
+template <int K, int DIR>
+PV_DEV float2 twid16(float2 a)
+{
+    constexpr int k = ((K % 16) + 16) % 16;
+    constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
+    if constexpr (k == 0) return a;
+    else if constexpr (k == 4) return DIR > 0 ? mul_pj(a) : mul_mj(a);
+    else if constexpr (k == 8) return make_float2(-a.x, -a.y);
+    else if constexpr (k == 12) return DIR > 0 ? mul_mj(a) : mul_pj(a);
+    else {
+        // general: (c + j*DIR*s) with c = cos(2 pi k/16), s = sin(2 pi k/16)
+        constexpr float c = (k == 1 || k == 15) ? C1 : (k == 2 || k == 14) ? H : (k == 3 || k == 13) ? S1
+                          : (k == 5 || k == 11) ? -S1 : (k == 6 || k == 10) ? -H : -C1;   // k == 7, 9
+        constexpr float sa = (k == 1 || k == 7) ? S1 : (k == 2 || k == 6) ? H : (k == 3 || k == 5) ? C1
+                           : (k == 9 || k == 15) ? -S1 : (k == 10 || k == 14) ? -H : -C1;  // k == 11, 13
+        constexpr float s = DIR > 0 ? sa : -sa;
+        return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
+    }
+}
+
+template <int DIR>
+PV_DEV void dft2(float2 &a, float2 &b)
+{
+    const float2 t = csub(a, b);
+    a = cadd(a, b);
+    b = t;
+}
+
+// natural order in, natural order out
+template <int DIR>
+PV_DEV void dft4(float2 &v0, float2 &v1, float2 &v2, float2 &v3)
+{
+    const float2 t0 = cadd(v0, v2), t1 = csub(v0, v2), t2 = cadd(v1, v3);
+    const float2 d = csub(v1, v3);
+    const float2 t3 = DIR > 0 ? mul_pj(d) : mul_mj(d);
+    v0 = cadd(t0, t2);
+    v2 = csub(t0, t2);
+    v1 = cadd(t1, t3);
+    v3 = csub(t1, t3);
+}
+
+template <int DIR>
+PV_DEV void dft8(float2 &v0, float2 &v1, float2 &v2, float2 &v3, float2 &v4, float2 &v5, float2 &v6, float2 &v7)
+{
+    dft4<DIR>(v0, v2, v4, v6);      // even samples -> e0..e3 in (v0, v2, v4, v6)
+    dft4<DIR>(v1, v3, v5, v7);      // odd samples  -> o0..o3 in (v1, v3, v5, v7)
+    const float2 o1 = twid16<2, DIR>(v3), o2 = twid16<4, DIR>(v5), o3 = twid16<6, DIR>(v7);
+    const float2 e0 = v0, e1 = v2, e2 = v4, e3 = v6, o0 = v1;
+    v0 = cadd(e0, o0); v4 = csub(e0, o0);
+    v1 = cadd(e1, o1); v5 = csub(e1, o1);
+    v2 = cadd(e2, o2); v6 = csub(e2, o2);
+    v3 = cadd(e3, o3); v7 = csub(e3, o3);
+}
+
+template <int R, int DIR>
+PV_DEV void dft(float2 (&v)[R])
+{
+    static_assert(R == 2 || R == 4 || R == 8 || R == 16, "radix");
+    if constexpr (R == 2) dft2<DIR>(v[0], v[1]);
+    else if constexpr (R == 4) dft4<DIR>(v[0], v[1], v[2], v[3]);
+    else if constexpr (R == 8) dft8<DIR>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+    else {
+        dft8<DIR>(v[0], v[2], v[4], v[6], v[8], v[10], v[12], v[14]);    // e_k in v[2k]
+        dft8<DIR>(v[1], v[3], v[5], v[7], v[9], v[11], v[13], v[15]);    // o_k in v[2k+1]
+        float2 e[8], o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { e[k] = v[2 * k]; o[k] = v[2 * k + 1]; }
+        o[1] = twid16<1, DIR>(o[1]); o[2] = twid16<2, DIR>(o[2]); o[3] = twid16<3, DIR>(o[3]);
+        o[4] = twid16<4, DIR>(o[4]); o[5] = twid16<5, DIR>(o[5]); o[6] = twid16<6, DIR>(o[6]);
+        o[7] = twid16<7, DIR>(o[7]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) { v[k] = cadd(e[k], o[k]); v[k + 8] = csub(e[k], o[k]); }
+    }
+}
+
+}  // namespace pvfft

@@ -1,0 +1,305 @@
+// pv_fused_core.cuh -- per-frame body of the fused kernels (compat mode), register blocked.
+//
+// One thread group of T = N/16 threads walks the frames of a segment.  Per frame:
+//
+//   fwd pass 1   radix-R1 over n1        inputs straight from global memory (window, zero-phase
+//                                        shift and zero pad folded into the load index)
+//   exchange 1   shared memory (padded, conflict free)
+//   fwd pass 2   radix-R2 over n2
+//   exchange 2
+//   fwd pass 3   radix-8 over n3, butterflies t3 = u and t3 = B3-u in the SAME thread, so that the
+//                conjugate partners C[k], C[N-k] sit in one thread's registers
+//   middle       real-FFT split, step D+E of the reference (collapsed: re'=|Re X|, im'=Re X Im X/|X|),
+//                Hermitian pack of the N-point C2R -- all in registers, no shared memory
+//   inv pass 1   radix-4 over the four packed values per butterfly, in registers
+//   exchange 3
+//   inv pass 2   radix-R1
+//   exchange 4
+//   inv pass 3   radix-R2 -> time samples; /N, half swap, window, overlap-add into the ring
+//
+// Index algebra (M = N complex points forward, M' = N/2 inverse, B3 = N/8 = 2T):
+//   forward  n = n1*S1 + n2*8 + n3          k = k1 + R1*k2 + B3*k3        S1 = N/R1 = R2*8
+//   inverse  kappa = n1*B3 + n2*R2 + n3     n = m1 + 4*m2 + 4*R1*m3       (B3 = R1*R2)
+#pragma once
+#include "pv_fft_regs.cuh"
+
+namespace pvfused {
+using namespace pvfft;
+
+template <int LOG2N>
+struct Shape {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int T = N / 16;              // threads per frame group
+    static constexpr int B3 = N / 8;              // butterflies of the last forward pass (= 2T)
+    static constexpr int R1 = (LOG2N >= 10) ? 16 : 8;
+    static constexpr int R2 = B3 / R1;            // 2048:16 1024:8 512:8 256:4
+    static constexpr int S1 = N / R1;             // = R2*8
+    static constexpr int PAD1 = 16 / R1;          // exchange-1 row padding (float2 units)
+    static constexpr int LD1 = S1 + PAD1;
+    static constexpr int LD2 = 9;                 // exchange-2: t3*9 + n3
+    static constexpr int EX1 = R1 * LD1;          // float2 elements
+    static constexpr int EX2 = B3 * LD2;
+    // inverse: M' = 4*B3, B3 = R1*R2
+    static constexpr int ILD1 = B3 + (R2 < 16 ? R2 : 0);   // exchange-3 rows (m1): m1*ILD1 + t1
+    static constexpr int IEX1 = 4 * ILD1;
+    static constexpr int ILD2 = R2 + 1;           // exchange-4: (m1 + 4*m2)*(R2+1) + n3
+    static constexpr int IEX2 = 4 * R1 * ILD2;
+    static constexpr int BUF_A = (EX1 > IEX1 ? EX1 : IEX1);     // exchanges 1 and 3
+    static constexpr int BUF_B = (EX2 > IEX2 ? EX2 : IEX2);     // exchanges 2 and 4
+    static_assert(R1 * R2 == B3 && R2 >= 4, "shape");
+};
+
+// Twiddle tables in global memory (built on the host in double precision).
+struct Tables {
+    const float2 *tw1;    // [(R1-1)][S1]   W_N^{k1*t1}
+    const float2 *tw2;    // [(R2-1)][8]    W_S1^{k2*n3}
+    const float2 *tw2n;   // [N]            exp(-j*pi*k/N) (2N-th roots) for the split / pack steps
+    const float2 *itw1;   // [3][B3]        exp(+2 pi i m1 t1 / (N/2))
+    const float2 *itw2;   // [(R1-1)][R2]   exp(+2 pi i m2 n3 / B3)
+    const float *win;     // [N]
+};
+
+struct FrameIO {
+    const float *in;      // stream base
+    long long n_in;       // valid samples in the stream
+    long long base;       // first sample of this frame (k*Ha)
+    bool analysed;        // false: zero spectrum (never analysed frame)
+    bool vec_ok;          // 8-byte aligned float2 loads are legal for this stream
+};
+
+// Loads x[base+i], x[base+i+1] (zero beyond n_in) times the window.
+PV_DEV float2 load_pair(const FrameIO &io, const float *win, int i)
+{
+    const long long g = io.base + i;
+    float x0, x1;
+    if (io.vec_ok && g + 1 < io.n_in) {
+        const float2 v = PV_LDG(reinterpret_cast<const float2 *>(io.in + g));
+        x0 = v.x; x1 = v.y;
+    } else {
+        x0 = (g < io.n_in) ? PV_LDG(io.in + g) : 0.f;
+        x1 = (g + 1 < io.n_in) ? PV_LDG(io.in + g + 1) : 0.f;
+    }
+    const float2 w = PV_LDG(reinterpret_cast<const float2 *>(win + i));
+    return make_float2(x0 * w.x, x1 * w.y);
+}
+
+// ---- forward passes 1 and 2 (results left in bufB for pass 3) ----
+template <int LOG2N, class Sync>
+PV_DEV void forward_12(int tid, const FrameIO &io, const Tables &tb, float2 *bufA, float2 *bufB, Sync sync)
+{
+    using S = Shape<LOG2N>;
+    constexpr int N = S::N, T = S::T, R1 = S::R1, R2 = S::R2, S1 = S::S1;
+    // pass 1: butterflies t1 in [0, S1)
+#pragma unroll
+    for (int t1 = tid; t1 < S1; t1 += T) {
+        float2 v[R1];
+#pragma unroll
+        for (int n1 = 0; n1 < R1; n1++) {
+            // c[n], n = n1*S1 + t1: n < N/4 -> f[N/2 + 2n]; n >= 3N/4 -> f[2(n - 3N/4)]; else 0
+            if (n1 < R1 / 4) v[n1] = load_pair(io, tb.win, N / 2 + 2 * (n1 * S1 + t1));
+            else if (n1 >= 3 * R1 / 4) v[n1] = load_pair(io, tb.win, 2 * ((n1 - 3 * R1 / 4) * S1 + t1));
+            else v[n1] = make_float2(0.f, 0.f);
+        }
+        dft<R1, -1>(v);
+        bufA[t1] = v[0];
+#pragma unroll
+        for (int k1 = 1; k1 < R1; k1++)
+            bufA[k1 * S::LD1 + t1] = cmul(v[k1], PV_LDG(tb.tw1 + (k1 - 1) * S1 + t1));
+    }
+    sync();
+    // pass 2: butterflies (k1, n3), k1 fastest across threads
+#pragma unroll
+    for (int b = tid; b < R1 * 8; b += T) {
+        const int k1 = b % R1, n3 = b / R1;
+        float2 v[R2];
+#pragma unroll
+        for (int n2 = 0; n2 < R2; n2++) v[n2] = bufA[k1 * S::LD1 + n2 * 8 + n3];
+        dft<R2, -1>(v);
+        bufB[k1 * S::LD2 + n3] = v[0];
+#pragma unroll
+        for (int k2 = 1; k2 < R2; k2++)
+            bufB[(k1 + R1 * k2) * S::LD2 + n3] = cmul(v[k2], PV_LDG(tb.tw2 + (k2 - 1) * 8 + n3));
+    }
+    sync();
+}
+
+// ---- forward pass 3 for the butterfly pair of thread u: P[j] = C[tP + B3*j], Q[j] = C[tQ + B3*j] ----
+template <int LOG2N>
+PV_DEV void forward_3(int u, const float2 *bufB, float2 (&P)[8], float2 (&Q)[8])
+{
+    using S = Shape<LOG2N>;
+    const int tP = u, tQ = (u == 0) ? S::B3 / 2 : S::B3 - u;
+#pragma unroll
+    for (int n3 = 0; n3 < 8; n3++) {
+        P[n3] = bufB[tP * S::LD2 + n3];
+        Q[n3] = bufB[tQ * S::LD2 + n3];
+    }
+    dft<8, -1>(P);
+    dft<8, -1>(Q);
+}
+
+// X[k] of the 2N-point real spectrum from a = C[k], b = C[N-k], w = exp(-j*pi*k/N)
+PV_DEV float2 split(float2 a, float2 b, float2 w)
+{
+    const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+    const float2 o = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));   // (a - conj b)/(2j)
+    return cadd(e, cmul(w, o));
+}
+
+// steps D+E of the reference collapsed algebraically: re' = |Re X|, im' = Re X Im X/|X|
+PV_DEV float2 compat_map(float2 X, bool nan_compat)
+{
+    const float m2 = X.x * X.x + X.y * X.y;
+    if (m2 == 0.f) {
+        const float z = nan_compat ? __builtin_nanf("") : 0.f;   // atanf(0/0) of kernel.cu:108
+        return make_float2(z, z);
+    }
+#ifdef PV_HOST_EMUL
+    const float r = 1.0f / sqrtf(m2);
+#else
+    const float r = rsqrtf(m2);
+#endif
+    return make_float2(fabsf(X.x), X.x * X.y * r);
+}
+
+// Z[k] = (Yk + conj(Ym)) + j*w*(Yk - conj(Ym)), w = exp(+2 pi i k/N), Ym = Y[N/2 - k]
+PV_DEV float2 herm_pack(float2 yk, float2 ym, float2 w)
+{
+    const float2 s = make_float2(yk.x + ym.x, yk.y - ym.y);
+    const float2 d = make_float2(yk.x - ym.x, yk.y + ym.y);
+    const float2 t = cmul(w, d);
+    return make_float2(s.x - t.y, s.y + t.x);
+}
+
+// ---- middle: P,Q (16 transform outputs) -> Zp[4], Zq[4] = packed inverse inputs at
+//      kappa = tP + B3*n1 and tQ + B3*n1 ----
+template <int LOG2N>
+PV_DEV void middle_compat(int u, const Tables &tb, bool nan_compat, const float2 (&P)[8], const float2 (&Q)[8],
+                          float2 (&Zp)[4], float2 (&Zq)[4])
+{
+    using S = Shape<LOG2N>;
+    constexpr int N = S::N, B3 = S::B3;
+    float2 Yp[5], Yq[4];
+    if (u != 0) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int kp = u + B3 * j, kq = (B3 - u) + B3 * j;
+            Yp[j] = compat_map(split(P[j], Q[7 - j], PV_LDG(tb.tw2n + kp)), nan_compat);
+            Yq[j] = compat_map(split(Q[j], P[7 - j], PV_LDG(tb.tw2n + kq)), nan_compat);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int kp = u + B3 * j, kq = (B3 - u) + B3 * j;
+            Zp[j] = herm_pack(Yp[j], Yq[3 - j], cconj(PV_LDG(tb.tw2n + 2 * kp)));
+            Zq[j] = herm_pack(Yq[j], Yp[3 - j], cconj(PV_LDG(tb.tw2n + 2 * kq)));
+        }
+    } else {
+        // thread 0 owns the self-paired columns t3 = 0 (bins 0, B3, .., 4*B3 = N/2) and t3 = B3/2
+#pragma unroll
+        for (int j = 0; j < 5; j++)
+            Yp[j] = compat_map(split(P[j], P[(8 - j) & 7], PV_LDG(tb.tw2n + B3 * j)), nan_compat);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            Yq[j] = compat_map(split(Q[j], Q[7 - j], PV_LDG(tb.tw2n + B3 / 2 + B3 * j)), nan_compat);
+        Yp[0].y = 0.f;          // C2R ignores Im of bins 0 and N/2 (cuFFT, kernel.cu:366)
+        Yp[4].y = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float2 wp = (j == 0) ? make_float2(1.f, 0.f) : cconj(PV_LDG(tb.tw2n + 2 * B3 * j));
+            Zp[j] = herm_pack(Yp[j], Yp[4 - j], wp);
+            Zq[j] = herm_pack(Yq[j], Yq[3 - j], cconj(PV_LDG(tb.tw2n + B3 + 2 * B3 * j)));
+        }
+    }
+    (void)N;
+}
+
+// ---- inverse pass 1 (radix 4 in registers) for one butterfly column t1, writes exchange 3 ----
+template <int LOG2N>
+PV_DEV void inverse_1(int t1, const Tables &tb, float2 (&Z)[4], float2 *bufA)
+{
+    using S = Shape<LOG2N>;
+    dft<4, +1>(Z);
+    bufA[t1] = Z[0];
+#pragma unroll
+    for (int m1 = 1; m1 < 4; m1++)
+        bufA[m1 * S::ILD1 + t1] = cmul(Z[m1], PV_LDG(tb.itw1 + (m1 - 1) * S::B3 + t1));
+}
+
+// ---- inverse passes 2 and 3 + steps G/H (scale, half swap, window, overlap-add) ----
+// acc: OLA ring of N floats, pos0: ring position of sample 0 of this frame.
+template <int LOG2N, class Sync>
+PV_DEV void inverse_23_ola(int tid, const Tables &tb, float2 *bufA, float2 *bufB, float *acc, int pos0, int Hs,
+                           bool zero_frame, Sync sync)
+{
+    using S = Shape<LOG2N>;
+    constexpr int N = S::N, T = S::T, R1 = S::R1, R2 = S::R2, B3 = S::B3;
+    constexpr int C2 = 4 * R2;       // pass-2 butterflies (m1, n3), radix R1
+    constexpr int C3 = 4 * R1;       // pass-3 butterflies (m1, m2), radix R2
+    if (!zero_frame) {
+        sync();
+        // pass 2: when there are fewer butterflies than threads, the low threads take it
+#pragma unroll
+        for (int b = tid; b < C2; b += T) {
+            const int n3 = b % R2, m1 = b / R2;         // n3 fastest: conflict-free on both sides
+            float2 v[R1];
+#pragma unroll
+            for (int n2 = 0; n2 < R1; n2++) v[n2] = bufA[m1 * S::ILD1 + n2 * R2 + n3];
+            dft<R1, +1>(v);
+            bufB[m1 * S::ILD2 + n3] = v[0];
+#pragma unroll
+            for (int m2 = 1; m2 < R1; m2++)
+                bufB[(m1 + 4 * m2) * S::ILD2 + n3] = cmul(v[m2], PV_LDG(tb.itw2 + (m2 - 1) * R2 + n3));
+        }
+        sync();
+    }
+    // pass 3 (high threads first when C3 < T, to balance the warps against pass 2)
+    constexpr int OFF3 = (C3 < T) ? (T - C3) : 0;
+    const int keep = N - Hs;
+#pragma unroll
+    for (int b0 = tid - OFF3; b0 < C3; b0 += T) {
+        if (b0 < 0) break;
+        const int b = b0;
+        float2 v[R2];
+        if (!zero_frame) {
+#pragma unroll
+            for (int n3 = 0; n3 < R2; n3++) v[n3] = bufB[b * S::ILD2 + n3];
+            dft<R2, +1>(v);
+        } else {
+#pragma unroll
+            for (int n3 = 0; n3 < R2; n3++) v[n3] = make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int m3 = 0; m3 < R2; m3++) {
+            const int n = b + C3 * m3;                     // complex output index: samples 2n, 2n+1
+            const int i = (2 * n + N / 2) & (N - 1);       // half swap (kernel.cu:51-59)
+            const float2 w = PV_LDG(reinterpret_cast<const float2 *>(tb.win + i));
+            const float y0 = (v[m3].x / (float)N) * w.x;   // cudaDivVec kernel.cu:130-138, cudaWindow :75-81
+            const float y1 = (v[m3].y / (float)N) * w.y;
+            float2 *slot = reinterpret_cast<float2 *>(acc + ((pos0 + i) & (N - 1)));
+            float2 a = *slot;
+            a.x = (i < keep ? a.x : 0.f) + y0;             // cudaOverlapAdd kernel.cu:111-119
+            a.y = (i + 1 < keep ? a.y : 0.f) + y1;
+            *slot = a;
+        }
+    }
+    (void)B3;
+}
+
+// ---- one whole frame ----
+template <int LOG2N, class Sync>
+PV_DEV void frame_compat(int tid, const FrameIO &io, const Tables &tb, bool nan_compat, float2 *bufA, float2 *bufB,
+                         float *acc, int pos0, int Hs, Sync sync)
+{
+    using S = Shape<LOG2N>;
+    if (io.analysed) {
+        forward_12<LOG2N>(tid, io, tb, bufA, bufB, sync);
+        float2 P[8], Q[8], Zp[4], Zq[4];
+        forward_3<LOG2N>(tid, bufB, P, Q);
+        middle_compat<LOG2N>(tid, tb, nan_compat, P, Q, Zp, Zq);
+        inverse_1<LOG2N>(tid, tb, Zp, bufA);
+        inverse_1<LOG2N>(tid == 0 ? S::B3 / 2 : S::B3 - tid, tb, Zq, bufA);
+    }
+    inverse_23_ola<LOG2N>(tid, tb, bufA, bufB, acc, pos0, Hs, !io.analysed, sync);
+}
+
+}  // namespace pvfused

@@ -1,0 +1,43 @@
+// pv_fused_tables.h -- host-side construction of the twiddle tables of the fused kernels
+// (double precision, rounded once to float).  Plain C++: shared by pv_capi.cu and the CPU
+// emulation harness in tests/emul.
+#pragma once
+#include <cmath>
+#include <vector>
+
+#ifndef PV_HOST_EMUL
+#include <cuda_runtime.h>
+#endif
+
+struct HostTables {
+    std::vector<float2> tw1, tw2, tw2n, itw1, itw2;
+};
+
+inline float2 pv_cis(double turns)   // exp(j * 2*pi * turns)
+{
+    const double a = 2.0 * 3.14159265358979323846 * turns;
+    float2 r;
+    r.x = (float)cos(a);
+    r.y = (float)sin(a);
+    return r;
+}
+
+// Shapes must match pvfused::Shape<LOG2N> (pv_fused_core.cuh).
+inline void build_tables(int log2n, HostTables &t)
+{
+    const int N = 1 << log2n, B3 = N / 8, R1 = (log2n >= 10) ? 16 : 8, R2 = B3 / R1, S1 = N / R1;
+    t.tw1.resize((size_t)(R1 - 1) * S1);
+    for (int k1 = 1; k1 < R1; k1++)
+        for (int t1 = 0; t1 < S1; t1++) t.tw1[(size_t)(k1 - 1) * S1 + t1] = pv_cis(-(double)((long)k1 * t1 % N) / N);
+    t.tw2.resize((size_t)(R2 - 1) * 8);
+    for (int k2 = 1; k2 < R2; k2++)
+        for (int n3 = 0; n3 < 8; n3++) t.tw2[(size_t)(k2 - 1) * 8 + n3] = pv_cis(-(double)(k2 * n3) / S1);
+    t.tw2n.resize(N);
+    for (int k = 0; k < N; k++) t.tw2n[k] = pv_cis(-(double)k / (2.0 * N));
+    t.itw1.resize((size_t)3 * B3);
+    for (int m1 = 1; m1 < 4; m1++)
+        for (int t1 = 0; t1 < B3; t1++) t.itw1[(size_t)(m1 - 1) * B3 + t1] = pv_cis((double)(m1 * t1) / (N / 2));
+    t.itw2.resize((size_t)(R1 - 1) * R2);
+    for (int m2 = 1; m2 < R1; m2++)
+        for (int n3 = 0; n3 < R2; n3++) t.itw2[(size_t)(m2 - 1) * R2 + n3] = pv_cis((double)(m2 * n3) / B3);
+}

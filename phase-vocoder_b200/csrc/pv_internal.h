@@ -46,7 +46,16 @@ struct PvProcessArgs {
     int32_t n_segs;
 };
 
+// Device copies of the fused kernels' twiddle tables (pv_fused_tables.h).
+struct PvFusedTables {
+    const float2 *tw1 = nullptr, *tw2 = nullptr, *tw2n = nullptr, *itw1 = nullptr, *itw2 = nullptr;
+};
+
 // ---- launchers (defined in the .cu files) ----
+bool pv_fused_compat_supported(int N, int Hs);
+// number of segment groups that can be resident on the device at once
+int pv_fused_compat_capacity(int N, int sm_count);
+cudaError_t pv_launch_compat_fused(const PvDev &d, const PvFusedTables &t, const PvProcessArgs &a, cudaStream_t st);
 cudaError_t pv_launch_analysis_batch(const PvDev &d, const float *in, int64_t n_in, int64_t n_frames,
                                      float *out_magphase, cudaStream_t st);
 cudaError_t pv_launch_resynthesis_batch(const PvDev &d, const float *spectra, int64_t n_frames,

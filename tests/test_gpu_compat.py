@@ -216,3 +216,27 @@ def test_bad_parameters_are_rejected():
     for kw in (dict(samples=100), dict(samples=8192), dict(samples=256, hop_out=512), dict(samples=256, hop_in=0)):
         with pytest.raises(pvb200.PvError):
             pvb200.PhaseVocoder(**kw)
+
+
+@pytest.mark.parametrize("N,Ha,Hs,nf", [(2048, 512, 512, 64), (256, 64, 64, 200), (1024, 102, 512, 40)])
+def test_generic_kernel_still_matches(monkeypatch, N, Ha, Hs, nf):
+    """The shape-generic stream kernel (used for windows / hops the tuned kernels do not cover)."""
+    monkeypatch.setenv("PV_FORCE_GENERIC", "1")
+    x = multitone(N + nf * Ha, seed=5)
+    pv = make(N, Ha, Hs)
+    got = pv.process(dev(x)[None, :], nf).cpu().numpy()[0, 0]
+    want, _ = po.process_compat(x, N, Ha, Hs, pv.imp, nf, nf)
+    assert snr_db(want, got) > 100
+
+
+def test_many_streams_and_odd_strides():
+    """More streams than resident groups, unaligned row pitch (scalar load path) and odd frame counts."""
+    N, H, nf, S = 256, 64, 37, 700
+    n_in = N + (nf - 1) * H + 1                   # odd pitch: no 8-byte alignment for most rows
+    rng = np.random.default_rng(0)
+    x = (rng.normal(size=(S, n_in)) * 0.1).astype(np.float32)
+    pv = make(N, H, H)
+    got = pv.process(dev(x), nf).cpu().numpy()
+    for s in (0, 1, 333, 699):
+        want, _ = po.process_compat(x[s], N, H, H, pv.imp, nf, nf)
+        assert snr_db(want, got[s, 0]) > 100
