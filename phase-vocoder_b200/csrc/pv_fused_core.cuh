@@ -83,12 +83,65 @@ PV_DEV float2 load_pair(const FrameIO &io, const float *win, int i)
     return make_float2(x0 * w.x, x1 * w.y);
 }
 
+// ---- private input ring ----------------------------------------------------------------------
+// When Ha is a multiple of 2*S1 every sample is consumed by the SAME thread in all the frames that
+// overlap it (frame coordinate i = 2*t1 mod 2*S1 is invariant under a shift by Ha).  Each thread
+// then owns a disjoint set of slots of a shared-memory ring of N floats: it copies its own new
+// samples of frame k+1 with cp.async while frame k is being processed and reads them back with no
+// barrier in between.  ring slot of absolute sample s: s mod N.
+#if defined(PV_HOST_EMUL)
+PV_DEV void cp_async8(float *dst, const float *src, int src_bytes)
+{
+    dst[0] = src_bytes >= 4 ? src[0] : 0.f;
+    dst[1] = src_bytes >= 8 ? src[1] : 0.f;
+}
+PV_DEV void cp_async_wait_all() {}
+#else
+PV_DEV void cp_async8(float *dst, const float *src, int src_bytes)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+PV_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#endif
+
+// Copies samples [i, i+2) (frame coordinates) of the frame starting at io.base into the ring.
+template <int N>
+PV_DEV void ring_fetch(const FrameIO &io, float *ring, int i)
+{
+    const long long g = io.base + i;
+    long long left = (io.n_in - g) * 4;
+    const int bytes = left >= 8 ? 8 : (left > 0 ? (int)left : 0);
+    const float *src = io.in + (bytes > 0 ? g : 0);           // keep the address valid when nothing is read
+    cp_async8(ring + ((int)(g & (N - 1))), src, bytes);
+}
+
+// Issues the copies of frame coordinates [lo, N) that belong to thread `tid` (lo = 0: whole frame).
+template <int LOG2N>
+PV_DEV void ring_prefetch(int tid, const FrameIO &io, float *ring, int lo)
+{
+    using S = Shape<LOG2N>;
+    constexpr int N = S::N, T = S::T, S1 = S::S1;
+#pragma unroll
+    for (int t1 = tid; t1 < S1; t1 += T)
+        for (int i = lo + 2 * t1; i < N; i += 2 * S1) ring_fetch<N>(io, ring, i);
+}
+
 // ---- forward passes 1 and 2 (results left in bufB for pass 3) ----
-template <int LOG2N, class Sync>
-PV_DEV void forward_12(int tid, const FrameIO &io, const Tables &tb, float2 *bufA, float2 *bufB, Sync sync)
+// ring == nullptr: inputs come straight from global memory.
+template <int LOG2N, class Sync, class Hook>
+PV_DEV void forward_12(int tid, const FrameIO &io, const Tables &tb, const float *ring, float2 *bufA, float2 *bufB,
+                       Sync sync, Hook after_exchange1)
 {
     using S = Shape<LOG2N>;
     constexpr int N = S::N, T = S::T, R1 = S::R1, R2 = S::R2, S1 = S::S1;
+    const int rbase = (int)(io.base & (N - 1));
+    auto ld = [&](int i) -> float2 {
+        if (ring == nullptr) return load_pair(io, tb.win, i);
+        const float2 x = *reinterpret_cast<const float2 *>(ring + ((rbase + i) & (N - 1)));
+        const float2 w = PV_LDG(reinterpret_cast<const float2 *>(tb.win + i));
+        return make_float2(x.x * w.x, x.y * w.y);
+    };
     // pass 1: butterflies t1 in [0, S1)
 #pragma unroll
     for (int t1 = tid; t1 < S1; t1 += T) {
@@ -96,8 +149,8 @@ PV_DEV void forward_12(int tid, const FrameIO &io, const Tables &tb, float2 *buf
 #pragma unroll
         for (int n1 = 0; n1 < R1; n1++) {
             // c[n], n = n1*S1 + t1: n < N/4 -> f[N/2 + 2n]; n >= 3N/4 -> f[2(n - 3N/4)]; else 0
-            if (n1 < R1 / 4) v[n1] = load_pair(io, tb.win, N / 2 + 2 * (n1 * S1 + t1));
-            else if (n1 >= 3 * R1 / 4) v[n1] = load_pair(io, tb.win, 2 * ((n1 - 3 * R1 / 4) * S1 + t1));
+            if (n1 < R1 / 4) v[n1] = ld(N / 2 + 2 * (n1 * S1 + t1));
+            else if (n1 >= 3 * R1 / 4) v[n1] = ld(2 * ((n1 - 3 * R1 / 4) * S1 + t1));
             else v[n1] = make_float2(0.f, 0.f);
         }
         dft<R1, -1>(v);
@@ -107,6 +160,7 @@ PV_DEV void forward_12(int tid, const FrameIO &io, const Tables &tb, float2 *buf
             bufA[k1 * S::LD1 + t1] = cmul(v[k1], PV_LDG(tb.tw1 + (k1 - 1) * S1 + t1));
     }
     sync();
+    after_exchange1();
     // pass 2: butterflies (k1, n3), k1 fastest across threads
 #pragma unroll
     for (int b = tid; b < R1 * 8; b += T) {
@@ -273,8 +327,9 @@ PV_DEV void inverse_23_ola(int tid, const Tables &tb, float2 *bufA, float2 *bufB
             const int n = b + C3 * m3;                     // complex output index: samples 2n, 2n+1
             const int i = (2 * n + N / 2) & (N - 1);       // half swap (kernel.cu:51-59)
             const float2 w = PV_LDG(reinterpret_cast<const float2 *>(tb.win + i));
-            const float y0 = (v[m3].x / (float)N) * w.x;   // cudaDivVec kernel.cu:130-138, cudaWindow :75-81
-            const float y1 = (v[m3].y / (float)N) * w.y;
+            // cudaDivVec kernel.cu:130-138 (x/N == x*(1/N) exactly, N a power of two), cudaWindow :75-81
+            const float y0 = (v[m3].x * (1.0f / (float)N)) * w.x;
+            const float y1 = (v[m3].y * (1.0f / (float)N)) * w.y;
             float2 *slot = reinterpret_cast<float2 *>(acc + ((pos0 + i) & (N - 1)));
             float2 a = *slot;
             a.x = (i < keep ? a.x : 0.f) + y0;             // cudaOverlapAdd kernel.cu:111-119
@@ -286,18 +341,25 @@ PV_DEV void inverse_23_ola(int tid, const Tables &tb, float2 *bufA, float2 *bufB
 }
 
 // ---- one whole frame ----
-template <int LOG2N, class Sync>
-PV_DEV void frame_compat(int tid, const FrameIO &io, const Tables &tb, bool nan_compat, float2 *bufA, float2 *bufB,
-                         float *acc, int pos0, int Hs, Sync sync)
+// `hook` runs once per frame at a point where (a) every thread has finished the overlap-add of the
+// PREVIOUS frame and (b) the next write to the accumulator is at least one barrier away: the caller
+// uses it to emit the previous frame's output hop without dedicated barriers.
+template <int LOG2N, class Sync, class Hook>
+PV_DEV void frame_compat(int tid, const FrameIO &io, const Tables &tb, bool nan_compat, const float *ring,
+                         float2 *bufA, float2 *bufB, float *acc, int pos0, int Hs, Sync sync, Hook hook)
 {
     using S = Shape<LOG2N>;
     if (io.analysed) {
-        forward_12<LOG2N>(tid, io, tb, bufA, bufB, sync);
+        forward_12<LOG2N>(tid, io, tb, ring, bufA, bufB, sync, hook);
         float2 P[8], Q[8], Zp[4], Zq[4];
         forward_3<LOG2N>(tid, bufB, P, Q);
         middle_compat<LOG2N>(tid, tb, nan_compat, P, Q, Zp, Zq);
         inverse_1<LOG2N>(tid, tb, Zp, bufA);
         inverse_1<LOG2N>(tid == 0 ? S::B3 / 2 : S::B3 - tid, tb, Zq, bufA);
+    } else {
+        sync();
+        hook();
+        sync();
     }
     inverse_23_ola<LOG2N>(tid, tb, bufA, bufB, acc, pos0, Hs, !io.analysed, sync);
 }

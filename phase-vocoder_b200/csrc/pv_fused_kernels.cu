@@ -22,7 +22,8 @@ struct Launch {
     static constexpr int G = (T >= 128) ? 1 : 128 / T;       // groups per CTA
     static constexpr int THREADS = T * G;
     static constexpr int GROUP_F2 = S::BUF_A + S::BUF_B;     // float2 per group
-    static constexpr size_t SMEM = (size_t)G * (GROUP_F2 * sizeof(float2) + S::N * sizeof(float));
+    // exchange buffers + OLA accumulator (+ private input ring)
+    static constexpr size_t smem(bool ring) { return (size_t)G * (GROUP_F2 * sizeof(float2) + (ring ? 2 : 1) * S::N * sizeof(float)); }
 };
 
 template <int T, int G>
@@ -37,7 +38,7 @@ struct GroupSync {
     }
 };
 
-template <int LOG2N, int MINB>
+template <int LOG2N, int MINB, bool RING>
 __global__ void __launch_bounds__(Launch<LOG2N>::THREADS, MINB)
 compat_fused_kernel(PvDev d, Tables tb, PvProcessArgs a, int vec_in_ok, int vec_out_ok)
 {
@@ -51,7 +52,9 @@ compat_fused_kernel(PvDev d, Tables tb, PvProcessArgs a, int vec_in_ok, int vec_
 
     float2 *bufA = reinterpret_cast<float2 *>(smem_raw) + (size_t)g * L::GROUP_F2;
     float2 *bufB = bufA + S::BUF_A;
-    float *acc = reinterpret_cast<float *>(reinterpret_cast<float2 *>(smem_raw) + (size_t)G * L::GROUP_F2) + (size_t)g * N;
+    float *fbase = reinterpret_cast<float *>(reinterpret_cast<float2 *>(smem_raw) + (size_t)G * L::GROUP_F2);
+    float *acc = fbase + (size_t)g * N;
+    float *ring = RING ? fbase + (size_t)(G + g) * N : nullptr;
 
     GroupSync<T, G> sync{g, T >= 32 ? 0xffffffffu : (((1u << (T & 31)) - 1u) << ((threadIdx.x & 31) / T * T))};
 
@@ -65,38 +68,73 @@ compat_fused_kernel(PvDev d, Tables tb, PvProcessArgs a, int vec_in_ok, int vec_
     for (int i = tid; i < N; i += T) acc[i] = (seg.carry_in && state && i + Hs < N) ? state[i + Hs] : 0.f;
     sync();
 
+    // emits the output hop of frame kk whose ring position is pp (src/main.cpp:281-295)
+    auto emit = [&](long long kk, int pp) {
+        if (kk < seg.k_emit) return;
+        float *o = out + kk * (long long)Hs;
+        if (vec_out_ok) {
+            for (int j = 4 * tid; j < Hs; j += 4 * T)
+                *reinterpret_cast<float4 *>(o + j) = *reinterpret_cast<const float4 *>(acc + ((pp + j) & (N - 1)));
+        } else {
+            for (int j = tid; j < Hs; j += T) o[j] = acc[(pp + j) & (N - 1)];
+        }
+    };
+
+    const long long k_an_end = seg.k_end < a.n_analysed ? seg.k_end : a.n_analysed;   // frames >= this are zero spectra
+    if (RING && seg.k_begin < k_an_end) {
+        FrameIO io0{in, a.n_in, seg.k_begin * (long long)d.Ha, true, true};
+        ring_prefetch<LOG2N>(tid, io0, ring, 0);
+    }
     int pos0 = 0;
     for (long long k = seg.k_begin; k < seg.k_end; ++k) {
         FrameIO io{in, a.n_in, k * (long long)d.Ha, k < a.n_analysed, vec_in_ok != 0};
-        frame_compat<LOG2N>(tid, io, tb, nan_compat, bufA, bufB, acc, pos0, Hs, sync);
-        sync();
-        if (k >= seg.k_emit) {
-            float *o = out + k * (long long)Hs;
-            if (vec_out_ok) {
-                for (int j = 4 * tid; j < Hs; j += 4 * T)
-                    *reinterpret_cast<float4 *>(o + j) = *reinterpret_cast<const float4 *>(acc + ((pos0 + j) & (N - 1)));
-            } else {
-                for (int j = tid; j < Hs; j += T) o[j] = acc[(pos0 + j) & (N - 1)];
+        // runs after the first barrier of the frame: prefetch the next frame's new samples into this
+        // thread's private ring slots, then write out the previous frame's hop
+        auto hook = [&]() {
+            if (RING && k + 1 < k_an_end) {
+                FrameIO nx{in, a.n_in, (k + 1) * (long long)d.Ha, true, true};
+                ring_prefetch<LOG2N>(tid, nx, ring, N - d.Ha);
             }
-        }
-        if (seg.carry_out && state && k + 1 == seg.k_end)
-            for (int i = tid; i < N; i += T) state[i] = acc[(pos0 + i) & (N - 1)];
-        sync();
+            if (k > seg.k_begin) emit(k - 1, (pos0 - Hs) & (N - 1));
+        };
+        if (RING) cp_async_wait_all();
+        frame_compat<LOG2N>(tid, io, tb, nan_compat, ring, bufA, bufB, acc, pos0, Hs, sync, hook);
         pos0 = (pos0 + Hs) & (N - 1);
     }
+    sync();
+    const int plast = (pos0 - Hs) & (N - 1);
+    emit(seg.k_end - 1, plast);
+    if (seg.carry_out && state)
+        for (int i = tid; i < N; i += T) state[i] = acc[(plast + i) & (N - 1)];
+}
+
+// The private ring needs every sample to be consumed by one thread (Ha multiple of 2*S1) and
+// 8-byte aligned rows for cp.async.
+template <int LOG2N>
+bool ring_ok(const PvDev &d, bool vec_in_ok) { return vec_in_ok && d.Ha <= d.N && (d.Ha % (2 * Shape<LOG2N>::S1)) == 0; }
+
+template <int LOG2N, int MINB, bool RING>
+cudaError_t launch2(const PvDev &d, const Tables &tb, const PvProcessArgs &a, int vec_in_ok, int vec_out_ok,
+                    cudaStream_t st)
+{
+    using L = Launch<LOG2N>;
+    auto kern = compat_fused_kernel<LOG2N, MINB, RING>;
+    const size_t smem = L::smem(RING);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    const int grid = (a.n_segs + L::G - 1) / L::G;
+    kern<<<grid, L::THREADS, smem, st>>>(d, tb, a, vec_in_ok, vec_out_ok);
+    return cudaGetLastError();
 }
 
 template <int LOG2N, int MINB>
 cudaError_t launch(const PvDev &d, const Tables &tb, const PvProcessArgs &a, int vec_in_ok, int vec_out_ok,
                    cudaStream_t st)
 {
-    using L = Launch<LOG2N>;
-    auto kern = compat_fused_kernel<LOG2N, MINB>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
-    if (e != cudaSuccess) return e;
-    const int grid = (a.n_segs + L::G - 1) / L::G;
-    kern<<<grid, L::THREADS, L::SMEM, st>>>(d, tb, a, vec_in_ok, vec_out_ok);
-    return cudaGetLastError();
+    if (ring_ok<LOG2N>(d, vec_in_ok != 0)) return launch2<LOG2N, MINB, true>(d, tb, a, vec_in_ok, vec_out_ok, st);
+    return launch2<LOG2N, MINB, false>(d, tb, a, vec_in_ok, vec_out_ok, st);
 }
 
 }  // namespace
@@ -107,10 +145,11 @@ template <int LOG2N, int MINB>
 static int capacity(int sm_count)
 {
     using L = Launch<LOG2N>;
-    auto kern = compat_fused_kernel<LOG2N, MINB>;
+    auto kern = compat_fused_kernel<LOG2N, MINB, true>;
+    const size_t smem = L::smem(true);
     int nb = 0;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, L::THREADS, L::SMEM) != cudaSuccess || nb < 1)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, L::THREADS, smem) != cudaSuccess || nb < 1)
         nb = 1;
     return nb * sm_count * L::G;
 }

@@ -23,19 +23,37 @@ static int run(const float *x, long n_in, int Ha, int Hs, const float *win, long
     build_tables(LOG2N, ht);
     Tables tb{ht.tw1.data(), ht.tw2.data(), ht.tw2n.data(), ht.itw1.data(), ht.itw2.data(), win};
     std::vector<float2> bufA(S::BUF_A), bufB(S::BUF_B);
-    std::vector<float> acc(N, 0.f);
+    std::vector<float> acc(N, 0.f), ringbuf(N, 0.f);
     std::barrier bar(T);
+    const bool use_ring = (Ha % (2 * S::S1)) == 0;
+    float *ring = use_ring ? ringbuf.data() : nullptr;
     auto body = [&](int tid) {
         auto sync = [&]() { bar.arrive_and_wait(); };
         int pos0 = 0;
+        if (use_ring && n_analysed > 0) {
+            FrameIO io0{x, n_in, 0, true, (Ha % 2) == 0};
+            ring_prefetch<LOG2N>(tid, io0, ring, 0);
+        }
         for (long k = 0; k < n_frames; k++) {
             FrameIO io{x, n_in, k * (long long)Ha, k < n_analysed, (Ha % 2) == 0};
-            frame_compat<LOG2N>(tid, io, tb, nan_compat != 0, bufA.data(), bufB.data(), acc.data(), pos0, Hs, sync);
-            sync();
-            for (int j = tid; j < Hs; j += T) out[k * (long)Hs + j] = acc[(pos0 + j) & (N - 1)];
-            sync();
+            auto hook = [&]() {
+                if (use_ring && k + 1 < n_analysed) {
+                    FrameIO nx{x, n_in, (k + 1) * (long long)Ha, true, true};
+                    ring_prefetch<LOG2N>(tid, nx, ring, N - Ha);
+                }
+                if (k > 0) {
+                    const int pp = (pos0 - Hs) & (N - 1);
+                    for (int j = tid; j < Hs; j += T) out[(k - 1) * (long)Hs + j] = acc[(pp + j) & (N - 1)];
+                }
+            };
+            cp_async_wait_all();
+            frame_compat<LOG2N>(tid, io, tb, nan_compat != 0, ring, bufA.data(), bufB.data(), acc.data(), pos0, Hs,
+                                sync, hook);
             pos0 = (pos0 + Hs) & (N - 1);
         }
+        sync();
+        const int pp = (pos0 - Hs) & (N - 1);
+        for (int j = tid; j < Hs; j += T) out[(n_frames - 1) * (long)Hs + j] = acc[(pp + j) & (N - 1)];
     };
     std::vector<std::thread> th;
     for (int t = 0; t < T; t++) th.emplace_back(body, t);
