@@ -106,4 +106,44 @@ PV_DEV void dft(float2 (&v)[R])
     }
 }
 
+// One half of a 16-point DFT: outputs k = 2q + ODD, q = 0..7.  Two threads share a butterfly when
+// a pass has fewer radix-16 butterflies than threads; the halves add up to exactly one dft<16>.
+template <int DIR, bool ODD>
+PV_DEV void dft16_half(const float2 (&a)[16], float2 (&o)[8])
+{
+#pragma unroll
+    for (int n = 0; n < 8; n++) o[n] = ODD ? csub(a[n], a[n + 8]) : cadd(a[n], a[n + 8]);
+    if constexpr (ODD) {
+        o[1] = twid16<1, DIR>(o[1]); o[2] = twid16<2, DIR>(o[2]); o[3] = twid16<3, DIR>(o[3]);
+        o[4] = twid16<4, DIR>(o[4]); o[5] = twid16<5, DIR>(o[5]); o[6] = twid16<6, DIR>(o[6]);
+        o[7] = twid16<7, DIR>(o[7]);
+    }
+    dft8<DIR>(o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+}
+
+// Forward R-point DFT of a sequence whose middle half is zero (only v[0..R/4) and v[3R/4..R) are
+// set): the zero-padded, zero-phase frame layout of the compat path.  With m = n for the low
+// quarter and m = n - R for the high quarter, X[2q] = DFT_{R/2}(u)[q] and X[2q+1] = DFT_{R/2}(u')[q],
+// u[m mod R/2] = v[m], u'[m mod R/2] = v[m] W_R^m.  ~20 % fewer flops than the full butterfly.
+template <int R>
+PV_DEV void dft_pruned_fwd(float2 (&v)[R])
+{
+    static_assert(R == 8 || R == 16, "radix");
+    constexpr int H = R / 2, Q = R / 4, STEP = 16 / R;
+    float2 e[H], o[H];
+#pragma unroll
+    for (int i = 0; i < Q; i++) { e[i] = v[i]; e[Q + i] = v[3 * Q + i]; }
+    if constexpr (R == 16) {
+        o[0] = e[0]; o[1] = twid16<1, -1>(e[1]); o[2] = twid16<2, -1>(e[2]); o[3] = twid16<3, -1>(e[3]);
+        o[4] = twid16<12, -1>(e[4]); o[5] = twid16<13, -1>(e[5]); o[6] = twid16<14, -1>(e[6]); o[7] = twid16<15, -1>(e[7]);
+    } else {
+        o[0] = e[0]; o[1] = twid16<2, -1>(e[1]); o[2] = twid16<12, -1>(e[2]); o[3] = twid16<14, -1>(e[3]);
+    }
+    dft<H, -1>(e);
+    dft<H, -1>(o);
+#pragma unroll
+    for (int q = 0; q < H; q++) { v[2 * q] = e[q]; v[2 * q + 1] = o[q]; }
+    (void)STEP;
+}
+
 }  // namespace pvfft

@@ -59,6 +59,28 @@ struct Tables {
     const float *win;     // [N]
 };
 
+// Loop-invariant per-thread twiddles kept in registers (used when every thread owns exactly one
+// pass-1 butterfly, S1 == T, so that t1 == u == tid for the whole segment).  All other twiddles of
+// the thread are products of these with compile-time constants, which removes ~37 L1 loads and
+// their address arithmetic per thread and frame.
+struct ThreadTw {
+    float2 w1, w2, w4, w8;   // W_N^{u}, ^2u, ^4u, ^8u      (W_N = exp(-2 pi i / N))
+    float2 h;                // exp(-j*pi*u/N)              (the 2N-th root)
+};
+
+template <int LOG2N>
+PV_DEV ThreadTw load_thread_tw(int u, const Tables &tb)
+{
+    using S = Shape<LOG2N>;
+    ThreadTw t;
+    t.w1 = PV_LDG(tb.tw1 + 0 * S::S1 + u);
+    t.w2 = PV_LDG(tb.tw1 + 1 * S::S1 + u);
+    t.w4 = PV_LDG(tb.tw1 + 3 * S::S1 + u);
+    t.w8 = (S::R1 > 8) ? PV_LDG(tb.tw1 + 7 * S::S1 + u) : make_float2(1.f, 0.f);
+    t.h = PV_LDG(tb.tw2n + u);
+    return t;
+}
+
 struct FrameIO {
     const float *in;      // stream base
     long long n_in;       // valid samples in the stream
@@ -129,9 +151,9 @@ PV_DEV void ring_prefetch(int tid, const FrameIO &io, float *ring, int lo)
 
 // ---- forward passes 1 and 2 (results left in bufB for pass 3) ----
 // ring == nullptr: inputs come straight from global memory.
-template <int LOG2N, class Sync, class Hook>
-PV_DEV void forward_12(int tid, const FrameIO &io, const Tables &tb, const float *ring, float2 *bufA, float2 *bufB,
-                       Sync sync, Hook after_exchange1)
+template <int LOG2N, bool TWREG, class Sync, class Hook>
+PV_DEV void forward_12(int tid, const FrameIO &io, const Tables &tb, const ThreadTw &tt, const float *ring,
+                       float2 *bufA, float2 *bufB, Sync sync, Hook after_exchange1)
 {
     using S = Shape<LOG2N>;
     constexpr int N = S::N, T = S::T, R1 = S::R1, R2 = S::R2, S1 = S::S1;
@@ -153,11 +175,22 @@ PV_DEV void forward_12(int tid, const FrameIO &io, const Tables &tb, const float
             else if (n1 >= 3 * R1 / 4) v[n1] = ld(2 * ((n1 - 3 * R1 / 4) * S1 + t1));
             else v[n1] = make_float2(0.f, 0.f);
         }
-        dft<R1, -1>(v);
+        dft_pruned_fwd<R1>(v);
         bufA[t1] = v[0];
+        if constexpr (TWREG && R1 == 16) {
+            static_assert(!TWREG || S1 == T, "register twiddles need one pass-1 butterfly per thread");
+            float2 w[16];
+            w[1] = tt.w1; w[2] = tt.w2; w[4] = tt.w4; w[8] = tt.w8;
+            w[3] = cmul(w[1], w[2]); w[5] = cmul(w[1], w[4]); w[6] = cmul(w[2], w[4]); w[7] = cmul(w[3], w[4]);
 #pragma unroll
-        for (int k1 = 1; k1 < R1; k1++)
-            bufA[k1 * S::LD1 + t1] = cmul(v[k1], PV_LDG(tb.tw1 + (k1 - 1) * S1 + t1));
+            for (int k1 = 9; k1 < 16; k1++) w[k1] = cmul(w[k1 - 8], w[8]);
+#pragma unroll
+            for (int k1 = 1; k1 < R1; k1++) bufA[k1 * S::LD1 + t1] = cmul(v[k1], w[k1]);
+        } else {
+#pragma unroll
+            for (int k1 = 1; k1 < R1; k1++)
+                bufA[k1 * S::LD1 + t1] = cmul(v[k1], PV_LDG(tb.tw1 + (k1 - 1) * S1 + t1));
+        }
     }
     sync();
     after_exchange1();
@@ -211,7 +244,9 @@ PV_DEV float2 compat_map(float2 X, bool nan_compat)
 #ifdef PV_HOST_EMUL
     const float r = 1.0f / sqrtf(m2);
 #else
-    const float r = rsqrtf(m2);
+    float r;     // single MUFU.RSQ (2 ulp); a denormal |X|^2 flushes to 0 -> r = inf, caught below
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(m2));
+    if (m2 < 1.17549435e-38f) return make_float2(fabsf(X.x), 0.f);
 #endif
     return make_float2(fabsf(X.x), X.x * X.y * r);
 }
@@ -227,25 +262,51 @@ PV_DEV float2 herm_pack(float2 yk, float2 ym, float2 w)
 
 // ---- middle: P,Q (16 transform outputs) -> Zp[4], Zq[4] = packed inverse inputs at
 //      kappa = tP + B3*n1 and tQ + B3*n1 ----
-template <int LOG2N>
-PV_DEV void middle_compat(int u, const Tables &tb, bool nan_compat, const float2 (&P)[8], const float2 (&Q)[8],
-                          float2 (&Zp)[4], float2 (&Zq)[4])
+// exp(-j*pi*(base + B3*J)/N) from exp(-j*pi*base/N): B3/N = 1/8 -> a multiple of the 16th root
+template <int J>
+PV_DEV float2 rot16(float2 a) { return twid16<J, -1>(a); }
+
+template <int LOG2N, bool TWREG>
+PV_DEV void middle_compat(int u, const Tables &tb, const ThreadTw &tt, bool nan_compat, const float2 (&P)[8],
+                          const float2 (&Q)[8], float2 (&Zp)[4], float2 (&Zq)[4])
 {
     using S = Shape<LOG2N>;
     constexpr int N = S::N, B3 = S::B3;
     float2 Yp[5], Yq[4];
     if (u != 0) {
+        if constexpr (TWREG) {
+            // tw2n[u + B3 j] = h * W16^j ; tw2n[B3 - u + B3 j] = conj(h) * W16^(j+1)
+            const float2 hc = cconj(tt.h), w1c = cconj(tt.w1);
+            Yp[0] = compat_map(split(P[0], Q[7], tt.h), nan_compat);
+            Yp[1] = compat_map(split(P[1], Q[6], rot16<1>(tt.h)), nan_compat);
+            Yp[2] = compat_map(split(P[2], Q[5], rot16<2>(tt.h)), nan_compat);
+            Yp[3] = compat_map(split(P[3], Q[4], rot16<3>(tt.h)), nan_compat);
+            Yq[0] = compat_map(split(Q[0], P[7], rot16<1>(hc)), nan_compat);
+            Yq[1] = compat_map(split(Q[1], P[6], rot16<2>(hc)), nan_compat);
+            Yq[2] = compat_map(split(Q[2], P[5], rot16<3>(hc)), nan_compat);
+            Yq[3] = compat_map(split(Q[3], P[4], rot16<4>(hc)), nan_compat);
+            // exp(+2 pi i k/N) = conj(tw2n[2k]); tw2n[2(u + B3 j)] = w1 * W16^(2j); tw2n[2(B3-u+B3 j)] = conj(w1) * W16^(2j+2)
+            Zp[0] = herm_pack(Yp[0], Yq[3], cconj(tt.w1));
+            Zp[1] = herm_pack(Yp[1], Yq[2], cconj(rot16<2>(tt.w1)));
+            Zp[2] = herm_pack(Yp[2], Yq[1], cconj(rot16<4>(tt.w1)));
+            Zp[3] = herm_pack(Yp[3], Yq[0], cconj(rot16<6>(tt.w1)));
+            Zq[0] = herm_pack(Yq[0], Yp[3], cconj(rot16<2>(w1c)));
+            Zq[1] = herm_pack(Yq[1], Yp[2], cconj(rot16<4>(w1c)));
+            Zq[2] = herm_pack(Yq[2], Yp[1], cconj(rot16<6>(w1c)));
+            Zq[3] = herm_pack(Yq[3], Yp[0], cconj(rot16<8>(w1c)));
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int kp = u + B3 * j, kq = (B3 - u) + B3 * j;
-            Yp[j] = compat_map(split(P[j], Q[7 - j], PV_LDG(tb.tw2n + kp)), nan_compat);
-            Yq[j] = compat_map(split(Q[j], P[7 - j], PV_LDG(tb.tw2n + kq)), nan_compat);
-        }
+            for (int j = 0; j < 4; j++) {
+                const int kp = u + B3 * j, kq = (B3 - u) + B3 * j;
+                Yp[j] = compat_map(split(P[j], Q[7 - j], PV_LDG(tb.tw2n + kp)), nan_compat);
+                Yq[j] = compat_map(split(Q[j], P[7 - j], PV_LDG(tb.tw2n + kq)), nan_compat);
+            }
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int kp = u + B3 * j, kq = (B3 - u) + B3 * j;
-            Zp[j] = herm_pack(Yp[j], Yq[3 - j], cconj(PV_LDG(tb.tw2n + 2 * kp)));
-            Zq[j] = herm_pack(Yq[j], Yp[3 - j], cconj(PV_LDG(tb.tw2n + 2 * kq)));
+            for (int j = 0; j < 4; j++) {
+                const int kp = u + B3 * j, kq = (B3 - u) + B3 * j;
+                Zp[j] = herm_pack(Yp[j], Yq[3 - j], cconj(PV_LDG(tb.tw2n + 2 * kp)));
+                Zq[j] = herm_pack(Yq[j], Yp[3 - j], cconj(PV_LDG(tb.tw2n + 2 * kq)));
+            }
         }
     } else {
         // thread 0 owns the self-paired columns t3 = 0 (bins 0, B3, .., 4*B3 = N/2) and t3 = B3/2
@@ -279,6 +340,18 @@ PV_DEV void inverse_1(int t1, const Tables &tb, float2 (&Z)[4], float2 *bufA)
         bufA[m1 * S::ILD1 + t1] = cmul(Z[m1], PV_LDG(tb.itw1 + (m1 - 1) * S::B3 + t1));
 }
 
+// same with the three twiddles exp(+2 pi i m1 t1/(N/2)), m1 = 1..3, supplied by the caller
+template <int LOG2N>
+PV_DEV void inverse_1_tw(int t1, float2 a1, float2 a2, float2 a3, float2 (&Z)[4], float2 *bufA)
+{
+    using S = Shape<LOG2N>;
+    dft<4, +1>(Z);
+    bufA[t1] = Z[0];
+    bufA[1 * S::ILD1 + t1] = cmul(Z[1], a1);
+    bufA[2 * S::ILD1 + t1] = cmul(Z[2], a2);
+    bufA[3 * S::ILD1 + t1] = cmul(Z[3], a3);
+}
+
 // ---- inverse passes 2 and 3 + steps G/H (scale, half swap, window, overlap-add) ----
 // acc: OLA ring of N floats, pos0: ring position of sample 0 of this frame.
 template <int LOG2N, class Sync>
@@ -289,52 +362,87 @@ PV_DEV void inverse_23_ola(int tid, const Tables &tb, float2 *bufA, float2 *bufB
     constexpr int N = S::N, T = S::T, R1 = S::R1, R2 = S::R2, B3 = S::B3;
     constexpr int C2 = 4 * R2;       // pass-2 butterflies (m1, n3), radix R1
     constexpr int C3 = 4 * R1;       // pass-3 butterflies (m1, m2), radix R2
+    static_assert(C2 >= T || 2 * C2 == T, "pass 2 cover");
+    static_assert(C3 >= T || 2 * C3 == T, "pass 3 cover");
+    constexpr bool SPLIT2 = (2 * C2 == T) && (R1 == 16);   // two threads per radix-16 butterfly
+    constexpr bool SPLIT3 = (2 * C3 == T) && (R2 == 16);
+    const int keep = N - Hs;
+    // steps G+H for complex output n (samples 2n, 2n+1)
+    auto ola = [&](int n, float2 v) {
+        const int i = (2 * n + N / 2) & (N - 1);       // half swap (kernel.cu:51-59)
+        const float2 w = PV_LDG(reinterpret_cast<const float2 *>(tb.win + i));
+        // cudaDivVec kernel.cu:130-138 (x/N == x*(1/N) exactly, N a power of two), cudaWindow :75-81
+        const float y0 = (v.x * (1.0f / (float)N)) * w.x;
+        const float y1 = (v.y * (1.0f / (float)N)) * w.y;
+        float2 *slot = reinterpret_cast<float2 *>(acc + ((pos0 + i) & (N - 1)));
+        float2 a = *slot;
+        a.x = (i < keep ? a.x : 0.f) + y0;             // cudaOverlapAdd kernel.cu:111-119
+        a.y = (i + 1 < keep ? a.y : 0.f) + y1;
+        *slot = a;
+    };
     if (!zero_frame) {
         sync();
-        // pass 2: when there are fewer butterflies than threads, the low threads take it
+        if constexpr (SPLIT2) {
+            const int b = tid % C2;
+            const int n3 = b % R2, m1 = b / R2;
+            float2 v[16], o[8];
 #pragma unroll
-        for (int b = tid; b < C2; b += T) {
-            const int n3 = b % R2, m1 = b / R2;         // n3 fastest: conflict-free on both sides
-            float2 v[R1];
+            for (int n2 = 0; n2 < 16; n2++) v[n2] = bufA[m1 * S::ILD1 + n2 * R2 + n3];
+            const int half = tid / C2;                  // warp-uniform
+            if (half == 0) dft16_half<+1, false>(v, o);
+            else dft16_half<+1, true>(v, o);
 #pragma unroll
-            for (int n2 = 0; n2 < R1; n2++) v[n2] = bufA[m1 * S::ILD1 + n2 * R2 + n3];
-            dft<R1, +1>(v);
-            bufB[m1 * S::ILD2 + n3] = v[0];
+            for (int q = 0; q < 8; q++) {
+                const int m2 = 2 * q + half;
+                float2 r = o[q];
+                if (m2 != 0) r = cmul(r, PV_LDG(tb.itw2 + (m2 - 1) * R2 + n3));
+                bufB[(m1 + 4 * m2) * S::ILD2 + n3] = r;
+            }
+        } else {
 #pragma unroll
-            for (int m2 = 1; m2 < R1; m2++)
-                bufB[(m1 + 4 * m2) * S::ILD2 + n3] = cmul(v[m2], PV_LDG(tb.itw2 + (m2 - 1) * R2 + n3));
+            for (int b = tid; b < C2; b += T) {
+                const int n3 = b % R2, m1 = b / R2;         // n3 fastest: conflict-free on both sides
+                float2 v[R1];
+#pragma unroll
+                for (int n2 = 0; n2 < R1; n2++) v[n2] = bufA[m1 * S::ILD1 + n2 * R2 + n3];
+                dft<R1, +1>(v);
+                bufB[m1 * S::ILD2 + n3] = v[0];
+#pragma unroll
+                for (int m2 = 1; m2 < R1; m2++)
+                    bufB[(m1 + 4 * m2) * S::ILD2 + n3] = cmul(v[m2], PV_LDG(tb.itw2 + (m2 - 1) * R2 + n3));
+            }
         }
         sync();
     }
-    // pass 3 (high threads first when C3 < T, to balance the warps against pass 2)
-    constexpr int OFF3 = (C3 < T) ? (T - C3) : 0;
-    const int keep = N - Hs;
-#pragma unroll
-    for (int b0 = tid - OFF3; b0 < C3; b0 += T) {
-        if (b0 < 0) break;
-        const int b = b0;
-        float2 v[R2];
+    // pass 3 -> time samples
+    if constexpr (SPLIT3) {
+        const int b = tid % C3, half = tid / C3;
+        float2 v[16], o[8];
         if (!zero_frame) {
 #pragma unroll
-            for (int n3 = 0; n3 < R2; n3++) v[n3] = bufB[b * S::ILD2 + n3];
-            dft<R2, +1>(v);
+            for (int n3 = 0; n3 < 16; n3++) v[n3] = bufB[b * S::ILD2 + n3];
+            if (half == 0) dft16_half<+1, false>(v, o);
+            else dft16_half<+1, true>(v, o);
         } else {
 #pragma unroll
-            for (int n3 = 0; n3 < R2; n3++) v[n3] = make_float2(0.f, 0.f);
+            for (int q = 0; q < 8; q++) o[q] = make_float2(0.f, 0.f);
         }
 #pragma unroll
-        for (int m3 = 0; m3 < R2; m3++) {
-            const int n = b + C3 * m3;                     // complex output index: samples 2n, 2n+1
-            const int i = (2 * n + N / 2) & (N - 1);       // half swap (kernel.cu:51-59)
-            const float2 w = PV_LDG(reinterpret_cast<const float2 *>(tb.win + i));
-            // cudaDivVec kernel.cu:130-138 (x/N == x*(1/N) exactly, N a power of two), cudaWindow :75-81
-            const float y0 = (v[m3].x * (1.0f / (float)N)) * w.x;
-            const float y1 = (v[m3].y * (1.0f / (float)N)) * w.y;
-            float2 *slot = reinterpret_cast<float2 *>(acc + ((pos0 + i) & (N - 1)));
-            float2 a = *slot;
-            a.x = (i < keep ? a.x : 0.f) + y0;             // cudaOverlapAdd kernel.cu:111-119
-            a.y = (i + 1 < keep ? a.y : 0.f) + y1;
-            *slot = a;
+        for (int q = 0; q < 8; q++) ola(b + C3 * (2 * q + half), o[q]);
+    } else {
+#pragma unroll
+        for (int b = tid; b < C3; b += T) {
+            float2 v[R2];
+            if (!zero_frame) {
+#pragma unroll
+                for (int n3 = 0; n3 < R2; n3++) v[n3] = bufB[b * S::ILD2 + n3];
+                dft<R2, +1>(v);
+            } else {
+#pragma unroll
+                for (int n3 = 0; n3 < R2; n3++) v[n3] = make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int m3 = 0; m3 < R2; m3++) ola(b + C3 * m3, v[m3]);
         }
     }
     (void)B3;
@@ -344,18 +452,26 @@ PV_DEV void inverse_23_ola(int tid, const Tables &tb, float2 *bufA, float2 *bufB
 // `hook` runs once per frame at a point where (a) every thread has finished the overlap-add of the
 // PREVIOUS frame and (b) the next write to the accumulator is at least one barrier away: the caller
 // uses it to emit the previous frame's output hop without dedicated barriers.
-template <int LOG2N, class Sync, class Hook>
-PV_DEV void frame_compat(int tid, const FrameIO &io, const Tables &tb, bool nan_compat, const float *ring,
-                         float2 *bufA, float2 *bufB, float *acc, int pos0, int Hs, Sync sync, Hook hook)
+template <int LOG2N, bool TWREG, class Sync, class Hook>
+PV_DEV void frame_compat(int tid, const FrameIO &io, const Tables &tb, const ThreadTw &tt, bool nan_compat,
+                         const float *ring, float2 *bufA, float2 *bufB, float *acc, int pos0, int Hs, Sync sync,
+                         Hook hook)
 {
     using S = Shape<LOG2N>;
     if (io.analysed) {
-        forward_12<LOG2N>(tid, io, tb, ring, bufA, bufB, sync, hook);
+        forward_12<LOG2N, TWREG>(tid, io, tb, tt, ring, bufA, bufB, sync, hook);
         float2 P[8], Q[8], Zp[4], Zq[4];
         forward_3<LOG2N>(tid, bufB, P, Q);
-        middle_compat<LOG2N>(tid, tb, nan_compat, P, Q, Zp, Zq);
-        inverse_1<LOG2N>(tid, tb, Zp, bufA);
-        inverse_1<LOG2N>(tid == 0 ? S::B3 / 2 : S::B3 - tid, tb, Zq, bufA);
+        middle_compat<LOG2N, TWREG>(tid, tb, tt, nan_compat, P, Q, Zp, Zq);
+        if (TWREG && tid != 0) {
+            // exp(+2 pi i m1 u/(N/2)) = conj(W_N^{2 m1 u}); for t1 = B3-u: j^m1 * W_N^{2 m1 u}
+            const float2 w6 = cmul(tt.w2, tt.w4);
+            inverse_1_tw<LOG2N>(tid, cconj(tt.w2), cconj(tt.w4), cconj(w6), Zp, bufA);
+            inverse_1_tw<LOG2N>(S::B3 - tid, mul_pj(tt.w2), make_float2(-tt.w4.x, -tt.w4.y), mul_mj(w6), Zq, bufA);
+        } else {
+            inverse_1<LOG2N>(tid, tb, Zp, bufA);
+            inverse_1<LOG2N>(tid == 0 ? S::B3 / 2 : S::B3 - tid, tb, Zq, bufA);
+        }
     } else {
         sync();
         hook();

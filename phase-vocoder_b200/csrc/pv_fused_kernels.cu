@@ -8,6 +8,8 @@
 // the real-FFT split, the reference's mag/phase + polar->rect steps and the Hermitian pack of
 // the inverse run in registers.  HBM traffic is the compulsory 4*Ha + 4*Hs bytes per frame
 // (the 75 % overlap re-reads of the input hit L1/L2).
+#include <cstdlib>
+
 #include "pv_fused_core.cuh"
 #include "pv_internal.h"
 
@@ -85,6 +87,9 @@ compat_fused_kernel(PvDev d, Tables tb, PvProcessArgs a, int vec_in_ok, int vec_
         FrameIO io0{in, a.n_in, seg.k_begin * (long long)d.Ha, true, true};
         ring_prefetch<LOG2N>(tid, io0, ring, 0);
     }
+    // per-thread twiddle bases live in registers for the whole segment
+    constexpr bool TWREG = (S::S1 == S::T) && (S::R1 == 16);
+    const ThreadTw tt = load_thread_tw<LOG2N>(tid, tb);
     int pos0 = 0;
     for (long long k = seg.k_begin; k < seg.k_end; ++k) {
         FrameIO io{in, a.n_in, k * (long long)d.Ha, k < a.n_analysed, vec_in_ok != 0};
@@ -98,7 +103,7 @@ compat_fused_kernel(PvDev d, Tables tb, PvProcessArgs a, int vec_in_ok, int vec_
             if (k > seg.k_begin) emit(k - 1, (pos0 - Hs) & (N - 1));
         };
         if (RING) cp_async_wait_all();
-        frame_compat<LOG2N>(tid, io, tb, nan_compat, ring, bufA, bufB, acc, pos0, Hs, sync, hook);
+        frame_compat<LOG2N, TWREG>(tid, io, tb, tt, nan_compat, ring, bufA, bufB, acc, pos0, Hs, sync, hook);
         pos0 = (pos0 + Hs) & (N - 1);
     }
     sync();
@@ -133,6 +138,8 @@ template <int LOG2N, int MINB>
 cudaError_t launch(const PvDev &d, const Tables &tb, const PvProcessArgs &a, int vec_in_ok, int vec_out_ok,
                    cudaStream_t st)
 {
+    static const char *variant = getenv("PV_VARIANT");      // experiment switch
+    if (variant && variant[0] == '5') return launch2<LOG2N, 5, false>(d, tb, a, vec_in_ok, vec_out_ok, st);
     if (ring_ok<LOG2N>(d, vec_in_ok != 0)) return launch2<LOG2N, MINB, true>(d, tb, a, vec_in_ok, vec_out_ok, st);
     return launch2<LOG2N, MINB, false>(d, tb, a, vec_in_ok, vec_out_ok, st);
 }

@@ -47,8 +47,10 @@ static int run(const float *x, long n_in, int Ha, int Hs, const float *win, long
                 }
             };
             cp_async_wait_all();
-            frame_compat<LOG2N>(tid, io, tb, nan_compat != 0, ring, bufA.data(), bufB.data(), acc.data(), pos0, Hs,
-                                sync, hook);
+            constexpr bool TWREG = (S::S1 == S::T) && (S::R1 == 16);
+            const ThreadTw tt = load_thread_tw<LOG2N>(tid, tb);
+            frame_compat<LOG2N, TWREG>(tid, io, tb, tt, nan_compat != 0, ring, bufA.data(), bufB.data(), acc.data(),
+                                       pos0, Hs, sync, hook);
             pos0 = (pos0 + Hs) & (N - 1);
         }
         sync();
