@@ -33,7 +33,7 @@ struct pv_handle {
     bool fused = false;
     int capacity = 0;
     PvFusedTables ft;
-    float2 *d_ft[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float2 *d_ft[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // segment plan cache
     PvSegment *d_segs = nullptr;
     size_t segs_cap = 0;
@@ -150,6 +150,9 @@ int plan_segments(pv_handle *h, int64_t n_streams, int64_t n_frames, int32_t fla
     const int64_t target = (int64_t)h->capacity * 8;
     int64_t per_stream = (target + n_streams - 1) / n_streams;
     if (per_stream < 1) per_stream = 1;
+    // corrected mode carries the phase accumulators from frame to frame: a stream is one segment
+    // (frame-range splitting of a corrected stream goes through the phase-carry path instead)
+    if (h->p.mode == PV_MODE_CORRECTED) per_stream = 1;
     int64_t seg_len = (n_frames + per_stream - 1) / per_stream;
     const int64_t min_len = std::max<int64_t>(32 * halo, 32);
     if (seg_len < min_len) seg_len = min_len;
@@ -277,18 +280,24 @@ int pv_create(const pv_params *params, pv_handle **out)
         if (rc == PV_OK) rc = upload(&h->d_nomS, nomS);
     }
     h->capacity = h->sm_count * 8;
-    if (rc == PV_OK && p.mode == PV_MODE_COMPAT && pv_fused_compat_supported(N, p.hop_out)) {
+    const bool want_fused = (p.mode == PV_MODE_COMPAT) ? pv_fused_compat_supported(N, p.hop_out)
+                                                       : pv_fused_corrected_supported(N, p.hop_in, p.hop_out);
+    if (rc == PV_OK && want_fused) {
         HostTables ht;
         build_tables(d.lgN, ht);
-        const std::vector<float2> *src[5] = {&ht.tw1, &ht.tw2, &ht.tw2n, &ht.itw1, &ht.itw2};
-        for (int i = 0; i < 5 && rc == PV_OK; i++) rc = upload(&h->d_ft[i], *src[i]);
+        const std::vector<float2> *src[7] = {&ht.tw1, &ht.tw2, &ht.tw2n, &ht.itw1, &ht.itw2, &ht.ctw1, &ht.ctw2};
+        for (int i = 0; i < 7 && rc == PV_OK; i++) rc = upload(&h->d_ft[i], *src[i]);
         h->ft.tw1 = h->d_ft[0];
         h->ft.tw2 = h->d_ft[1];
         h->ft.tw2n = h->d_ft[2];
         h->ft.itw1 = h->d_ft[3];
         h->ft.itw2 = h->d_ft[4];
+        h->ft.ctw1 = h->d_ft[5];
+        h->ft.ctw2 = h->d_ft[6];
         h->fused = rc == PV_OK;
-        if (h->fused) h->capacity = pv_fused_compat_capacity(N, h->sm_count);
+        if (h->fused)
+            h->capacity = (p.mode == PV_MODE_COMPAT) ? pv_fused_compat_capacity(N, h->sm_count)
+                                                     : pv_fused_corrected_capacity(N, V, h->sm_count);
     }
     if (rc != PV_OK) {
         pv_destroy(h);
@@ -437,8 +446,8 @@ int pv_process_device(pv_handle *h, const float *in, int64_t n_streams, int64_t 
     if (n_streams == 0 || n_frames == 0) return PV_OK;
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    if (h->p.mode != PV_MODE_COMPAT)
-        return fail(PV_ERR_UNSUPPORTED, "corrected mode is not available in this build yet");
+    if (h->p.mode != PV_MODE_COMPAT && !h->fused)
+        return fail(PV_ERR_UNSUPPORTED, "corrected mode needs window in {256,512,1024,2048} and an even hop_out");
     int rc = plan_segments(h, n_streams, n_frames, flags, st);
     if (rc != PV_OK) return rc;
     PvProcessArgs a{};
@@ -450,8 +459,8 @@ int pv_process_device(pv_handle *h, const float *in, int64_t n_streams, int64_t 
     a.out = out;
     a.out_stream_stride = out_stream_stride;
     a.out_voice_stride = out_voice_stride;
-    a.state = (float *)state;
-    a.state_stride = (int64_t)(pv_state_bytes(h) / sizeof(float));
+    a.state = (unsigned char *)state;
+    a.state_stride = (int64_t)pv_state_bytes(h);
     a.segs = h->d_segs;
     a.n_segs = h->n_segs;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -460,7 +469,8 @@ int pv_process_device(pv_handle *h, const float *in, int64_t n_streams, int64_t 
         PV_CUDA(cudaEventCreate(&e1));
         PV_CUDA(cudaEventRecord(e0, st));
     }
-    if (h->fused && !getenv("PV_FORCE_GENERIC")) PV_CUDA(pv_launch_compat_fused(h->dev, h->ft, a, st));
+    if (h->p.mode == PV_MODE_CORRECTED) PV_CUDA(pv_launch_corrected_fused(h->dev, h->ft, a, st));
+    else if (h->fused && !getenv("PV_FORCE_GENERIC")) PV_CUDA(pv_launch_compat_fused(h->dev, h->ft, a, st));
     else PV_CUDA(pv_launch_compat_generic(h->dev, a, st));
     h->launches++;
     if (h->timing) {

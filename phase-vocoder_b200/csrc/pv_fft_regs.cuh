@@ -16,6 +16,7 @@ static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 #define PV_LDG(p) (*(p))
 #else
 #include <cuda_runtime.h>
+#include <stdint.h>
 #define PV_DEV __device__ __forceinline__
 #define PV_LDG(p) __ldg(p)
 #endif

@@ -354,9 +354,11 @@ PV_DEV void inverse_1_tw(int t1, float2 a1, float2 a2, float2 a3, float2 (&Z)[4]
 
 // ---- inverse passes 2 and 3 + steps G/H (scale, half swap, window, overlap-add) ----
 // acc: OLA ring of N floats, pos0: ring position of sample 0 of this frame.
-template <int LOG2N, class Sync>
+// `scale` multiplies the unnormalised inverse (compat: 1/N; corrected: gain/N); `pre_last_sync` runs
+// just before the last barrier of the frame (used to complete asynchronous ring copies).
+template <int LOG2N, class Sync, class PreLast>
 PV_DEV void inverse_23_ola(int tid, const Tables &tb, float2 *bufA, float2 *bufB, float *acc, int pos0, int Hs,
-                           bool zero_frame, Sync sync)
+                           bool zero_frame, float scale, Sync sync, PreLast pre_last_sync)
 {
     using S = Shape<LOG2N>;
     constexpr int N = S::N, T = S::T, R1 = S::R1, R2 = S::R2, B3 = S::B3;
@@ -372,8 +374,8 @@ PV_DEV void inverse_23_ola(int tid, const Tables &tb, float2 *bufA, float2 *bufB
         const int i = (2 * n + N / 2) & (N - 1);       // half swap (kernel.cu:51-59)
         const float2 w = PV_LDG(reinterpret_cast<const float2 *>(tb.win + i));
         // cudaDivVec kernel.cu:130-138 (x/N == x*(1/N) exactly, N a power of two), cudaWindow :75-81
-        const float y0 = (v.x * (1.0f / (float)N)) * w.x;
-        const float y1 = (v.y * (1.0f / (float)N)) * w.y;
+        const float y0 = (v.x * scale) * w.x;
+        const float y1 = (v.y * scale) * w.y;
         float2 *slot = reinterpret_cast<float2 *>(acc + ((pos0 + i) & (N - 1)));
         float2 a = *slot;
         a.x = (i < keep ? a.x : 0.f) + y0;             // cudaOverlapAdd kernel.cu:111-119
@@ -412,6 +414,7 @@ PV_DEV void inverse_23_ola(int tid, const Tables &tb, float2 *bufA, float2 *bufB
                     bufB[(m1 + 4 * m2) * S::ILD2 + n3] = cmul(v[m2], PV_LDG(tb.itw2 + (m2 - 1) * R2 + n3));
             }
         }
+        pre_last_sync();
         sync();
     }
     // pass 3 -> time samples
@@ -477,7 +480,7 @@ PV_DEV void frame_compat(int tid, const FrameIO &io, const Tables &tb, const Thr
         hook();
         sync();
     }
-    inverse_23_ola<LOG2N>(tid, tb, bufA, bufB, acc, pos0, Hs, !io.analysed, sync);
+    inverse_23_ola<LOG2N>(tid, tb, bufA, bufB, acc, pos0, Hs, !io.analysed, 1.0f / (float)S::N, sync, []() {});
 }
 
 }  // namespace pvfused

@@ -1,0 +1,298 @@
+// pv_fused_corrected.cuh -- per-frame body of the fused CORRECTED-mode kernel.
+//
+// The reference never implemented this stage (PITCH_SHIFT is an empty case, src/phaseVocoder.h:
+// 107-111, src/main.cpp:301-303); the arithmetic is specified in DESIGN.md "corrected mode" and
+// restated by oracle/pv_oracle_impl.inc (corrected_process).  Per frame and stream:
+//
+//   forward   N-point real FFT of the windowed, zero-phase frame as an N/2-point complex FFT:
+//             radix-R1, exchange, radix-R2, exchange, radix-4 with the butterfly pair (u, B3-u) in
+//             one thread, so the real-FFT split is register-local
+//   analysis  mag = |X|, P = atan2 in turns*2^32 (uint32), D = (int32)(P - P_prev - nomA): the
+//             phase-difference unwrap is integer wrap-around; P_prev stays in registers
+//   exchange  mag[] and D[] through shared memory (the pitch map gathers across bins)
+//   per voice synthesis bin s gathers analysis bins a_lo..a_hi (pitch ratio beta), accumulates the
+//             phase psi[s] += nomS[s] + D[a_hi]*Rq in 64-bit fixed point (turns*2^64: an associative
+//             scan across frames, wrapped mod 2 pi for free), Y = m * exp(2 pi j psi); Hermitian
+//             pack, inverse N-point real FFT (same passes as the compat kernel), gain/N, half
+//             swap, window, overlap-add
+#pragma once
+#include "pv_fused_core.cuh"
+
+namespace pvfused {
+
+template <int LOG2N>
+struct CShape {
+    using S = Shape<LOG2N>;
+    static constexpr int N = S::N, T = S::T, B3 = S::B3, R1 = S::R1, R2 = S::R2;
+    static constexpr int M = N / 2;                 // complex points of the forward transform
+    static constexpr int S1 = M / R1;               // = 4*R2
+    static constexpr int LD1 = S1 + 16 / R1;
+    static constexpr int LD2 = 5;                   // exchange 2: t3*5 + n3, n3 < 4
+    static constexpr int EX1 = R1 * LD1, EX2 = B3 * LD2;
+    static constexpr int BUF_A = EX1 > S::IEX1 ? EX1 : S::IEX1;
+    static constexpr int BUF_B = EX2 > S::IEX2 ? EX2 : S::IEX2;
+    static constexpr int NB = N / 2 + 1;
+    static constexpr int C1 = S1;                   // pass-1 butterflies (radix R1)
+    static constexpr int C2 = R1 * 4;               // pass-2 butterflies (radix R2)
+    static_assert(C1 >= T || (2 * C1 == T && R1 == 16), "pass 1 cover");
+    static_assert(C2 >= T || (2 * C2 == T && R2 == 16), "pass 2 cover");
+};
+
+struct CTables {
+    const float2 *ctw1;     // [(R1-1)][S1]  W_{N/2}^{k1 t1}
+    const float2 *ctw2;     // [(R2-1)][4]   W_{S1}^{k2 n3}
+    const float2 *tw2n;     // [N]           exp(-j pi k / N)
+    const float2 *itw1;     // inverse tables, shared with the compat kernel
+    const float2 *itw2;
+    const float *win;
+    const uint32_t *nomA;   // [NB]
+    const int32_t *a_lo;    // [V][NB]
+    const int32_t *a_hi;    // [V][NB]
+    const unsigned long long *nomS;   // [V][NB]
+    unsigned long long Rq[8];
+    float scale;            // gain / N
+    int V;
+};
+
+// Cooperative ring refill: pairs [lo, N) of the frame at io.base, spread over the T threads.
+// Must be issued after a barrier that follows the last read of the replaced samples, and be
+// completed (cp_async_wait_all + barrier) before the first read of the new ones.
+template <int N, int T>
+PV_DEV void ring_prefetch_coop(int tid, const FrameIO &io, float *ring, int lo)
+{
+    for (int i = lo + 2 * tid; i < N; i += 2 * T) ring_fetch<N>(io, ring, i);
+}
+
+PV_DEV uint32_t phase_turns32(float re, float im)
+{
+    // atan2 in turns, scaled by 2^32 and rounded; the conversion wraps mod 2^32 (t in [-0.5, 0.5])
+    const float t = atan2f(im, re) * 0.15915494309189535f;
+#ifdef PV_HOST_EMUL
+    return (uint32_t)(int64_t)llrintf(t * 4294967296.0f);
+#else
+    return (uint32_t)__float2ll_rn(t * 4294967296.0f);
+#endif
+}
+
+PV_DEV float2 cis_turns64(unsigned long long psi)
+{
+    // top 32 bits as signed turns in [-0.5, 0.5)
+    const float t = (float)(int32_t)(psi >> 32) * (1.0f / 4294967296.0f);
+    float s, c;
+#ifdef PV_HOST_EMUL
+    const float ang = t * 6.283185307179586f;
+    s = sinf(ang); c = cosf(ang);
+#else
+    sincospif(2.0f * t, &s, &c);
+#endif
+    return make_float2(c, s);
+}
+
+// X[k] and X[M-k] of the N-point real spectrum (M = N/2) from a = C[k], b = C[M-k], w = W_N^k
+PV_DEV void split_both(float2 a, float2 b, float2 w, float2 &xk, float2 &xm)
+{
+    const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+    const float2 o = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));
+    const float2 t = cmul(w, o);
+    xk = make_float2(e.x + t.x, e.y + t.y);
+    xm = make_float2(e.x - t.x, -(e.y - t.y));
+}
+
+struct CState {             // per-thread registers carried across the frames of a stream
+    uint32_t Pprev[9];
+    int have_prev;
+};
+
+// bin owned by slot sl of thread u: slots 0..3 = p side (u + B3 j), 4..7 = q side (B3 - u + B3 j),
+// slot 8 = bin N/2 (thread 0 only)
+template <int B3>
+PV_DEV int slot_bin(int u, int sl)
+{
+    if (sl == 8) return 4 * B3;
+    const int j = sl & 3;
+    if (sl < 4) return (u == 0 ? 0 : u) + B3 * j;
+    return (u == 0 ? B3 / 2 : B3 - u) + B3 * j;
+}
+
+template <int LOG2N, class Sync, class Hook, class PreLast>
+PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const float *ring, float2 *bufA,
+                            float2 *bufB, float *magS, int32_t *dS, unsigned long long *psi, float *acc,
+                            CState &st, int pos0, int Hs, Sync sync, Hook hook, PreLast pre_last_sync)
+{
+    using C = CShape<LOG2N>;
+    using S = Shape<LOG2N>;
+    constexpr int N = C::N, T = C::T, B3 = C::B3, R1 = C::R1, R2 = C::R2, M = C::M, S1 = C::S1, NB = C::NB;
+    const int rbase = (int)(io.base & (N - 1));
+    auto ld = [&](int i) -> float2 {
+        float2 x;
+        if (ring != nullptr) x = *reinterpret_cast<const float2 *>(ring + ((rbase + i) & (N - 1)));
+        else {
+            const long long g = io.base + i;
+            if (io.vec_ok && g + 1 < io.n_in) x = PV_LDG(reinterpret_cast<const float2 *>(io.in + g));
+            else x = make_float2(g < io.n_in ? PV_LDG(io.in + g) : 0.f, g + 1 < io.n_in ? PV_LDG(io.in + g + 1) : 0.f);
+        }
+        const float2 w = PV_LDG(reinterpret_cast<const float2 *>(tb.win + i));
+        return make_float2(x.x * w.x, x.y * w.y);
+    };
+
+    // ---- forward pass 1: c[m] = (f[(N/2 + 2m) mod N], f[.. + 1]), m = n1*S1 + t1 ----
+    if constexpr (2 * C::C1 == T) {
+        const int t1 = tid % C::C1, half = tid / C::C1;
+        float2 v[16], o[8];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) v[n1] = ld((N / 2 + 2 * (n1 * S1 + t1)) & (N - 1));
+        if (half == 0) dft16_half<-1, false>(v, o);
+        else dft16_half<-1, true>(v, o);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int k1 = 2 * q + half;
+            float2 r = o[q];
+            if (k1 != 0) r = cmul(r, PV_LDG(tb.ctw1 + (k1 - 1) * S1 + t1));
+            bufA[k1 * C::LD1 + t1] = r;
+        }
+    } else {
+#pragma unroll
+        for (int t1 = tid; t1 < C::C1; t1 += T) {
+            float2 v[R1];
+#pragma unroll
+            for (int n1 = 0; n1 < R1; n1++) v[n1] = ld((N / 2 + 2 * (n1 * S1 + t1)) & (N - 1));
+            dft<R1, -1>(v);
+            bufA[t1] = v[0];
+#pragma unroll
+            for (int k1 = 1; k1 < R1; k1++) bufA[k1 * C::LD1 + t1] = cmul(v[k1], PV_LDG(tb.ctw1 + (k1 - 1) * S1 + t1));
+        }
+    }
+    sync();
+    hook();
+    // ---- forward pass 2: butterflies (k1, n3), radix R2 over n2 ----
+    if constexpr (2 * C::C2 == T) {
+        const int b = tid % C::C2, half = tid / C::C2;
+        const int k1 = b % R1, n3 = b / R1;
+        float2 v[16], o[8];
+#pragma unroll
+        for (int n2 = 0; n2 < 16; n2++) v[n2] = bufA[k1 * C::LD1 + n2 * 4 + n3];
+        if (half == 0) dft16_half<-1, false>(v, o);
+        else dft16_half<-1, true>(v, o);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int k2 = 2 * q + half;
+            float2 r = o[q];
+            if (k2 != 0) r = cmul(r, PV_LDG(tb.ctw2 + (k2 - 1) * 4 + n3));
+            bufB[(k1 + R1 * k2) * C::LD2 + n3] = r;
+        }
+    } else {
+#pragma unroll
+        for (int b = tid; b < C::C2; b += T) {
+            const int k1 = b % R1, n3 = b / R1;
+            float2 v[R2];
+#pragma unroll
+            for (int n2 = 0; n2 < R2; n2++) v[n2] = bufA[k1 * C::LD1 + n2 * 4 + n3];
+            dft<R2, -1>(v);
+            bufB[k1 * C::LD2 + n3] = v[0];
+#pragma unroll
+            for (int k2 = 1; k2 < R2; k2++)
+                bufB[(k1 + R1 * k2) * C::LD2 + n3] = cmul(v[k2], PV_LDG(tb.ctw2 + (k2 - 1) * 4 + n3));
+        }
+    }
+    sync();
+    // ---- forward pass 3 (radix 4, paired) + real-FFT split ----
+    const int u = tid;
+    const int tP = u, tQ = (u == 0) ? B3 / 2 : B3 - u;
+    float2 P[4], Q[4];
+#pragma unroll
+    for (int n3 = 0; n3 < 4; n3++) {
+        P[n3] = bufB[tP * C::LD2 + n3];
+        Q[n3] = bufB[tQ * C::LD2 + n3];
+    }
+    dft<4, -1>(P);
+    dft<4, -1>(Q);
+    float2 X[9];                         // by slot
+    float2 wp[4];                        // W_N^{bin of p-side slot j}; reused by the Hermitian pack
+    if (u != 0) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            wp[j] = PV_LDG(tb.tw2n + 2 * (u + B3 * j));
+            split_both(P[j], Q[3 - j], wp[j], X[j], X[4 + (3 - j)]);
+        }
+        X[8] = make_float2(0.f, 0.f);
+    } else {
+        X[0] = make_float2(P[0].x + P[0].y, 0.f);
+        X[8] = make_float2(P[0].x - P[0].y, 0.f);
+        float2 dummy;
+        split_both(P[1], P[3], PV_LDG(tb.tw2n + 2 * B3), X[1], X[3]);
+        split_both(P[2], P[2], make_float2(0.f, -1.f), X[2], dummy);
+        split_both(Q[0], Q[3], PV_LDG(tb.tw2n + B3), X[4], X[7]);
+        split_both(Q[1], Q[2], PV_LDG(tb.tw2n + 3 * B3), X[5], X[6]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) wp[j] = make_float2(1.f, 0.f);   // unused
+    }
+    // ---- analysis: magnitude, phase (turns*2^32), unwrapped phase difference ----
+    const bool first = st.have_prev == 0;
+#pragma unroll
+    for (int sl = 0; sl < 9; sl++) {
+        if (sl == 8 && u != 0) break;
+        const int bin = slot_bin<B3>(u, sl);
+        const float2 x = X[sl];
+        const uint32_t Pc = phase_turns32(x.x, x.y);
+        magS[bin] = sqrtf(x.x * x.x + x.y * x.y);
+        dS[bin] = first ? (int32_t)Pc : (int32_t)(Pc - st.Pprev[sl] - PV_LDG(tb.nomA + bin));
+        st.Pprev[sl] = Pc;
+    }
+    st.have_prev = 1;
+    sync();
+    // ---- synthesis, one voice at a time ----
+    for (int v = 0; v < tb.V; v++) {
+        const int32_t *alo = tb.a_lo + v * NB, *ahi = tb.a_hi + v * NB;
+        const unsigned long long *nomS = tb.nomS + (size_t)v * NB;
+        unsigned long long *ps = psi + (size_t)v * NB;
+        const unsigned long long Rq = tb.Rq[v];
+        float2 Y[9];
+#pragma unroll
+        for (int sl = 0; sl < 9; sl++) {
+            Y[sl] = make_float2(0.f, 0.f);
+            if (sl == 8 && u != 0) break;
+            const int s = slot_bin<B3>(u, sl);
+            const int lo = PV_LDG(alo + s), hi = PV_LDG(ahi + s);
+            if (lo > hi) continue;                       // no analysis bin maps here
+            float m = 0.f;
+            for (int a = lo; a <= hi; a++) m += magS[a];
+            const int32_t d = dS[hi];
+            unsigned long long p;
+            if (first) p = (unsigned long long)(uint32_t)d << 32;
+            else p = ps[s] + PV_LDG(nomS + s) + (unsigned long long)((long long)d * (long long)Rq);
+            ps[s] = p;
+            const float2 cs = cis_turns64(p);
+            Y[sl] = make_float2(m * cs.x, m * cs.y);
+        }
+        // Hermitian pack (same register pattern as the compat kernel); exp(+2 pi i k/N) = conj(W_N^k)
+        float2 Zp[4], Zq[4];
+        if (u != 0) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                // q-side bin (B3-u)+B3 j = M - (u + B3(3-j)): W_N^{M-k} = -conj(W_N^k)
+                const float2 wq = make_float2(-wp[3 - j].x, wp[3 - j].y);
+                Zp[j] = herm_pack(Y[j], Y[4 + (3 - j)], cconj(wp[j]));
+                Zq[j] = herm_pack(Y[4 + j], Y[3 - j], cconj(wq));
+            }
+        } else {
+            Y[0].y = 0.f;
+            Y[8].y = 0.f;
+            const float2 Yp4[5] = {Y[0], Y[1], Y[2], Y[3], Y[8]};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float2 w0 = (j == 0) ? make_float2(1.f, 0.f) : cconj(PV_LDG(tb.tw2n + 2 * B3 * j));
+                Zp[j] = herm_pack(Yp4[j], Yp4[4 - j], w0);
+                Zq[j] = herm_pack(Y[4 + j], Y[4 + (3 - j)], cconj(PV_LDG(tb.tw2n + B3 + 2 * B3 * j)));
+            }
+        }
+        Tables itb{nullptr, nullptr, tb.tw2n, tb.itw1, tb.itw2, tb.win};
+        inverse_1<LOG2N>(tP, itb, Zp, bufA);
+        inverse_1<LOG2N>(tQ, itb, Zq, bufA);
+        inverse_23_ola<LOG2N>(tid, itb, bufA, bufB, acc + (size_t)v * N, pos0, Hs, false, tb.scale, sync,
+                              [&]() { if (v + 1 == tb.V) pre_last_sync(); });
+        (void)S::T;
+    }
+    (void)M;
+}
+
+}  // namespace pvfused

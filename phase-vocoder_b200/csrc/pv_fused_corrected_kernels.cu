@@ -1,0 +1,214 @@
+// pv_fused_corrected_kernels.cu -- fused CORRECTED-mode stream kernel (windows 256..2048).
+//
+// Same work decomposition as the compat kernel: a group of T = N/16 threads walks the frames of
+// one stream segment; the stream state (previous analysis phase in registers, 64-bit phase
+// accumulators and the per-voice overlap-add rings in shared memory) never leaves the SM between
+// frames.  HBM traffic per frame: 4*Ha bytes in, 4*V*Hs bytes out.
+#include <cstdlib>
+
+#include "pv_fused_corrected.cuh"
+#include "pv_internal.h"
+
+namespace {
+
+using namespace pvfused;
+
+template <int LOG2N>
+struct CLaunch {
+    using C = CShape<LOG2N>;
+    static constexpr int T = C::T;
+    static constexpr int G = (T >= 128) ? 1 : 128 / T;
+    static constexpr int THREADS = T * G;
+    // per group: exchange buffers | psi (u64) | mag | D | acc[V] | ring
+    static size_t group_bytes(int V)
+    {
+        return (size_t)(C::BUF_A + C::BUF_B) * sizeof(float2) + (size_t)V * ((C::NB + 1) & ~1) * 8 +
+               (size_t)((C::NB + 3) & ~3) * 4 * 2 + (size_t)V * C::N * 4 + (size_t)C::N * 4;
+    }
+};
+
+template <int T, int G>
+struct CGroupSync {
+    int g;
+    unsigned mask;
+    __device__ __forceinline__ void operator()() const
+    {
+        if constexpr (G == 1) __syncthreads();
+        else if constexpr (T >= 32) asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(T) : "memory");
+        else __syncwarp(mask);
+    }
+};
+
+template <int LOG2N, int MINB>
+__global__ void __launch_bounds__(CLaunch<LOG2N>::THREADS, MINB)
+corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int vec_out_ok, int use_ring,
+                       unsigned group_bytes)
+{
+    using C = CShape<LOG2N>;
+    using L = CLaunch<LOG2N>;
+    constexpr int N = C::N, T = C::T, G = L::G, NB = C::NB, B3 = C::B3;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int g = threadIdx.x / T, tid = threadIdx.x % T;
+    const int seg_idx = blockIdx.x * G + g;
+    if (seg_idx >= a.n_segs) return;
+    const int V = tb.V;
+
+    unsigned char *base = smem_raw + (size_t)g * group_bytes;
+    float2 *bufA = reinterpret_cast<float2 *>(base);
+    float2 *bufB = bufA + C::BUF_A;
+    unsigned long long *psi = reinterpret_cast<unsigned long long *>(bufB + C::BUF_B);
+    float *magS = reinterpret_cast<float *>(psi + (size_t)V * ((NB + 1) & ~1));
+    int32_t *dS = reinterpret_cast<int32_t *>(magS + ((NB + 3) & ~3));
+    float *acc = reinterpret_cast<float *>(dS + ((NB + 3) & ~3));
+    float *ring = use_ring ? acc + (size_t)V * N : nullptr;
+    unsigned long long *psi_v0 = psi;      // voice stride in psi is NB (kernel body) -> keep packed
+    (void)psi_v0;
+
+    CGroupSync<T, G> sync{g, T >= 32 ? 0xffffffffu : (((1u << (T & 31)) - 1u) << ((threadIdx.x & 31) / T * T))};
+
+    const PvSegment seg = a.segs[seg_idx];
+    const float *in = a.in + seg.stream * a.in_stride;
+    float *out = a.out + seg.stream * a.out_stream_stride;
+    unsigned char *state = a.state ? a.state + seg.stream * a.state_stride : nullptr;
+    const int Hs = d.Hs;
+
+    // state layout: [have_prev u32][pad][P_prev u32 x NB (8-byte padded)][psi u64 x V*NB][acc f32 x V*N]
+    uint32_t *st_hdr = reinterpret_cast<uint32_t *>(state);
+    uint32_t *st_P = st_hdr ? st_hdr + 2 : nullptr;
+    unsigned long long *st_psi = state ? reinterpret_cast<unsigned long long *>(state + 8 + ((NB * 4 + 7) / 8) * 8) : nullptr;
+    float *st_acc = st_psi ? reinterpret_cast<float *>(st_psi + (size_t)V * NB) : nullptr;
+
+    CState st;
+    st.have_prev = 0;
+#pragma unroll
+    for (int sl = 0; sl < 9; sl++) st.Pprev[sl] = 0;
+    const bool cin = seg.carry_in && state;
+    if (cin) {
+        st.have_prev = (int)st_hdr[0];
+#pragma unroll
+        for (int sl = 0; sl < 9; sl++)
+            if (sl < 8 || tid == 0) st.Pprev[sl] = st_P[slot_bin<B3>(tid, sl)];
+    }
+    for (int i = tid; i < V * NB; i += T) psi[i] = cin ? st_psi[i] : 0ull;
+    for (int i = tid; i < V * N; i += T) {
+        const int ii = i & (N - 1);
+        acc[i] = (cin && ii + Hs < N) ? st_acc[i + Hs] : 0.f;
+    }
+    if (use_ring) {
+        FrameIO io0{in, a.n_in, seg.k_begin * (long long)d.Ha, true, true};
+        ring_prefetch_coop<N, T>(tid, io0, ring, 0);
+        cp_async_wait_all();
+    }
+    sync();
+
+    auto emit = [&](long long kk, int pp) {
+        if (kk < seg.k_emit) return;
+        for (int v = 0; v < V; v++) {
+            float *o = out + v * a.out_voice_stride + kk * (long long)Hs;
+            const float *ac = acc + (size_t)v * N;
+            if (vec_out_ok) {
+                for (int j = 4 * tid; j < Hs; j += 4 * T)
+                    *reinterpret_cast<float4 *>(o + j) = *reinterpret_cast<const float4 *>(ac + ((pp + j) & (N - 1)));
+            } else {
+                for (int j = tid; j < Hs; j += T) o[j] = ac[(pp + j) & (N - 1)];
+            }
+        }
+    };
+
+    int pos0 = 0;
+    for (long long k = seg.k_begin; k < seg.k_end; ++k) {
+        FrameIO io{in, a.n_in, k * (long long)d.Ha, true, vec_in_ok != 0};
+        auto hook = [&]() {
+            if (use_ring && k + 1 < seg.k_end) {
+                FrameIO nx{in, a.n_in, (k + 1) * (long long)d.Ha, true, true};
+                ring_prefetch_coop<N, T>(tid, nx, ring, N - d.Ha);
+            }
+            if (k > seg.k_begin) emit(k - 1, (pos0 - Hs) & (N - 1));
+        };
+        frame_corrected<LOG2N>(tid, io, tb, ring, bufA, bufB, magS, dS, psi, acc, st, pos0, Hs, sync, hook,
+                               [&]() { if (use_ring) cp_async_wait_all(); });
+        pos0 = (pos0 + Hs) & (N - 1);
+    }
+    sync();
+    const int plast = (pos0 - Hs) & (N - 1);
+    emit(seg.k_end - 1, plast);
+    if (seg.carry_out && state) {
+        if (tid == 0) { st_hdr[0] = (uint32_t)st.have_prev; st_hdr[1] = 0; }
+#pragma unroll
+        for (int sl = 0; sl < 9; sl++)
+            if (sl < 8 || tid == 0) st_P[slot_bin<B3>(tid, sl)] = st.Pprev[sl];
+        for (int i = tid; i < V * NB; i += T) st_psi[i] = psi[i];
+        for (int i = tid; i < V * N; i += T) st_acc[i] = acc[(i & ~(N - 1)) + ((plast + i) & (N - 1))];
+    }
+}
+
+template <int LOG2N, int MINB>
+cudaError_t claunch(const PvDev &d, const CTables &tb, const PvProcessArgs &a, cudaStream_t st)
+{
+    using L = CLaunch<LOG2N>;
+    auto kern = corrected_fused_kernel<LOG2N, MINB>;
+    const bool in_ok = (d.Ha % 2 == 0) && (a.in_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 7) == 0);
+    const bool out_ok = (d.Hs % 4 == 0) && (a.out_stream_stride % 4 == 0) && (a.out_voice_stride % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
+    const bool ring = in_ok && d.Ha <= d.N;
+    const size_t gb = L::group_bytes(tb.V);
+    const size_t smem = gb * L::G;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    const int grid = (a.n_segs + L::G - 1) / L::G;
+    kern<<<grid, L::THREADS, smem, st>>>(d, tb, a, in_ok, out_ok, ring, (unsigned)gb);
+    return cudaGetLastError();
+}
+
+template <int LOG2N, int MINB>
+int ccapacity(int V, int sm_count)
+{
+    using L = CLaunch<LOG2N>;
+    auto kern = corrected_fused_kernel<LOG2N, MINB>;
+    const size_t smem = L::group_bytes(V) * L::G;
+    int nb = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, L::THREADS, smem) != cudaSuccess || nb < 1)
+        nb = 1;
+    return nb * sm_count * L::G;
+}
+
+}  // namespace
+
+bool pv_fused_corrected_supported(int N, int Ha, int Hs)
+{
+    (void)Ha;
+    return (N == 256 || N == 512 || N == 1024 || N == 2048) && (Hs % 2) == 0;
+}
+
+int pv_fused_corrected_capacity(int N, int V, int sm_count)
+{
+    switch (N) {
+        case 256: return ccapacity<8, 1>(V, sm_count);
+        case 512: return ccapacity<9, 1>(V, sm_count);
+        case 1024: return ccapacity<10, 1>(V, sm_count);
+        case 2048: return ccapacity<11, 1>(V, sm_count);
+        default: return sm_count;
+    }
+}
+
+cudaError_t pv_launch_corrected_fused(const PvDev &d, const PvFusedTables &t, const PvProcessArgs &a, cudaStream_t st)
+{
+    if (a.n_segs <= 0) return cudaSuccess;
+    CTables tb{};
+    tb.ctw1 = t.ctw1; tb.ctw2 = t.ctw2; tb.tw2n = t.tw2n; tb.itw1 = t.itw1; tb.itw2 = t.itw2;
+    tb.win = d.win; tb.nomA = d.nomA; tb.a_lo = d.a_lo; tb.a_hi = d.a_hi;
+    tb.nomS = reinterpret_cast<const unsigned long long *>(d.nomS);
+    for (int v = 0; v < d.V; v++) tb.Rq[v] = d.Rq[v];
+    tb.scale = d.gain / (float)d.N;
+    tb.V = d.V;
+    switch (d.N) {
+        case 256: return claunch<8, 1>(d, tb, a, st);
+        case 512: return claunch<9, 1>(d, tb, a, st);
+        case 1024: return claunch<10, 1>(d, tb, a, st);
+        case 2048: return claunch<11, 1>(d, tb, a, st);
+        default: return cudaErrorInvalidValue;
+    }
+}

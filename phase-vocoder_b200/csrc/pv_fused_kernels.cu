@@ -63,7 +63,7 @@ compat_fused_kernel(PvDev d, Tables tb, PvProcessArgs a, int vec_in_ok, int vec_
     const PvSegment seg = a.segs[seg_idx];
     const float *in = a.in + seg.stream * a.in_stride;
     float *out = a.out + seg.stream * a.out_stream_stride;
-    float *state = a.state ? a.state + seg.stream * a.state_stride : nullptr;
+    float *state = a.state ? reinterpret_cast<float *>(a.state + seg.stream * a.state_stride) : nullptr;
     const int Hs = d.Hs;
     const bool nan_compat = (d.flags & PV_FLAG_NAN_COMPAT) != 0;
 

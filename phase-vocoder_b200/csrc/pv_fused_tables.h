@@ -11,6 +11,7 @@
 
 struct HostTables {
     std::vector<float2> tw1, tw2, tw2n, itw1, itw2;
+    std::vector<float2> ctw1, ctw2;          // corrected-mode forward (N/2 complex points)
 };
 
 inline float2 pv_cis(double turns)   // exp(j * 2*pi * turns)
@@ -37,6 +38,14 @@ inline void build_tables(int log2n, HostTables &t)
     t.itw1.resize((size_t)3 * B3);
     for (int m1 = 1; m1 < 4; m1++)
         for (int t1 = 0; t1 < B3; t1++) t.itw1[(size_t)(m1 - 1) * B3 + t1] = pv_cis((double)(m1 * t1) / (N / 2));
+    // corrected forward: M = N/2 = R1*R2*4, S1c = M/R1 = 4*R2
+    const int M = N / 2, S1c = M / R1;
+    t.ctw1.resize((size_t)(R1 - 1) * S1c);
+    for (int k1 = 1; k1 < R1; k1++)
+        for (int t1 = 0; t1 < S1c; t1++) t.ctw1[(size_t)(k1 - 1) * S1c + t1] = pv_cis(-(double)((long)k1 * t1 % M) / M);
+    t.ctw2.resize((size_t)(R2 - 1) * 4);
+    for (int k2 = 1; k2 < R2; k2++)
+        for (int n3 = 0; n3 < 4; n3++) t.ctw2[(size_t)(k2 - 1) * 4 + n3] = pv_cis(-(double)(k2 * n3) / S1c);
     t.itw2.resize((size_t)(R1 - 1) * R2);
     for (int m2 = 1; m2 < R1; m2++)
         for (int n3 = 0; n3 < R2; n3++) t.itw2[(size_t)(m2 - 1) * R2 + n3] = pv_cis((double)(m2 * n3) / B3);

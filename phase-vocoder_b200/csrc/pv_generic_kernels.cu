@@ -229,7 +229,7 @@ compat_generic_kernel(PvDev d, PvProcessArgs a)
     const PvSegment seg = a.segs[blockIdx.x];
     const float *in = a.in + seg.stream * a.in_stride;
     float *out = a.out + seg.stream * a.out_stream_stride;
-    float *state = a.state ? a.state + seg.stream * a.state_stride : nullptr;
+    float *state = a.state ? reinterpret_cast<float *>(a.state + seg.stream * a.state_stride) : nullptr;
 
     for (int i = threadIdx.x; i < N; i += blockDim.x)
         acc[i] = (seg.carry_in && state && i + d.Hs < N) ? state[i + d.Hs] : 0.f;

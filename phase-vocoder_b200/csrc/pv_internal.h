@@ -40,8 +40,8 @@ struct PvProcessArgs {
     int64_t in_stride, n_in, n_analysed, n_frames;
     float *out;
     int64_t out_stream_stride, out_voice_stride;
-    float *state;         // per-stream state (floats), stride state_stride
-    int64_t state_stride;
+    unsigned char *state; // per-stream carried state, pv_state_bytes() each
+    int64_t state_stride; // bytes
     const PvSegment *segs;
     int32_t n_segs;
 };
@@ -49,6 +49,7 @@ struct PvProcessArgs {
 // Device copies of the fused kernels' twiddle tables (pv_fused_tables.h).
 struct PvFusedTables {
     const float2 *tw1 = nullptr, *tw2 = nullptr, *tw2n = nullptr, *itw1 = nullptr, *itw2 = nullptr;
+    const float2 *ctw1 = nullptr, *ctw2 = nullptr;
 };
 
 // ---- launchers (defined in the .cu files) ----
@@ -56,6 +57,9 @@ bool pv_fused_compat_supported(int N, int Hs);
 // number of segment groups that can be resident on the device at once
 int pv_fused_compat_capacity(int N, int sm_count);
 cudaError_t pv_launch_compat_fused(const PvDev &d, const PvFusedTables &t, const PvProcessArgs &a, cudaStream_t st);
+bool pv_fused_corrected_supported(int N, int Ha, int Hs);
+int pv_fused_corrected_capacity(int N, int V, int sm_count);
+cudaError_t pv_launch_corrected_fused(const PvDev &d, const PvFusedTables &t, const PvProcessArgs &a, cudaStream_t st);
 cudaError_t pv_launch_analysis_batch(const PvDev &d, const float *in, int64_t n_in, int64_t n_frames,
                                      float *out_magphase, cudaStream_t st);
 cudaError_t pv_launch_resynthesis_batch(const PvDev &d, const float *spectra, int64_t n_frames,

@@ -121,8 +121,8 @@ class PhaseVocoder:
         _check(load().pv_window_table(self._h, self.imp.ctypes.data))
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h:
-            load().pv_destroy(self._h)
+        if getattr(self, "_h", None) is not None and self._h and _lib is not None:
+            _lib.pv_destroy(self._h)
             self._h = C.c_void_p()
 
     __del__ = close

@@ -74,3 +74,82 @@ extern "C" int emul_compat(int log2n, const float *x, long n_in, int Ha, int Hs,
         default: return -1;
     }
 }
+
+// ---------------- corrected mode ----------------
+#include "../../phase-vocoder_b200/csrc/pv_fused_corrected.cuh"
+
+template <int LOG2N>
+static int run_corrected(const float *x, long n_in, int Ha, int Hs, const float *win, int V, const uint32_t *nomA,
+                         const int32_t *a_lo, const int32_t *a_hi, const unsigned long long *nomS,
+                         const unsigned long long *Rq, float gain, long n_frames, float *out, long out_stride)
+{
+    using C = CShape<LOG2N>;
+    constexpr int N = C::N, T = C::T, NB = C::NB;
+    HostTables ht;
+    build_tables(LOG2N, ht);
+    CTables tb{};
+    tb.ctw1 = ht.ctw1.data(); tb.ctw2 = ht.ctw2.data(); tb.tw2n = ht.tw2n.data();
+    tb.itw1 = ht.itw1.data(); tb.itw2 = ht.itw2.data(); tb.win = win;
+    tb.nomA = nomA; tb.a_lo = a_lo; tb.a_hi = a_hi; tb.nomS = nomS;
+    for (int v = 0; v < V; v++) tb.Rq[v] = Rq[v];
+    tb.scale = gain / (float)N;
+    tb.V = V;
+    std::vector<float2> bufA(C::BUF_A), bufB(C::BUF_B);
+    std::vector<float> acc((size_t)V * N, 0.f), ringbuf(N, 0.f), magS(NB);
+    std::vector<int32_t> dS(NB);
+    std::vector<unsigned long long> psi((size_t)V * NB, 0ull);
+    std::barrier bar(T);
+    const bool use_ring = (Ha % 2) == 0 && Ha <= N;
+    float *ring = use_ring ? ringbuf.data() : nullptr;
+    auto body = [&](int tid) {
+        auto sync = [&]() { bar.arrive_and_wait(); };
+        CState st{};
+        int pos0 = 0;
+        if (use_ring) {
+            FrameIO io0{x, n_in, 0, true, true};
+            ring_prefetch_coop<N, T>(tid, io0, ring, 0);
+            cp_async_wait_all();
+        }
+        sync();
+        for (long k = 0; k < n_frames; k++) {
+            FrameIO io{x, n_in, k * (long long)Ha, true, (Ha % 2) == 0};
+            auto hook = [&]() {
+                if (use_ring && k + 1 < n_frames) {
+                    FrameIO nx{x, n_in, (k + 1) * (long long)Ha, true, true};
+                    ring_prefetch_coop<N, T>(tid, nx, ring, N - Ha);
+                }
+                if (k > 0) {
+                    const int pp = (pos0 - Hs) & (N - 1);
+                    for (int v = 0; v < V; v++)
+                        for (int j = tid; j < Hs; j += T)
+                            out[v * out_stride + (k - 1) * (long)Hs + j] = acc[(size_t)v * N + ((pp + j) & (N - 1))];
+                }
+            };
+            frame_corrected<LOG2N>(tid, io, tb, ring, bufA.data(), bufB.data(), magS.data(), dS.data(), psi.data(),
+                                   acc.data(), st, pos0, Hs, sync, hook, [&]() { cp_async_wait_all(); });
+            pos0 = (pos0 + Hs) & (N - 1);
+        }
+        sync();
+        const int pp = (pos0 - Hs) & (N - 1);
+        for (int v = 0; v < V; v++)
+            for (int j = tid; j < Hs; j += T)
+                out[v * out_stride + (n_frames - 1) * (long)Hs + j] = acc[(size_t)v * N + ((pp + j) & (N - 1))];
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) th.emplace_back(body, t);
+    for (auto &t : th) t.join();
+    return 0;
+}
+
+extern "C" int emul_corrected(int log2n, const float *x, long n_in, int Ha, int Hs, const float *win, int V,
+                              const uint32_t *nomA, const int32_t *a_lo, const int32_t *a_hi,
+                              const unsigned long long *nomS, const unsigned long long *Rq, float gain, long n_frames,
+                              float *out, long out_stride)
+{
+#define RC(L) case L: return run_corrected<L>(x, n_in, Ha, Hs, win, V, nomA, a_lo, a_hi, nomS, Rq, gain, n_frames, out, out_stride)
+    switch (log2n) {
+        RC(8); RC(9); RC(10); RC(11);
+        default: return -1;
+    }
+#undef RC
+}

@@ -42,3 +42,33 @@ def test_fused_body_matches_oracle(emul, N, Ha, Hs, nf):
     assert rc == 0
     want, _ = po.process_compat(x, N, Ha, Hs, win, nf - 1, nf)
     assert snr_db(want, out) > 100, snr_db(want, out)
+
+
+@pytest.mark.parametrize("N,Ha,Hs,betas,nf", [
+    (256, 64, 64, [1.0], 30), (256, 64, 64, [1.0, 2 ** (4 / 12), 2 ** (7 / 12), 2.0], 30),
+    (512, 128, 128, [1.5], 16), (1024, 102, 512, [1.0], 12), (2048, 512, 512, [2 ** (7 / 12)], 9),
+    (2048, 512, 512, [0.75, 1.0], 7),
+])
+def test_corrected_body_matches_oracle(emul, N, Ha, Hs, betas, nf):
+    emul.emul_corrected.argtypes = [C.c_int, C.POINTER(C.c_float), C.c_long, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                    C.c_long, C.POINTER(C.c_float), C.c_long]
+    n_in = N + (nf - 1) * Ha - 3
+    x = multitone(n_in, seed=N + Ha)
+    win = po.window(po.WIN_HANN_PERIODIC, N)
+    V = len(betas)
+    tabs = [po.corrected_tables(N, Ha, Hs, b) for b in betas]
+    a_lo = np.concatenate([t["a_lo"] for t in tabs]).astype(np.int32)
+    a_hi = np.concatenate([t["a_hi"] for t in tabs]).astype(np.int32)
+    nomS = np.concatenate([t["nomS"] for t in tabs]).astype(np.uint64)
+    Rq = np.array([t["Rq"] for t in tabs], np.uint64)
+    nomA = tabs[0]["nomA"]
+    out = np.zeros((V, nf * Hs), np.float32)
+    fp = C.POINTER(C.c_float)
+    rc = emul.emul_corrected(int(np.log2(N)), x.ctypes.data_as(fp), n_in, Ha, Hs, win.ctypes.data_as(fp), V,
+                             nomA.ctypes.data, a_lo.ctypes.data, a_hi.ctypes.data, nomS.ctypes.data, Rq.ctypes.data,
+                             po.corrected_gain(win, Hs), nf, out.ctypes.data_as(fp), nf * Hs)
+    assert rc == 0
+    want, _ = po.process_corrected(x, N, Ha, Hs, win, betas, nf)
+    for v in range(V):
+        assert snr_db(want[v], out[v]) > 100, (v, snr_db(want[v], out[v]))

@@ -167,3 +167,18 @@ def test_corrected_aggregate_reproduces_phase_carry():
     want = (P0[a].astype(np.uint64) << np.uint64(32)) + np.uint64(K - 1) * t["nomS"][ok] \
         + (sumD[a] * np.int64(t["Rq"])).astype(np.uint64)
     assert np.array_equal(st.psi[0][ok], want)
+
+
+def test_unwrap_conditioning_f32_vs_f64_oracle():
+    """DESIGN.md "conditioning of the phase unwrap": the fp32 and fp64 variants of the SAME oracle agree
+    to > 100 dB for integer R but can unwrap weak bins differently when R is fractional."""
+    N, Ha, Hs, nf = 1024, 256, 256, 60
+    win = po.window(po.WIN_HANN_PERIODIC, N)
+    tonal = multitone(N + nf * Ha, seed=7, noise=0.0)
+    a, _ = po.process_corrected(tonal, N, Ha, Hs, win, [1.4983], nf, precision=64)
+    b, _ = po.process_corrected(tonal, N, Ha, Hs, win, [1.4983], nf, precision=32)
+    assert snr_db(a[0], b[0]) > 60           # fractional R: unwrap flips on weak bins are possible
+    noisy = multitone(N + nf * Ha, seed=7, noise=1e-3)
+    a, _ = po.process_corrected(noisy, N, Ha, Hs, win, [2.0], nf, precision=64)      # integer R
+    b, _ = po.process_corrected(noisy, N, Ha, Hs, win, [2.0], nf, precision=32)
+    assert snr_db(a[0], b[0]) > 100
