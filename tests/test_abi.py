@@ -2,6 +2,7 @@
 include/pv_b200.h declares (no compute calls: there is no GPU here and no CPU fallback)."""
 import os
 import re
+import subprocess
 
 import pytest
 
@@ -37,11 +38,17 @@ def test_no_cpu_fallback_without_device():
 
 
 def test_product_never_imports_oracle():
-    """The oracle is test infrastructure: nothing under phase-vocoder_b200/ or include/ may name it."""
+    """The oracle is test infrastructure: nothing under phase-vocoder_b200/ or include/ may include,
+    import, load or link it (comments that cite it as the specification are fine)."""
+    bad = re.compile(r'#\s*include\s*[<"][^>"]*oracle|import\s+pv_oracle|from\s+pv_oracle|import\s+wav_oracle|'
+                     r'libpv_oracle|CDLL\([^)]*oracle|-lpv_oracle')
     for base in ("phase-vocoder_b200", "include"):
         for dp, _, fs in os.walk(os.path.join(ROOT, base)):
             for f in fs:
                 if f.endswith((".so", ".o", ".log", ".pyc")):
                     continue
                 txt = open(os.path.join(dp, f), errors="ignore").read()
-                assert "pv_oracle" not in txt or "oracle/pv_oracle.h" in txt and f.endswith(".cu"), f
+                assert not bad.search(txt), os.path.join(dp, f)
+    # and the built library has no undefined pvo_* symbols
+    out = subprocess.run(["nm", "-D", pvb200.LIB_PATH], capture_output=True, text=True).stdout
+    assert "pvo_" not in out
