@@ -14,6 +14,8 @@
 #include "pv_oracle.h"
 
 typedef struct job {
+    int corrected;
+    double beta;
     const float *x;
     long n_streams, n_in, n_frames;
     int N, Ha, Hs;
@@ -26,16 +28,33 @@ typedef struct job {
 static void *worker(void *arg)
 {
     job *j = (job *)arg;
+    const int nb = j->N / 2 + 1;
     float *back = (float *)malloc(sizeof(float) * (size_t)j->N);
+    uint32_t *P = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)nb);
+    uint64_t *psi = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)nb);
+    double *tail = (double *)malloc(sizeof(double) * (size_t)j->N);
+    double *dout = j->corrected ? (double *)malloc(sizeof(double) * (size_t)(j->n_frames * j->Hs)) : NULL;
     for (;;) {
         long s = atomic_fetch_add(&j->next, 1);
         if (s >= j->n_streams) break;
-        memset(back, 0, sizeof(float) * (size_t)j->N);
-        int r = pvo_process_compat_f32(j->x + s * j->n_in, j->n_in, j->N, j->Ha, j->Hs, j->win, j->n_frames, 0,
+        int r;
+        if (!j->corrected) {
+            memset(back, 0, sizeof(float) * (size_t)j->N);
+            r = pvo_process_compat_f32(j->x + s * j->n_in, j->n_in, j->N, j->Ha, j->Hs, j->win, j->n_frames, 0,
                                        j->n_frames, 0, back, j->out + s * j->n_frames * (long)j->Hs);
+        } else {
+            pvo_corrected_state st = {0, P, psi, tail};
+            memset(P, 0, sizeof(uint32_t) * (size_t)nb);
+            memset(psi, 0, sizeof(uint64_t) * (size_t)nb);
+            memset(tail, 0, sizeof(double) * (size_t)j->N);
+            r = pvo_process_corrected(j->x + s * j->n_in, j->n_in, j->N, j->Ha, j->Hs, j->win, 1, &j->beta,
+                                      j->n_frames, &st, 32, dout, j->n_frames * (long)j->Hs);
+            float *o = j->out + s * j->n_frames * (long)j->Hs;
+            for (long i = 0; i < j->n_frames * (long)j->Hs; i++) o[i] = (float)dout[i];
+        }
         if (r) atomic_store(&j->rc, r);
     }
-    free(back);
+    free(back); free(P); free(psi); free(tail); free(dout);
     return NULL;
 }
 
@@ -45,13 +64,14 @@ int pvo_bench_threads(void)
     return n > 0 ? (int)n : 1;
 }
 
-/* x: [n_streams][n_in], out: [n_streams][n_frames*Hs]; n_threads <= 0: all online cores. */
-int pvo_bench_compat_f32(const float *x, long n_streams, long n_in, int N, int Ha, int Hs, const float *win,
-                         long n_frames, float *out, int n_threads)
+/* x: [n_streams][n_in], out: [n_streams][n_frames*Hs]; n_threads <= 0: all online cores.
+ * corrected != 0: one voice with pitch ratio beta (f32 arithmetic), else the compat pipeline. */
+int pvo_bench_f32(int corrected, double beta, const float *x, long n_streams, long n_in, int N, int Ha, int Hs,
+                  const float *win, long n_frames, float *out, int n_threads)
 {
     if (n_threads <= 0) n_threads = pvo_bench_threads();
     if (n_threads > n_streams) n_threads = (int)n_streams;
-    job j = {x, n_streams, n_in, n_frames, N, Ha, Hs, win, out, 0, 0};
+    job j = {corrected, beta, x, n_streams, n_in, n_frames, N, Ha, Hs, win, out, 0, 0};
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_threads);
     for (int i = 0; i < n_threads; i++) pthread_create(&th[i], NULL, worker, &j);
     for (int i = 0; i < n_threads; i++) pthread_join(th[i], NULL);
