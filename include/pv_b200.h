@@ -8,6 +8,9 @@
  * message retrievable with pv_last_error() (the reference prints and exit()s instead:
  * checkCUDAError_, src/io.cpp:115-124 -- the C++ shim host/phaseVocoder.h restores that).
  *
+ * A pv_handle is NOT thread-safe (it caches its segment plan and staging buffers; the reference's
+ * class is not re-entrant either, karnel/kernel.cu:170-174): use one handle per host thread.
+ *
  * There is no CPU fallback: every call needs a CUDA device of compute capability 10.x and
  * fails with PV_ERR_CUDA otherwise.
  *
@@ -150,6 +153,34 @@ int pv_process_device(pv_handle *h, const float *in, int64_t n_streams, int64_t 
                       int64_t n_in, int64_t n_analysed, int64_t n_frames, float *out,
                       int64_t out_stream_stride, int64_t out_voice_stride, void *state,
                       int32_t flags, void *cuda_stream);
+
+/* pv_process_device with `skip_frames` leading frames computed but NOT written: frame k of the call
+ * (k >= skip_frames) lands at out[(k - skip_frames)*Hs ..].  This is how a frame range [k0, k1) of a
+ * longer stream is produced on its own (another GPU, another call): pass the input from frame
+ * k0 - halo, halo = (N-1)/Hs, and skip the halo.  Compat frames are independent, so nothing else is
+ * needed; corrected mode additionally takes the phase carry as the carried-in state (below).
+ * Replaces the frame bookkeeping of src/main.cpp:231,266 for a sharded stream.                      */
+int pv_process_device_ex(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride,
+                         int64_t n_in, int64_t n_analysed, int64_t n_frames, int64_t skip_frames,
+                         float *out, int64_t out_stream_stride, int64_t out_voice_stride,
+                         void *state, int32_t flags, void *cuda_stream);
+
+/* Corrected mode, frame-range scan support (the per-bin phase carry of SURVEY 8e).  Analysis-only
+ * pass over frames 0..n_frames-1 of every stream:
+ *   sumD[stream][bin]   int64  sum of the unwrapped phase differences D_k (k >= 1; k >= 0 if P_prev given)
+ *   P_first[stream][bin] u32   phase of frame 0 (turns*2^32); may be NULL
+ *   P_last[stream][bin]  u32   phase of the last frame; may be NULL
+ * Integer sums are associative, so per-range aggregates combine exactly (any order, any sharding). */
+int pv_corrected_aggregate(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride,
+                           int64_t n_in, int64_t n_frames, const uint32_t *P_prev, int64_t *sumD,
+                           uint32_t *P_first, uint32_t *P_last, void *cuda_stream);
+
+/* Builds the carried state at frame boundary n_before (frames 0..n_before-1 already accounted for):
+ * psi = (P_first[a] << 32) + (n_before-1)*nomS + Rq * sumD[a], P_prev as given, empty OLA
+ * accumulators (run the halo frames with skip_frames to fill them).  All pointers are device memory. */
+int pv_corrected_state_from_carry(pv_handle *h, int64_t n_streams, const uint32_t *P_first,
+                                  const int64_t *sumD, int64_t n_before, const uint32_t *P_prev,
+                                  void *state, void *cuda_stream);
 
 /* Same with HOST buffers (pinned or pageable): H2D, kernel, D2H, synchronise.  This is the
  * call the C++ PhaseVocoder shim and the CLI make, and what bench.py times as `e2e`.         */

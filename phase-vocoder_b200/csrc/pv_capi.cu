@@ -38,7 +38,7 @@ struct pv_handle {
     PvSegment *d_segs = nullptr;
     size_t segs_cap = 0;
     int32_t n_segs = 0;
-    int64_t plan_streams = -1, plan_frames = -1;
+    int64_t plan_streams = -1, plan_frames = -1, plan_skip = -1;
     int32_t plan_flags = -1;
     // staging for the host-pointer entry point
     float *d_in = nullptr, *d_out = nullptr;
@@ -140,9 +140,10 @@ void corrected_tables(int N, int Ha, int Hs, double beta, uint64_t *Rq, int32_t 
 // Splits every stream into frame-range segments so that the grid fills the machine.
 // The (R-1)-frame OLA halo in front of each segment is recomputed (compat frames are
 // independent), so the output does not depend on the split.
-int plan_segments(pv_handle *h, int64_t n_streams, int64_t n_frames, int32_t flags, cudaStream_t st)
+int plan_segments(pv_handle *h, int64_t n_streams, int64_t n_frames, int64_t skip, int32_t flags, cudaStream_t st)
 {
-    if (h->plan_streams == n_streams && h->plan_frames == n_frames && h->plan_flags == flags) return PV_OK;
+    if (h->plan_streams == n_streams && h->plan_frames == n_frames && h->plan_flags == flags && h->plan_skip == skip)
+        return PV_OK;
     const int N = h->p.window, Hs = h->p.hop_out;
     const int64_t halo = (N - 1) / Hs;                     // frames k' < k that still overlap frame k
     // aim at ~8 waves of resident groups so that the tail wave is small, but keep the halo
@@ -158,13 +159,14 @@ int plan_segments(pv_handle *h, int64_t n_streams, int64_t n_frames, int32_t fla
     if (seg_len < min_len) seg_len = min_len;
     std::vector<PvSegment> segs;
     for (int64_t s = 0; s < n_streams; s++) {
-        for (int64_t k0 = 0; k0 < n_frames; k0 += seg_len) {
+        for (int64_t k0 = skip; k0 < n_frames; k0 += seg_len) {
             PvSegment g{};
             g.stream = (int32_t)s;
             g.k_emit = k0;
             g.k_end = std::min(n_frames, k0 + seg_len);
-            g.k_begin = std::max<int64_t>(0, k0 - halo);
-            g.carry_in = (k0 == 0 && (flags & PV_PROCESS_CARRY_IN)) ? 1 : 0;
+            // the first segment also computes the caller's skipped (halo) frames from frame 0
+            g.k_begin = (k0 == skip) ? 0 : std::max<int64_t>(0, k0 - halo);
+            g.carry_in = (k0 == skip && (flags & PV_PROCESS_CARRY_IN)) ? 1 : 0;
             g.carry_out = (g.k_end == n_frames && (flags & PV_PROCESS_CARRY_OUT)) ? 1 : 0;
             segs.push_back(g);
         }
@@ -181,6 +183,7 @@ int plan_segments(pv_handle *h, int64_t n_streams, int64_t n_frames, int32_t fla
     h->n_segs = (int32_t)segs.size();
     h->plan_streams = n_streams;
     h->plan_frames = n_frames;
+    h->plan_skip = skip;
     h->plan_flags = flags;
     return PV_OK;
 }
@@ -434,21 +437,59 @@ int pv_process_device(pv_handle *h, const float *in, int64_t n_streams, int64_t 
                       int64_t n_analysed, int64_t n_frames, float *out, int64_t out_stream_stride,
                       int64_t out_voice_stride, void *state, int32_t flags, void *cuda_stream)
 {
+    return pv_process_device_ex(h, in, n_streams, in_stride, n_in, n_analysed, n_frames, 0, out, out_stream_stride,
+                                out_voice_stride, state, flags, cuda_stream);
+}
+
+int pv_corrected_aggregate(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride, int64_t n_in,
+                           int64_t n_frames, const uint32_t *P_prev, int64_t *sumD, uint32_t *P_first,
+                           uint32_t *P_last, void *cuda_stream)
+{
+    if (!h || !in || !sumD || n_streams < 0 || n_frames < 0) return fail(PV_ERR_PARAM, "pv_corrected_aggregate: bad argument");
+    if (h->p.mode != PV_MODE_CORRECTED || !h->fused)
+        return fail(PV_ERR_PARAM, "pv_corrected_aggregate needs a corrected-mode handle with a supported window");
+    DeviceGuard guard(h->device);
+    PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, in, n_streams, in_stride, n_in, n_frames, P_prev, sumD, P_first,
+                                          P_last, (cudaStream_t)cuda_stream));
+    h->launches++;
+    return PV_OK;
+}
+
+int pv_corrected_state_from_carry(pv_handle *h, int64_t n_streams, const uint32_t *P_first, const int64_t *sumD,
+                                  int64_t n_before, const uint32_t *P_prev, void *state, void *cuda_stream)
+{
+    if (!h || !state || n_streams < 0 || n_before < 0 || (n_before > 0 && (!P_first || !sumD || !P_prev)))
+        return fail(PV_ERR_PARAM, "pv_corrected_state_from_carry: bad argument");
+    if (h->p.mode != PV_MODE_CORRECTED || !h->fused)
+        return fail(PV_ERR_PARAM, "pv_corrected_state_from_carry needs a corrected-mode handle");
+    DeviceGuard guard(h->device);
+    PV_CUDA(pv_launch_state_from_carry(h->dev, h->ft, n_streams, P_first, sumD, n_before, P_prev, state,
+                                       (int64_t)pv_state_bytes(h), (cudaStream_t)cuda_stream));
+    h->launches++;
+    return PV_OK;
+}
+
+int pv_process_device_ex(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride, int64_t n_in,
+                         int64_t n_analysed, int64_t n_frames, int64_t skip_frames, float *out,
+                         int64_t out_stream_stride, int64_t out_voice_stride, void *state, int32_t flags,
+                         void *cuda_stream)
+{
     if (!h || !in || !out) return fail(PV_ERR_PARAM, "pv_process: null argument");
+    if (skip_frames < 0 || skip_frames > n_frames) return fail(PV_ERR_PARAM, "pv_process: bad skip_frames");
     if (n_streams < 0 || n_in < 0 || n_frames < 0 || in_stride < n_in)
         return fail(PV_ERR_PARAM, "pv_process: bad sizes (n_streams=%lld n_in=%lld n_frames=%lld in_stride=%lld)",
                     (long long)n_streams, (long long)n_in, (long long)n_frames, (long long)in_stride);
     if (n_streams > 0x7fffffffLL) return fail(PV_ERR_PARAM, "too many streams");
-    if (out_stream_stride < n_frames * h->p.hop_out * (int64_t)h->p.n_voices && n_streams > 1)
+    if (out_stream_stride < (n_frames - skip_frames) * h->p.hop_out * (int64_t)h->p.n_voices && n_streams > 1)
         return fail(PV_ERR_PARAM, "pv_process: out_stream_stride too small");
     if ((flags & (PV_PROCESS_CARRY_IN | PV_PROCESS_CARRY_OUT)) && !state)
         return fail(PV_ERR_PARAM, "pv_process: carry requested without a state buffer");
-    if (n_streams == 0 || n_frames == 0) return PV_OK;
+    if (n_streams == 0 || n_frames == skip_frames) return PV_OK;
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     if (h->p.mode != PV_MODE_COMPAT && !h->fused)
         return fail(PV_ERR_UNSUPPORTED, "corrected mode needs window in {256,512,1024,2048} and an even hop_out");
-    int rc = plan_segments(h, n_streams, n_frames, flags, st);
+    int rc = plan_segments(h, n_streams, n_frames, skip_frames, flags, st);
     if (rc != PV_OK) return rc;
     PvProcessArgs a{};
     a.in = in;
@@ -456,7 +497,7 @@ int pv_process_device(pv_handle *h, const float *in, int64_t n_streams, int64_t 
     a.n_in = n_in;
     a.n_analysed = n_analysed;
     a.n_frames = n_frames;
-    a.out = out;
+    a.out = out - skip_frames * (int64_t)h->p.hop_out;     // kernels index the output by frame number
     a.out_stream_stride = out_stream_stride;
     a.out_voice_stride = out_voice_stride;
     a.state = (unsigned char *)state;

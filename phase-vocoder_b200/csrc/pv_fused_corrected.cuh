@@ -114,10 +114,11 @@ PV_DEV int slot_bin(int u, int sl)
     return (u == 0 ? B3 / 2 : B3 - u) + B3 * j;
 }
 
-template <int LOG2N, class Sync, class Hook, class PreLast>
-PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const float *ring, float2 *bufA,
-                            float2 *bufB, float *magS, int32_t *dS, unsigned long long *psi, float *acc,
-                            CState &st, int pos0, int Hs, Sync sync, Hook hook, PreLast pre_last_sync)
+// Forward transform of one frame: X[slot] = spectrum at the bins owned by this thread, wp[j] = W_N^bin of
+// the p-side slots (reused by the Hermitian pack).  Two barriers; `hook` runs after the first.
+template <int LOG2N, class Sync, class Hook>
+PV_DEV void cforward(int tid, const FrameIO &io, const CTables &tb, const float *ring, float2 *bufA, float2 *bufB,
+                     Sync sync, Hook hook, float2 (&X)[9], float2 (&wp)[4])
 {
     using C = CShape<LOG2N>;
     using S = Shape<LOG2N>;
@@ -206,8 +207,6 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
     }
     dft<4, -1>(P);
     dft<4, -1>(Q);
-    float2 X[9];                         // by slot
-    float2 wp[4];                        // W_N^{bin of p-side slot j}; reused by the Hermitian pack
     if (u != 0) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -226,6 +225,21 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
 #pragma unroll
         for (int j = 0; j < 4; j++) wp[j] = make_float2(1.f, 0.f);   // unused
     }
+    (void)M;
+}
+
+template <int LOG2N, class Sync, class Hook, class PreLast>
+PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const float *ring, float2 *bufA,
+                            float2 *bufB, float *magS, int32_t *dS, unsigned long long *psi, float *acc,
+                            CState &st, int pos0, int Hs, Sync sync, Hook hook, PreLast pre_last_sync)
+{
+    using C = CShape<LOG2N>;
+    using S = Shape<LOG2N>;
+    constexpr int N = C::N, B3 = C::B3, M = C::M, NB = C::NB;
+    const int u = tid;
+    const int tP = u, tQ = (u == 0) ? B3 / 2 : B3 - u;
+    float2 X[9], wp[4];
+    cforward<LOG2N>(tid, io, tb, ring, bufA, bufB, sync, hook, X, wp);
     // ---- analysis: magnitude, phase (turns*2^32), unwrapped phase difference ----
     const bool first = st.have_prev == 0;
 #pragma unroll
@@ -293,6 +307,26 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
         (void)S::T;
     }
     (void)M;
+}
+
+// Analysis-only frame for the phase-carry aggregate: updates P_prev and sum += D (k >= 1).
+template <int LOG2N, class Sync>
+PV_DEV void frame_aggregate(int tid, const FrameIO &io, const CTables &tb, float2 *bufA, float2 *bufB, CState &st,
+                            long long (&sumD)[9], uint32_t (&Pfirst)[9], Sync sync)
+{
+    using C = CShape<LOG2N>;
+    float2 X[9], wp[4];
+    cforward<LOG2N>(tid, io, tb, nullptr, bufA, bufB, sync, []() {}, X, wp);
+#pragma unroll
+    for (int sl = 0; sl < 9; sl++) {
+        if (sl == 8 && tid != 0) break;
+        const int bin = slot_bin<C::B3>(tid, sl);
+        const uint32_t Pc = phase_turns32(X[sl].x, X[sl].y);
+        if (st.have_prev) sumD[sl] += (long long)(int32_t)(Pc - st.Pprev[sl] - PV_LDG(tb.nomA + bin));
+        else Pfirst[sl] = Pc;
+        st.Pprev[sl] = Pc;
+    }
+    st.have_prev = 1;   // no trailing barrier: the next frame's first barrier orders the buffer reuse
 }
 
 }  // namespace pvfused

@@ -142,6 +142,78 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
     }
 }
 
+// ---- phase-carry aggregate: analysis only, one group per stream ----
+// sumD[stream][bin] = sum over frames k >= 1 (k >= 0 when P_prev is given) of the unwrapped phase
+// difference D_k; P_first = phase of the first frame, P_last = phase of the last frame.
+template <int LOG2N>
+__global__ void __launch_bounds__(CLaunch<LOG2N>::THREADS)
+corrected_aggregate_kernel(PvDev d, CTables tb, const float *in, long long n_streams, long long in_stride,
+                           long long n_in, long long n_frames, const uint32_t *P_prev, long long *sumD,
+                           uint32_t *P_first, uint32_t *P_last, int vec_in_ok)
+{
+    using C = CShape<LOG2N>;
+    using L = CLaunch<LOG2N>;
+    constexpr int T = C::T, G = L::G, NB = C::NB, B3 = C::B3;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int g = threadIdx.x / T, tid = threadIdx.x % T;
+    const long long s = (long long)blockIdx.x * G + g;
+    if (s >= n_streams) return;
+    float2 *bufA = reinterpret_cast<float2 *>(smem_raw) + (size_t)g * (C::BUF_A + C::BUF_B);
+    float2 *bufB = bufA + C::BUF_A;
+    CGroupSync<T, G> sync{g, T >= 32 ? 0xffffffffu : (((1u << (T & 31)) - 1u) << ((threadIdx.x & 31) / T * T))};
+    CState st;
+    long long acc[9];
+    uint32_t pf[9];
+    st.have_prev = P_prev != nullptr;
+#pragma unroll
+    for (int sl = 0; sl < 9; sl++) {
+        acc[sl] = 0;
+        pf[sl] = 0;
+        st.Pprev[sl] = (P_prev && (sl < 8 || tid == 0)) ? P_prev[s * NB + slot_bin<B3>(tid, sl)] : 0u;
+    }
+    const bool had_prev = st.have_prev;
+    for (long long k = 0; k < n_frames; ++k) {
+        FrameIO io{in + s * in_stride, n_in, k * (long long)d.Ha, true, vec_in_ok != 0};
+        frame_aggregate<LOG2N>(tid, io, tb, bufA, bufB, st, acc, pf, sync);
+    }
+#pragma unroll
+    for (int sl = 0; sl < 9; sl++) {
+        if (sl == 8 && tid != 0) break;
+        const int bin = slot_bin<B3>(tid, sl);
+        sumD[s * NB + bin] = acc[sl];
+        if (P_first) P_first[s * NB + bin] = had_prev ? 0u : pf[sl];
+        if (P_last) P_last[s * NB + bin] = st.Pprev[sl];
+    }
+}
+
+// psi[v][s] = (P_first[a] << 32) + (n_before - 1) * nomS[v][s] + Rq[v] * sumD[a],  a = a_hi[v][s]
+__global__ void state_from_carry_kernel(PvDev d, CTables tb, long long n_streams, const uint32_t *P_first,
+                                        const long long *sumD, long long n_before, const uint32_t *P_prev,
+                                        unsigned char *state, long long state_stride)
+{
+    const int NB = d.N / 2 + 1, V = tb.V, N = d.N;
+    const long long s = blockIdx.x;
+    if (s >= n_streams) return;
+    unsigned char *st = state + s * state_stride;
+    uint32_t *hdr = reinterpret_cast<uint32_t *>(st);
+    uint32_t *stP = hdr + 2;
+    unsigned long long *psi = reinterpret_cast<unsigned long long *>(st + 8 + ((NB * 4 + 7) / 8) * 8);
+    float *acc = reinterpret_cast<float *>(psi + (size_t)V * NB);
+    if (threadIdx.x == 0) { hdr[0] = n_before > 0 ? 1u : 0u; hdr[1] = 0u; }
+    for (int b = threadIdx.x; b < NB; b += blockDim.x) stP[b] = (n_before > 0 && P_prev) ? P_prev[s * NB + b] : 0u;
+    for (int i = threadIdx.x; i < V * NB; i += blockDim.x) {
+        const int v = i / NB, sb = i - v * NB;
+        const int lo = tb.a_lo[i], hi = tb.a_hi[i];
+        unsigned long long p = 0;
+        if (n_before > 0 && lo <= hi)
+            p = ((unsigned long long)P_first[s * NB + hi] << 32) + (unsigned long long)(n_before - 1) * tb.nomS[i] +
+                (unsigned long long)(sumD[s * NB + hi] * (long long)tb.Rq[v]);
+        psi[i] = p;
+        (void)sb;
+    }
+    for (int i = threadIdx.x; i < V * N; i += blockDim.x) acc[i] = 0.f;
+}
+
 template <int LOG2N, int MINB>
 cudaError_t claunch(const PvDev &d, const CTables &tb, const PvProcessArgs &a, cudaStream_t st)
 {
@@ -194,9 +266,8 @@ int pv_fused_corrected_capacity(int N, int V, int sm_count)
     }
 }
 
-cudaError_t pv_launch_corrected_fused(const PvDev &d, const PvFusedTables &t, const PvProcessArgs &a, cudaStream_t st)
+static CTables make_ctables(const PvDev &d, const PvFusedTables &t)
 {
-    if (a.n_segs <= 0) return cudaSuccess;
     CTables tb{};
     tb.ctw1 = t.ctw1; tb.ctw2 = t.ctw2; tb.tw2n = t.tw2n; tb.itw1 = t.itw1; tb.itw2 = t.itw2;
     tb.win = d.win; tb.nomA = d.nomA; tb.a_lo = d.a_lo; tb.a_hi = d.a_hi;
@@ -204,6 +275,58 @@ cudaError_t pv_launch_corrected_fused(const PvDev &d, const PvFusedTables &t, co
     for (int v = 0; v < d.V; v++) tb.Rq[v] = d.Rq[v];
     tb.scale = d.gain / (float)d.N;
     tb.V = d.V;
+    return tb;
+}
+
+template <int LOG2N>
+static cudaError_t agg_launch(const PvDev &d, const CTables &tb, const float *in, int64_t n_streams, int64_t in_stride,
+                              int64_t n_in, int64_t n_frames, const uint32_t *P_prev, int64_t *sumD, uint32_t *P_first,
+                              uint32_t *P_last, cudaStream_t st)
+{
+    using L = CLaunch<LOG2N>;
+    using C = CShape<LOG2N>;
+    auto kern = corrected_aggregate_kernel<LOG2N>;
+    const size_t smem = (size_t)L::G * (C::BUF_A + C::BUF_B) * sizeof(float2);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const bool in_ok = (d.Ha % 2 == 0) && (in_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & 7) == 0);
+    const int grid = (int)((n_streams + L::G - 1) / L::G);
+    kern<<<grid, L::THREADS, smem, st>>>(d, tb, in, n_streams, in_stride, n_in, n_frames, P_prev,
+                                          reinterpret_cast<long long *>(sumD), P_first, P_last, in_ok);
+    return cudaGetLastError();
+}
+
+cudaError_t pv_launch_corrected_aggregate(const PvDev &d, const PvFusedTables &t, const float *in, int64_t n_streams,
+                                          int64_t in_stride, int64_t n_in, int64_t n_frames, const uint32_t *P_prev,
+                                          int64_t *sumD, uint32_t *P_first, uint32_t *P_last, cudaStream_t st)
+{
+    if (n_streams <= 0) return cudaSuccess;
+    const CTables tb = make_ctables(d, t);
+    switch (d.N) {
+        case 256: return agg_launch<8>(d, tb, in, n_streams, in_stride, n_in, n_frames, P_prev, sumD, P_first, P_last, st);
+        case 512: return agg_launch<9>(d, tb, in, n_streams, in_stride, n_in, n_frames, P_prev, sumD, P_first, P_last, st);
+        case 1024: return agg_launch<10>(d, tb, in, n_streams, in_stride, n_in, n_frames, P_prev, sumD, P_first, P_last, st);
+        case 2048: return agg_launch<11>(d, tb, in, n_streams, in_stride, n_in, n_frames, P_prev, sumD, P_first, P_last, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t pv_launch_state_from_carry(const PvDev &d, const PvFusedTables &t, int64_t n_streams, const uint32_t *P_first,
+                                       const int64_t *sumD, int64_t n_before, const uint32_t *P_prev, void *state,
+                                       int64_t state_stride, cudaStream_t st)
+{
+    if (n_streams <= 0) return cudaSuccess;
+    const CTables tb = make_ctables(d, t);
+    state_from_carry_kernel<<<(unsigned)n_streams, 256, 0, st>>>(d, tb, n_streams, P_first,
+                                                                reinterpret_cast<const long long *>(sumD), n_before, P_prev,
+                                                                reinterpret_cast<unsigned char *>(state), state_stride);
+    return cudaGetLastError();
+}
+
+cudaError_t pv_launch_corrected_fused(const PvDev &d, const PvFusedTables &t, const PvProcessArgs &a, cudaStream_t st)
+{
+    if (a.n_segs <= 0) return cudaSuccess;
+    const CTables tb = make_ctables(d, t);
     switch (d.N) {
         case 256: return claunch<8, 1>(d, tb, a, st);
         case 512: return claunch<9, 1>(d, tb, a, st);

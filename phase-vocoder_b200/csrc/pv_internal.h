@@ -60,6 +60,12 @@ cudaError_t pv_launch_compat_fused(const PvDev &d, const PvFusedTables &t, const
 bool pv_fused_corrected_supported(int N, int Ha, int Hs);
 int pv_fused_corrected_capacity(int N, int V, int sm_count);
 cudaError_t pv_launch_corrected_fused(const PvDev &d, const PvFusedTables &t, const PvProcessArgs &a, cudaStream_t st);
+cudaError_t pv_launch_corrected_aggregate(const PvDev &d, const PvFusedTables &t, const float *in, int64_t n_streams,
+                                          int64_t in_stride, int64_t n_in, int64_t n_frames, const uint32_t *P_prev,
+                                          int64_t *sumD, uint32_t *P_first, uint32_t *P_last, cudaStream_t st);
+cudaError_t pv_launch_state_from_carry(const PvDev &d, const PvFusedTables &t, int64_t n_streams, const uint32_t *P_first,
+                                       const int64_t *sumD, int64_t n_before, const uint32_t *P_prev, void *state,
+                                       int64_t state_stride, cudaStream_t st);
 cudaError_t pv_launch_analysis_batch(const PvDev &d, const float *in, int64_t n_in, int64_t n_frames,
                                      float *out_magphase, cudaStream_t st);
 cudaError_t pv_launch_resynthesis_batch(const PvDev &d, const float *spectra, int64_t n_frames,

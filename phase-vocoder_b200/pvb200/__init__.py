@@ -24,8 +24,8 @@ MAX_VOICES = 8
 EXPORTS = [
     "pv_last_error", "pv_version", "pv_create", "pv_destroy", "pv_get_params", "pv_window_table",
     "pv_reference_schedule", "pv_analysis", "pv_resynthesis", "pv_test_overlap_add", "pv_analysis_batch",
-    "pv_resynthesis_batch", "pv_state_bytes", "pv_process_device", "pv_process_host", "pv_launch_count",
-    "pv_timing_enable", "pv_timing_read",
+    "pv_resynthesis_batch", "pv_state_bytes", "pv_process_device", "pv_process_device_ex", "pv_process_host",
+    "pv_corrected_aggregate", "pv_corrected_state_from_carry", "pv_launch_count", "pv_timing_enable", "pv_timing_read",
 ]
 
 
@@ -69,6 +69,9 @@ def load():
     L.pv_state_bytes.restype = C.c_size_t
     L.pv_process_device.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, i64, i64, vp, i32, vp]
     L.pv_process_host.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, i64, i64, vp, i32]
+    L.pv_process_device_ex.argtypes = [vp, vp, i64, i64, i64, i64, i64, i64, vp, i64, i64, vp, i32, vp]
+    L.pv_corrected_aggregate.argtypes = [vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp]
+    L.pv_corrected_state_from_carry.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp]
     L.pv_launch_count.argtypes = [vp]
     L.pv_launch_count.restype = i64
     L.pv_timing_enable.argtypes = [vp, i32]
@@ -168,18 +171,44 @@ class PhaseVocoder:
     def state_bytes(self):
         return load().pv_state_bytes(self._h)
 
-    def process(self, x, n_frames, n_analysed=None, out=None, state=None, flags=0):
-        """Fused hot path on device tensors.  x: [streams, n_in] float32 CUDA -> out [streams, V, n_frames*Hs]."""
+    def process(self, x, n_frames, n_analysed=None, out=None, state=None, flags=0, skip=0, n_in=None):
+        """Fused hot path on device tensors.  x: [streams, n_in] float32 CUDA -> out [streams, V, (n_frames-skip)*Hs].
+        `skip` leading (halo) frames are computed but not written; `n_in` overrides the number of valid
+        samples per row (rows may overlap: frame-range parts of one long stream)."""
         import torch
         assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
-        S, n_in = x.shape
-        n_out = n_frames * self.outHopSize
+        S = x.shape[0]
+        n_in = x.shape[1] if n_in is None else n_in
+        n_out = (n_frames - skip) * self.outHopSize
         if out is None:
             out = torch.empty((S, self.n_voices, n_out), dtype=torch.float32, device=x.device)
         na = n_frames if n_analysed is None else n_analysed
-        _check(load().pv_process_device(self._h, _ptr(x), S, x.stride(0), n_in, na, n_frames, _ptr(out),
-                                        out.stride(0), out.stride(1), _ptr(state), flags, _cuda_stream()))
+        _check(load().pv_process_device_ex(self._h, _ptr(x), S, x.stride(0), n_in, na, n_frames, skip, _ptr(out),
+                                           out.stride(0), out.stride(1), _ptr(state), flags, _cuda_stream()))
         return out
+
+    # ---- corrected mode: phase carry for frame-range sharding ----
+    def aggregate(self, x, n_frames, P_prev=None, n_in=None):
+        """Analysis-only pass: (sumD int64 [S, nb], P_first uint32-as-int32 [S, nb], P_last [S, nb])."""
+        import torch
+        S = x.shape[0]
+        n_in = x.shape[1] if n_in is None else n_in
+        nb = self.nSamps // 2 + 1
+        sumD = torch.zeros((S, nb), dtype=torch.int64, device=x.device)
+        P_first = torch.zeros((S, nb), dtype=torch.int32, device=x.device)
+        P_last = torch.zeros((S, nb), dtype=torch.int32, device=x.device)
+        _check(load().pv_corrected_aggregate(self._h, _ptr(x), S, x.stride(0), n_in, n_frames, _ptr(P_prev), _ptr(sumD),
+                                             _ptr(P_first), _ptr(P_last), _cuda_stream()))
+        return sumD, P_first, P_last
+
+    def state_from_carry(self, P_first, sumD, n_before, P_prev):
+        """Carried state [S, state_bytes] (uint8) at frame boundary n_before from a phase carry."""
+        import torch
+        S = sumD.shape[0]
+        st = torch.zeros((S, self.state_bytes()), dtype=torch.uint8, device=sumD.device)
+        _check(load().pv_corrected_state_from_carry(self._h, S, _ptr(P_first), _ptr(sumD), n_before, _ptr(P_prev),
+                                                    _ptr(st), _cuda_stream()))
+        return st
 
     def process_host(self, x, n_frames, n_analysed=None, out=None, state=None, flags=0):
         """Same through host buffers (numpy arrays or pinned CPU torch tensors): H2D + kernel + D2H."""

@@ -1,0 +1,90 @@
+"""Frame-range sharding of one long stream on the GPU engine: four virtual ranks (threads with an
+in-process all_gather) reproduce the single-launch result BIT FOR BIT in both modes -- the only data
+crossing rank boundaries is the per-bin int64 phase carry (corrected) or nothing (compat)."""
+import threading
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import pvb200  # noqa: E402
+from pvb200 import sharding  # noqa: E402
+from sharding_engines import ThreadComm  # noqa: E402
+from signals import multitone  # noqa: E402
+
+
+def _run_ranks(world, fn):
+    comms = ThreadComm.make(world)
+    res, err = [None] * world, []
+
+    def body(r):
+        try:
+            torch.cuda.set_device(0)
+            res[r] = fn(comms[r])
+        except Exception as e:       # pragma: no cover
+            err.append(e)
+            comms[r].sh["bar"].abort()
+
+    th = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not err, err
+    return res
+
+
+@pytest.mark.parametrize("N,Ha,Hs,betas,nf,world", [(2048, 512, 512, [1.4983071], 203, 4), (256, 64, 64, [1.0, 1.5, 2.0], 1001, 4),
+                                                    (1024, 256, 512, [1.0], 150, 3)])
+def test_corrected_frame_sharding_is_bit_exact(N, Ha, Hs, betas, nf, world):
+    x = torch.from_numpy(multitone(N + nf * Ha, seed=8, noise=1e-3)).cuda()
+    pv = pvb200.PhaseVocoder(N, hop_in=Ha, hop_out=Hs, mode=pvb200.MODE_CORRECTED,
+                             window_type=pvb200.WIN_HANN_PERIODIC, pitch=tuple(betas))
+    full = pv.process(x[None, :], nf).cpu().numpy()
+    launches0 = pv.launch_count()
+
+    def fn(comm):
+        # one handle per rank, as on real ranks (a handle is not thread-safe: it caches its segment plan)
+        pvr = pvb200.PhaseVocoder(N, hop_in=Ha, hop_out=Hs, mode=pvb200.MODE_CORRECTED,
+                                  window_type=pvb200.WIN_HANN_PERIODIC, pitch=tuple(betas))
+        out, p = sharding.process_corrected_sharded(pvr, lambda k: x[None, k * Ha:], nf, comm, Ha, Hs, N)
+        torch.cuda.synchronize()
+        assert pvr.launch_count() >= 2
+        return out.cpu().numpy()
+
+    parts = _run_ranks(world, fn)
+    got = np.concatenate(parts, axis=2)
+    assert np.array_equal(got, full)
+    assert launches0 == 1
+
+
+@pytest.mark.parametrize("N,Ha,Hs,nf,world", [(2048, 512, 512, 203, 4), (256, 64, 64, 999, 8), (4096, 1024, 1024, 50, 2)])
+def test_compat_frame_sharding_is_bit_exact(N, Ha, Hs, nf, world):
+    x = torch.from_numpy(multitone(N + nf * Ha, seed=9)).cuda()
+    pv = pvb200.PhaseVocoder(N, hop_in=Ha, hop_out=Hs)
+    full = pv.process(x[None, :], nf, n_analysed=nf - 2).cpu().numpy()
+
+    def fn(comm):
+        pvr = pvb200.PhaseVocoder(N, hop_in=Ha, hop_out=Hs)
+        p = sharding.plan(nf, comm.world, comm.rank, N, Hs)
+        out, _ = sharding.process_compat_sharded(pvr, x[None, p.ks * Ha:], nf, nf - 2, comm, Ha, Hs, N)
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+
+    got = np.concatenate(_run_ranks(world, fn), axis=2)
+    assert np.array_equal(got, full)
+
+
+def test_aggregate_matches_oracle():
+    import pv_oracle as po
+    N, Ha, nf = 1024, 256, 40
+    x = multitone(N + nf * Ha, seed=3, noise=1e-3)
+    pv = pvb200.PhaseVocoder(N, hop_in=Ha, hop_out=Ha, mode=pvb200.MODE_CORRECTED, window_type=pvb200.WIN_HANN_PERIODIC)
+    sumD, P_first, P_last = pv.aggregate(torch.from_numpy(x).cuda()[None, :], nf)
+    want, wlast = po.corrected_aggregate(x, N, Ha, po.window(po.WIN_HANN_PERIODIC, N), nf)
+    d = (P_last[0].cpu().numpy().view(np.uint32).astype(np.int64) - wlast.astype(np.int64) + 2 ** 31) % 2 ** 32 - 2 ** 31
+    assert np.abs(d).max() < 2 ** 32 * 1e-3
+    # sums agree up to fp32 phase noise and whole-turn unwrap flips
+    ds = (sumD[0].cpu().numpy() - want) / 2.0 ** 32
+    frac = np.abs(ds - np.round(ds))
+    assert frac.max() < 1e-3 and (np.round(ds) != 0).mean() < 0.02
