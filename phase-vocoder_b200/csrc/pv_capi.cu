@@ -28,6 +28,7 @@ struct pv_handle {
     uint32_t *d_nomA = nullptr;
     int32_t *d_alo = nullptr, *d_ahi = nullptr;
     uint64_t *d_nomS = nullptr;
+    uint32_t *d_gather = nullptr;
     std::vector<float> h_win;
     // fused-kernel tables
     bool fused = false;
@@ -281,6 +282,11 @@ int pv_create(const pv_params *params, pv_handle **out)
         if (rc == PV_OK) rc = upload(&h->d_alo, alo);
         if (rc == PV_OK) rc = upload(&h->d_ahi, ahi);
         if (rc == PV_OK) rc = upload(&h->d_nomS, nomS);
+        if (rc == PV_OK && N >= 256 && N <= 2048) {
+            std::vector<uint32_t> gath;
+            build_gather_table(N, V, alo.data(), ahi.data(), nomS.data(), gath);
+            rc = upload(&h->d_gather, gath);
+        }
     }
     h->capacity = h->sm_count * 8;
     const bool want_fused = (p.mode == PV_MODE_COMPAT) ? pv_fused_compat_supported(N, p.hop_out)
@@ -312,6 +318,7 @@ int pv_create(const pv_params *params, pv_handle **out)
     d.a_lo = h->d_alo;
     d.a_hi = h->d_ahi;
     d.nomS = h->d_nomS;
+    d.gather = h->d_gather;
     *out = h;
     return PV_OK;
 }
@@ -326,6 +333,7 @@ void pv_destroy(pv_handle *h)
     cudaFree(h->d_alo);
     cudaFree(h->d_ahi);
     cudaFree(h->d_nomS);
+    cudaFree(h->d_gather);
     for (auto p : h->d_ft) cudaFree(p);
     cudaFree(h->d_segs);
     cudaFree(h->d_in);

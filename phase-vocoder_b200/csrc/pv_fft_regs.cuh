@@ -11,6 +11,7 @@
 #include <cstdint>
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
+struct uint4 { unsigned x, y, z, w; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 #define PV_DEV inline
 #define PV_LDG(p) (*(p))

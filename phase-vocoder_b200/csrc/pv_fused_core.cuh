@@ -21,6 +21,8 @@
 //   forward  n = n1*S1 + n2*8 + n3          k = k1 + R1*k2 + B3*k3        S1 = N/R1 = R2*8
 //   inverse  kappa = n1*B3 + n2*R2 + n3     n = m1 + 4*m2 + 4*R1*m3       (B3 = R1*R2)
 #pragma once
+#include <type_traits>
+
 #include "pv_fft_regs.cuh"
 
 namespace pvfused {
@@ -356,9 +358,16 @@ PV_DEV void inverse_1_tw(int t1, float2 a1, float2 a2, float2 a3, float2 (&Z)[4]
 // acc: OLA ring of N floats, pos0: ring position of sample 0 of this frame.
 // `scale` multiplies the unnormalised inverse (compat: 1/N; corrected: gain/N); `pre_last_sync` runs
 // just before the last barrier of the frame (used to complete asynchronous ring copies).
-template <int LOG2N, class Sync, class PreLast>
+struct TableTw2 {      // default source of the inverse pass-2 twiddles: the global table
+    const float2 *itw2;
+    int R2;
+    PV_DEV float2 operator()(int /*q*/, int m2, int n3) const { return PV_LDG(itw2 + (m2 - 1) * R2 + n3); }
+};
+
+template <int LOG2N, class Sync, class PreLast, class Tw2 = TableTw2>
 PV_DEV void inverse_23_ola(int tid, const Tables &tb, float2 *bufA, float2 *bufB, float *acc, int pos0, int Hs,
-                           bool zero_frame, float scale, Sync sync, PreLast pre_last_sync)
+                           bool zero_frame, float scale, Sync sync, PreLast pre_last_sync,
+                           Tw2 tw2 = TableTw2{nullptr, 0})
 {
     using S = Shape<LOG2N>;
     constexpr int N = S::N, T = S::T, R1 = S::R1, R2 = S::R2, B3 = S::B3;
@@ -397,7 +406,10 @@ PV_DEV void inverse_23_ola(int tid, const Tables &tb, float2 *bufA, float2 *bufB
             for (int q = 0; q < 8; q++) {
                 const int m2 = 2 * q + half;
                 float2 r = o[q];
-                if (m2 != 0) r = cmul(r, PV_LDG(tb.itw2 + (m2 - 1) * R2 + n3));
+                if (m2 != 0) {
+                    if constexpr (std::is_same<Tw2, TableTw2>::value) r = cmul(r, PV_LDG(tb.itw2 + (m2 - 1) * R2 + n3));
+                    else r = cmul(r, tw2(q, m2, n3));
+                }
                 bufB[(m1 + 4 * m2) * S::ILD2 + n3] = r;
             }
         } else {

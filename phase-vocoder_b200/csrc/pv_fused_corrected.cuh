@@ -49,9 +49,11 @@ struct CTables {
     const int32_t *a_lo;    // [V][NB]
     const int32_t *a_hi;    // [V][NB]
     const unsigned long long *nomS;   // [V][NB]
+    const uint4 *gather;    // [V][T][9] per-thread packed {a_lo, a_hi, nomS lo, nomS hi} in slot order
     unsigned long long Rq[8];
     float scale;            // gain / N
     int V;
+    int Ha;
 };
 
 // Cooperative ring refill: pairs [lo, N) of the frame at io.base, spread over the T threads.
@@ -98,6 +100,73 @@ PV_DEV void split_both(float2 a, float2 b, float2 w, float2 &xk, float2 &xm)
     xm = make_float2(e.x - t.x, -(e.y - t.y));
 }
 
+// Loop-invariant per-thread twiddle bases (N = 2048 layout: both forward passes and inverse pass 2 use
+// split radix-16 butterflies, thread = (butterfly b = tid % 64, half = tid / 64), outputs 2q + half).
+// The 8 twiddles of a pass are o * g1^q0 * g2^q1 * g4^q2 for q = q0 + 2 q1 + 4 q2.
+struct TwBase4 { float2 o, g1, g2, g4; };
+
+PV_DEV void tw_expand(const TwBase4 &b, float2 (&e)[8])
+{
+    e[0] = b.o;
+    e[1] = cmul(b.o, b.g1);
+    e[2] = cmul(b.o, b.g2);
+    e[3] = cmul(e[1], b.g2);
+    e[4] = cmul(b.o, b.g4);
+    e[5] = cmul(e[1], b.g4);
+    e[6] = cmul(e[2], b.g4);
+    e[7] = cmul(e[3], b.g4);
+}
+
+struct CThreadTw {
+    TwBase4 p1, p2, ip2;     // forward pass 1, forward pass 2, inverse pass 2
+    float2 wN, w2, w4;       // W_N^u, W_N^2u, W_N^4u  (split / pack / inverse pass 1)
+};
+
+// exact table values for the bases (cis of integer fractions, rounded once)
+template <int LOG2N>
+PV_DEV CThreadTw load_cthread_tw(int tid, const CTables &tb)
+{
+    using C = CShape<LOG2N>;
+    constexpr int S1 = C::S1, R2 = C::R2;
+    CThreadTw t;
+    auto one = make_float2(1.f, 0.f);
+    if constexpr (2 * C::C1 == C::T && 2 * C::C2 == C::T) {
+        const int half = tid / C::C1;
+        {   // forward pass 1: W_M^{k1 t1}, k1 = 2q + half, t1 = tid % C1; table row k1-1
+            const int t1 = tid % C::C1;
+            t.p1.o = half ? PV_LDG(tb.ctw1 + 0 * S1 + t1) : one;
+            t.p1.g1 = PV_LDG(tb.ctw1 + 1 * S1 + t1);
+            t.p1.g2 = PV_LDG(tb.ctw1 + 3 * S1 + t1);
+            t.p1.g4 = PV_LDG(tb.ctw1 + 7 * S1 + t1);
+        }
+        {   // forward pass 2: W_S1^{k2 n3}, n3 = (tid % C2) / R1
+            const int n3 = (tid % C::C2) / C::R1;
+            t.p2.o = half ? PV_LDG(tb.ctw2 + 0 * 4 + n3) : one;
+            t.p2.g1 = PV_LDG(tb.ctw2 + 1 * 4 + n3);
+            t.p2.g2 = PV_LDG(tb.ctw2 + 3 * 4 + n3);
+            t.p2.g4 = PV_LDG(tb.ctw2 + 7 * 4 + n3);
+        }
+        {   // inverse pass 2: exp(+2 pi i m2 n3 / B3), m2 = 2q + half, n3 = (tid % 64) % R2
+            const int n3 = (tid % (4 * R2)) % R2;
+            t.ip2.o = half ? PV_LDG(tb.itw2 + 0 * R2 + n3) : one;
+            t.ip2.g1 = PV_LDG(tb.itw2 + 1 * R2 + n3);
+            t.ip2.g2 = PV_LDG(tb.itw2 + 3 * R2 + n3);
+            t.ip2.g4 = PV_LDG(tb.itw2 + 7 * R2 + n3);
+        }
+    } else {
+        t.p1 = t.p2 = t.ip2 = TwBase4{one, one, one, one};
+    }
+    t.wN = PV_LDG(tb.tw2n + 2 * tid);
+    t.w2 = PV_LDG(tb.tw2n + 4 * tid);
+    t.w4 = cmul(t.w2, t.w2);
+    return t;
+}
+
+struct RegTw2 {            // inverse pass-2 twiddles from registers
+    const float2 *e;
+    PV_DEV float2 operator()(int q, int /*m2*/, int /*n3*/) const { return e[q]; }
+};
+
 struct CState {             // per-thread registers carried across the frames of a stream
     uint32_t Pprev[9];
     int have_prev;
@@ -116,9 +185,9 @@ PV_DEV int slot_bin(int u, int sl)
 
 // Forward transform of one frame: X[slot] = spectrum at the bins owned by this thread, wp[j] = W_N^bin of
 // the p-side slots (reused by the Hermitian pack).  Two barriers; `hook` runs after the first.
-template <int LOG2N, class Sync, class Hook>
-PV_DEV void cforward(int tid, const FrameIO &io, const CTables &tb, const float *ring, float2 *bufA, float2 *bufB,
-                     Sync sync, Hook hook, float2 (&X)[9], float2 (&wp)[4])
+template <int LOG2N, bool TWREG, class Sync, class Hook>
+PV_DEV void cforward(int tid, const FrameIO &io, const CTables &tb, const CThreadTw &tt, const float *ring,
+                     float2 *bufA, float2 *bufB, Sync sync, Hook hook, float2 (&X)[9], float2 (&wp)[4])
 {
     using C = CShape<LOG2N>;
     using S = Shape<LOG2N>;
@@ -144,11 +213,13 @@ PV_DEV void cforward(int tid, const FrameIO &io, const CTables &tb, const float 
         for (int n1 = 0; n1 < 16; n1++) v[n1] = ld((N / 2 + 2 * (n1 * S1 + t1)) & (N - 1));
         if (half == 0) dft16_half<-1, false>(v, o);
         else dft16_half<-1, true>(v, o);
+        float2 e[8];
+        if constexpr (TWREG) tw_expand(tt.p1, e);
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             const int k1 = 2 * q + half;
             float2 r = o[q];
-            if (k1 != 0) r = cmul(r, PV_LDG(tb.ctw1 + (k1 - 1) * S1 + t1));
+            if (k1 != 0) r = cmul(r, TWREG ? e[q] : PV_LDG(tb.ctw1 + (k1 - 1) * S1 + t1));
             bufA[k1 * C::LD1 + t1] = r;
         }
     } else {
@@ -174,11 +245,13 @@ PV_DEV void cforward(int tid, const FrameIO &io, const CTables &tb, const float 
         for (int n2 = 0; n2 < 16; n2++) v[n2] = bufA[k1 * C::LD1 + n2 * 4 + n3];
         if (half == 0) dft16_half<-1, false>(v, o);
         else dft16_half<-1, true>(v, o);
+        float2 e[8];
+        if constexpr (TWREG) tw_expand(tt.p2, e);
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             const int k2 = 2 * q + half;
             float2 r = o[q];
-            if (k2 != 0) r = cmul(r, PV_LDG(tb.ctw2 + (k2 - 1) * 4 + n3));
+            if (k2 != 0) r = cmul(r, TWREG ? e[q] : PV_LDG(tb.ctw2 + (k2 - 1) * 4 + n3));
             bufB[(k1 + R1 * k2) * C::LD2 + n3] = r;
         }
     } else {
@@ -209,10 +282,10 @@ PV_DEV void cforward(int tid, const FrameIO &io, const CTables &tb, const float 
     dft<4, -1>(Q);
     if (u != 0) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            wp[j] = PV_LDG(tb.tw2n + 2 * (u + B3 * j));
-            split_both(P[j], Q[3 - j], wp[j], X[j], X[4 + (3 - j)]);
-        }
+        // W_N^{u + B3 j} = W_N^u * exp(-2 pi i j/8)
+        wp[0] = tt.wN; wp[1] = twid16<2, -1>(tt.wN); wp[2] = twid16<4, -1>(tt.wN); wp[3] = twid16<6, -1>(tt.wN);
+#pragma unroll
+        for (int j = 0; j < 4; j++) split_both(P[j], Q[3 - j], wp[j], X[j], X[4 + (3 - j)]);
         X[8] = make_float2(0.f, 0.f);
     } else {
         X[0] = make_float2(P[0].x + P[0].y, 0.f);
@@ -229,17 +302,18 @@ PV_DEV void cforward(int tid, const FrameIO &io, const CTables &tb, const float 
 }
 
 template <int LOG2N, class Sync, class Hook, class PreLast>
-PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const float *ring, float2 *bufA,
-                            float2 *bufB, float *magS, int32_t *dS, unsigned long long *psi, float *acc,
+PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const CThreadTw &tt, const float *ring,
+                            float2 *bufA, float2 *bufB, float *magS, int32_t *dS, unsigned long long *psi, float *acc,
                             CState &st, int pos0, int Hs, Sync sync, Hook hook, PreLast pre_last_sync)
 {
     using C = CShape<LOG2N>;
     using S = Shape<LOG2N>;
     constexpr int N = C::N, B3 = C::B3, M = C::M, NB = C::NB;
+    constexpr bool TWREG = (2 * C::C1 == C::T) && (2 * C::C2 == C::T);
     const int u = tid;
     const int tP = u, tQ = (u == 0) ? B3 / 2 : B3 - u;
     float2 X[9], wp[4];
-    cforward<LOG2N>(tid, io, tb, ring, bufA, bufB, sync, hook, X, wp);
+    cforward<LOG2N, TWREG>(tid, io, tb, tt, ring, bufA, bufB, sync, hook, X, wp);
     // ---- analysis: magnitude, phase (turns*2^32), unwrapped phase difference ----
     const bool first = st.have_prev == 0;
 #pragma unroll
@@ -249,15 +323,16 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
         const float2 x = X[sl];
         const uint32_t Pc = phase_turns32(x.x, x.y);
         magS[bin] = sqrtf(x.x * x.x + x.y * x.y);
-        dS[bin] = first ? (int32_t)Pc : (int32_t)(Pc - st.Pprev[sl] - PV_LDG(tb.nomA + bin));
+        // nomA[bin] = (bin*Ha*2^32/N) mod 2^32 (see pv_capi.cu): two integer ops instead of a table load
+        const uint32_t nomA = ((uint32_t)bin * (uint32_t)tb.Ha) << (32 - LOG2N);
+        dS[bin] = first ? (int32_t)Pc : (int32_t)(Pc - st.Pprev[sl] - nomA);
         st.Pprev[sl] = Pc;
     }
     st.have_prev = 1;
     sync();
     // ---- synthesis, one voice at a time ----
     for (int v = 0; v < tb.V; v++) {
-        const int32_t *alo = tb.a_lo + v * NB, *ahi = tb.a_hi + v * NB;
-        const unsigned long long *nomS = tb.nomS + (size_t)v * NB;
+        const uint4 *gt = tb.gather + ((size_t)v * C::T + u) * 9;
         unsigned long long *ps = psi + (size_t)v * NB;
         const unsigned long long Rq = tb.Rq[v];
         float2 Y[9];
@@ -266,14 +341,15 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
             Y[sl] = make_float2(0.f, 0.f);
             if (sl == 8 && u != 0) break;
             const int s = slot_bin<B3>(u, sl);
-            const int lo = PV_LDG(alo + s), hi = PV_LDG(ahi + s);
+            const uint4 ge = PV_LDG(gt + sl);            // {a_lo, a_hi, nomS}
+            const int lo = (int)ge.x, hi = (int)ge.y;
             if (lo > hi) continue;                       // no analysis bin maps here
             float m = 0.f;
             for (int a = lo; a <= hi; a++) m += magS[a];
             const int32_t d = dS[hi];
             unsigned long long p;
             if (first) p = (unsigned long long)(uint32_t)d << 32;
-            else p = ps[s] + PV_LDG(nomS + s) + (unsigned long long)((long long)d * (long long)Rq);
+            else p = ps[s] + (((unsigned long long)ge.w << 32) | ge.z) + (unsigned long long)((long long)d * (long long)Rq);
             ps[s] = p;
             const float2 cs = cis_turns64(p);
             Y[sl] = make_float2(m * cs.x, m * cs.y);
@@ -300,10 +376,24 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
             }
         }
         Tables itb{nullptr, nullptr, tb.tw2n, tb.itw1, tb.itw2, tb.win};
-        inverse_1<LOG2N>(tP, itb, Zp, bufA);
-        inverse_1<LOG2N>(tQ, itb, Zq, bufA);
-        inverse_23_ola<LOG2N>(tid, itb, bufA, bufB, acc + (size_t)v * N, pos0, Hs, false, tb.scale, sync,
-                              [&]() { if (v + 1 == tb.V) pre_last_sync(); });
+        if (u != 0) {
+            // exp(+2 pi i m1 u/(N/2)) = conj(W_N^{2 m1 u}); for t1 = B3-u: j^m1 * W_N^{2 m1 u}
+            const float2 w6 = cmul(tt.w2, tt.w4);
+            inverse_1_tw<LOG2N>(tP, cconj(tt.w2), cconj(tt.w4), cconj(w6), Zp, bufA);
+            inverse_1_tw<LOG2N>(tQ, mul_pj(tt.w2), make_float2(-tt.w4.x, -tt.w4.y), mul_mj(w6), Zq, bufA);
+        } else {
+            inverse_1<LOG2N>(tP, itb, Zp, bufA);
+            inverse_1<LOG2N>(tQ, itb, Zq, bufA);
+        }
+        if constexpr (TWREG) {
+            float2 e[8];
+            tw_expand(tt.ip2, e);
+            inverse_23_ola<LOG2N>(tid, itb, bufA, bufB, acc + (size_t)v * N, pos0, Hs, false, tb.scale, sync,
+                                  [&]() { if (v + 1 == tb.V) pre_last_sync(); }, RegTw2{e});
+        } else {
+            inverse_23_ola<LOG2N>(tid, itb, bufA, bufB, acc + (size_t)v * N, pos0, Hs, false, tb.scale, sync,
+                                  [&]() { if (v + 1 == tb.V) pre_last_sync(); });
+        }
         (void)S::T;
     }
     (void)M;
@@ -311,18 +401,20 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
 
 // Analysis-only frame for the phase-carry aggregate: updates P_prev and sum += D (k >= 1).
 template <int LOG2N, class Sync>
-PV_DEV void frame_aggregate(int tid, const FrameIO &io, const CTables &tb, float2 *bufA, float2 *bufB, CState &st,
-                            long long (&sumD)[9], uint32_t (&Pfirst)[9], Sync sync)
+PV_DEV void frame_aggregate(int tid, const FrameIO &io, const CTables &tb, const CThreadTw &tt, float2 *bufA,
+                            float2 *bufB, CState &st, long long (&sumD)[9], uint32_t (&Pfirst)[9], Sync sync)
 {
     using C = CShape<LOG2N>;
+    constexpr bool TWREG = (2 * C::C1 == C::T) && (2 * C::C2 == C::T);
     float2 X[9], wp[4];
-    cforward<LOG2N>(tid, io, tb, nullptr, bufA, bufB, sync, []() {}, X, wp);
+    cforward<LOG2N, TWREG>(tid, io, tb, tt, nullptr, bufA, bufB, sync, []() {}, X, wp);
 #pragma unroll
     for (int sl = 0; sl < 9; sl++) {
         if (sl == 8 && tid != 0) break;
         const int bin = slot_bin<C::B3>(tid, sl);
         const uint32_t Pc = phase_turns32(X[sl].x, X[sl].y);
-        if (st.have_prev) sumD[sl] += (long long)(int32_t)(Pc - st.Pprev[sl] - PV_LDG(tb.nomA + bin));
+        const uint32_t nomA = ((uint32_t)bin * (uint32_t)tb.Ha) << (32 - LOG2N);
+        if (st.have_prev) sumD[sl] += (long long)(int32_t)(Pc - st.Pprev[sl] - nomA);
         else Pfirst[sl] = Pc;
         st.Pprev[sl] = Pc;
     }

@@ -78,6 +78,7 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
     unsigned long long *st_psi = state ? reinterpret_cast<unsigned long long *>(state + 8 + ((NB * 4 + 7) / 8) * 8) : nullptr;
     float *st_acc = st_psi ? reinterpret_cast<float *>(st_psi + (size_t)V * NB) : nullptr;
 
+    const CThreadTw tt = load_cthread_tw<LOG2N>(tid, tb);
     CState st;
     st.have_prev = 0;
 #pragma unroll
@@ -125,7 +126,7 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
             }
             if (k > seg.k_begin) emit(k - 1, (pos0 - Hs) & (N - 1));
         };
-        frame_corrected<LOG2N>(tid, io, tb, ring, bufA, bufB, magS, dS, psi, acc, st, pos0, Hs, sync, hook,
+        frame_corrected<LOG2N>(tid, io, tb, tt, ring, bufA, bufB, magS, dS, psi, acc, st, pos0, Hs, sync, hook,
                                [&]() { if (use_ring) cp_async_wait_all(); });
         pos0 = (pos0 + Hs) & (N - 1);
     }
@@ -161,6 +162,7 @@ corrected_aggregate_kernel(PvDev d, CTables tb, const float *in, long long n_str
     float2 *bufA = reinterpret_cast<float2 *>(smem_raw) + (size_t)g * (C::BUF_A + C::BUF_B);
     float2 *bufB = bufA + C::BUF_A;
     CGroupSync<T, G> sync{g, T >= 32 ? 0xffffffffu : (((1u << (T & 31)) - 1u) << ((threadIdx.x & 31) / T * T))};
+    const CThreadTw tt = load_cthread_tw<LOG2N>(tid, tb);
     CState st;
     long long acc[9];
     uint32_t pf[9];
@@ -174,7 +176,7 @@ corrected_aggregate_kernel(PvDev d, CTables tb, const float *in, long long n_str
     const bool had_prev = st.have_prev;
     for (long long k = 0; k < n_frames; ++k) {
         FrameIO io{in + s * in_stride, n_in, k * (long long)d.Ha, true, vec_in_ok != 0};
-        frame_aggregate<LOG2N>(tid, io, tb, bufA, bufB, st, acc, pf, sync);
+        frame_aggregate<LOG2N>(tid, io, tb, tt, bufA, bufB, st, acc, pf, sync);
     }
 #pragma unroll
     for (int sl = 0; sl < 9; sl++) {
@@ -258,10 +260,10 @@ bool pv_fused_corrected_supported(int N, int Ha, int Hs)
 int pv_fused_corrected_capacity(int N, int V, int sm_count)
 {
     switch (N) {
-        case 256: return ccapacity<8, 1>(V, sm_count);
-        case 512: return ccapacity<9, 1>(V, sm_count);
-        case 1024: return ccapacity<10, 1>(V, sm_count);
-        case 2048: return ccapacity<11, 1>(V, sm_count);
+        case 256: return ccapacity<8, 4>(V, sm_count);
+        case 512: return ccapacity<9, 4>(V, sm_count);
+        case 1024: return ccapacity<10, 4>(V, sm_count);
+        case 2048: return ccapacity<11, 4>(V, sm_count);
         default: return sm_count;
     }
 }
@@ -275,6 +277,8 @@ static CTables make_ctables(const PvDev &d, const PvFusedTables &t)
     for (int v = 0; v < d.V; v++) tb.Rq[v] = d.Rq[v];
     tb.scale = d.gain / (float)d.N;
     tb.V = d.V;
+    tb.Ha = d.Ha;
+    tb.gather = reinterpret_cast<const uint4 *>(d.gather);
     return tb;
 }
 
@@ -328,10 +332,10 @@ cudaError_t pv_launch_corrected_fused(const PvDev &d, const PvFusedTables &t, co
     if (a.n_segs <= 0) return cudaSuccess;
     const CTables tb = make_ctables(d, t);
     switch (d.N) {
-        case 256: return claunch<8, 1>(d, tb, a, st);
-        case 512: return claunch<9, 1>(d, tb, a, st);
-        case 1024: return claunch<10, 1>(d, tb, a, st);
-        case 2048: return claunch<11, 1>(d, tb, a, st);
+        case 256: return claunch<8, 4>(d, tb, a, st);
+        case 512: return claunch<9, 4>(d, tb, a, st);
+        case 1024: return claunch<10, 4>(d, tb, a, st);
+        case 2048: return claunch<11, 4>(d, tb, a, st);
         default: return cudaErrorInvalidValue;
     }
 }

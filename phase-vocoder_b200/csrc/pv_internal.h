@@ -22,6 +22,7 @@ struct PvDev {
     const int32_t *a_lo;  // V*nb
     const int32_t *a_hi;  // V*nb
     const uint64_t *nomS; // V*nb
+    const uint32_t *gather; // V*T*9*4: per-thread packed {a_lo, a_hi, nomS} (pv_fused_tables.h)
     uint64_t Rq[PV_MAX_VOICES];
 };
 

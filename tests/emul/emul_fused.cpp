@@ -94,6 +94,10 @@ static int run_corrected(const float *x, long n_in, int Ha, int Hs, const float 
     for (int v = 0; v < V; v++) tb.Rq[v] = Rq[v];
     tb.scale = gain / (float)N;
     tb.V = V;
+    tb.Ha = Ha;
+    std::vector<uint32_t> gath;
+    build_gather_table(N, V, a_lo, a_hi, (const uint64_t *)nomS, gath);
+    tb.gather = reinterpret_cast<const uint4 *>(gath.data());
     std::vector<float2> bufA(C::BUF_A), bufB(C::BUF_B);
     std::vector<float> acc((size_t)V * N, 0.f), ringbuf(N, 0.f), magS(NB);
     std::vector<int32_t> dS(NB);
@@ -104,6 +108,7 @@ static int run_corrected(const float *x, long n_in, int Ha, int Hs, const float 
     auto body = [&](int tid) {
         auto sync = [&]() { bar.arrive_and_wait(); };
         CState st{};
+        const CThreadTw tt = load_cthread_tw<LOG2N>(tid, tb);
         int pos0 = 0;
         if (use_ring) {
             FrameIO io0{x, n_in, 0, true, true};
@@ -125,7 +130,7 @@ static int run_corrected(const float *x, long n_in, int Ha, int Hs, const float 
                             out[v * out_stride + (k - 1) * (long)Hs + j] = acc[(size_t)v * N + ((pp + j) & (N - 1))];
                 }
             };
-            frame_corrected<LOG2N>(tid, io, tb, ring, bufA.data(), bufB.data(), magS.data(), dS.data(), psi.data(),
+            frame_corrected<LOG2N>(tid, io, tb, tt, ring, bufA.data(), bufB.data(), magS.data(), dS.data(), psi.data(),
                                    acc.data(), st, pos0, Hs, sync, hook, [&]() { cp_async_wait_all(); });
             pos0 = (pos0 + Hs) & (N - 1);
         }
