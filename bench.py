@@ -129,6 +129,28 @@ def cpu_baseline(mode, target_s=12.0):
             "audio_s_per_s": value * HOP / FS}
 
 
+def reference_gpu_build():
+    """The reference's OWN cuFFT pipeline (oracle/_ref/pv_ref_harness: unmodified karnel/*.cu + phaseVocoder.cpp
+    driven like src/main.cpp:204-297) on this GPU.  Comparison point only; window 256 / hop 128 because the
+    unmodified reference cannot launch windows > 512 (<<<1, 2N>>>, karnel/kernel.cu:337)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "pv_ref_harness")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/pv_ref_harness not built (needs the reference checkout at build time)"}
+    import tempfile
+    from signals import multitone
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.f32"), os.path.join(td, "out.f32")
+        multitone(400 * 128 + 256, fs=FS, seed=0).tofile(fin)
+        try:
+            r = subprocess.run([exe, fin, fout, "256", "2"], capture_output=True, text=True, timeout=120)
+            info = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:      # comparison point only: never fail the bench on it
+            return {"unavailable": f"harness failed: {e}"}
+    return {"value": info["frames_per_s"], "unit": "frames/s", "window": 256, "hop": 128,
+            "frames": info["frames_synth"], "analysis_s": info["analysis_s"], "resynthesis_s": info["resynthesis_s"],
+            "note": "unmodified reference kernels + cuFFT plan per frame + managed-memory attach per call, 1 channel"}
+
+
 def run_reference(args):
     """--impl reference: the reference has no CPU implementation of this path (src/phaseVocoder.cpp only
     launches CUDA), so the timed arm is the oracle PORT of its pipeline on all host threads."""
@@ -356,6 +378,8 @@ def run_ours(args):
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         line["other_mode"] = other
+        if world == 1:
+            line["reference_gpu_build"] = reference_gpu_build()
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.mode)
         print(json.dumps(line), flush=True)
