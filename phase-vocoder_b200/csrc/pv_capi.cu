@@ -46,6 +46,8 @@ struct pv_handle {
     size_t in_cap = 0, out_cap = 0;
     void *d_state = nullptr;
     size_t state_cap = 0;
+    void *d_scratch_state = nullptr;
+    size_t scratch_cap = 0;
     cudaStream_t copy_stream = nullptr;
     // accounting
     int64_t launches = 0;
@@ -339,6 +341,7 @@ void pv_destroy(pv_handle *h)
     cudaFree(h->d_in);
     cudaFree(h->d_out);
     cudaFree(h->d_state);
+    cudaFree(h->d_scratch_state);
     for (auto &e : h->events) {
         cudaEventDestroy(e.first);
         cudaEventDestroy(e.second);
@@ -454,11 +457,14 @@ int pv_corrected_aggregate(pv_handle *h, const float *in, int64_t n_streams, int
                            uint32_t *P_last, void *cuda_stream)
 {
     if (!h || !in || !sumD || n_streams < 0 || n_frames < 0) return fail(PV_ERR_PARAM, "pv_corrected_aggregate: bad argument");
-    if (h->p.mode != PV_MODE_CORRECTED || !h->fused)
-        return fail(PV_ERR_PARAM, "pv_corrected_aggregate needs a corrected-mode handle with a supported window");
+    if (h->p.mode != PV_MODE_CORRECTED) return fail(PV_ERR_PARAM, "pv_corrected_aggregate needs a corrected-mode handle");
     DeviceGuard guard(h->device);
-    PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, in, n_streams, in_stride, n_in, n_frames, P_prev, sumD, P_first,
-                                          P_last, (cudaStream_t)cuda_stream));
+    if (h->fused && !getenv("PV_FORCE_GENERIC"))
+        PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, in, n_streams, in_stride, n_in, n_frames, P_prev, sumD,
+                                              P_first, P_last, (cudaStream_t)cuda_stream));
+    else
+        PV_CUDA(pv_launch_aggregate_generic(h->dev, in, n_streams, in_stride, n_in, n_frames, P_prev, sumD, P_first,
+                                            P_last, (cudaStream_t)cuda_stream));
     h->launches++;
     return PV_OK;
 }
@@ -468,7 +474,7 @@ int pv_corrected_state_from_carry(pv_handle *h, int64_t n_streams, const uint32_
 {
     if (!h || !state || n_streams < 0 || n_before < 0 || (n_before > 0 && (!P_first || !sumD || !P_prev)))
         return fail(PV_ERR_PARAM, "pv_corrected_state_from_carry: bad argument");
-    if (h->p.mode != PV_MODE_CORRECTED || !h->fused)
+    if (h->p.mode != PV_MODE_CORRECTED)
         return fail(PV_ERR_PARAM, "pv_corrected_state_from_carry needs a corrected-mode handle");
     DeviceGuard guard(h->device);
     PV_CUDA(pv_launch_state_from_carry(h->dev, h->ft, n_streams, P_first, sumD, n_before, P_prev, state,
@@ -495,8 +501,6 @@ int pv_process_device_ex(pv_handle *h, const float *in, int64_t n_streams, int64
     if (n_streams == 0 || n_frames == skip_frames) return PV_OK;
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    if (h->p.mode != PV_MODE_COMPAT && !h->fused)
-        return fail(PV_ERR_UNSUPPORTED, "corrected mode needs window in {256,512,1024,2048} and an even hop_out");
     int rc = plan_segments(h, n_streams, n_frames, skip_frames, flags, st);
     if (rc != PV_OK) return rc;
     PvProcessArgs a{};
@@ -518,8 +522,23 @@ int pv_process_device_ex(pv_handle *h, const float *in, int64_t n_streams, int64
         PV_CUDA(cudaEventCreate(&e1));
         PV_CUDA(cudaEventRecord(e0, st));
     }
-    if (h->p.mode == PV_MODE_CORRECTED) PV_CUDA(pv_launch_corrected_fused(h->dev, h->ft, a, st));
-    else if (h->fused && !getenv("PV_FORCE_GENERIC")) PV_CUDA(pv_launch_compat_fused(h->dev, h->ft, a, st));
+    const bool force_generic = getenv("PV_FORCE_GENERIC") != nullptr;
+    if (h->p.mode == PV_MODE_CORRECTED && (!h->fused || force_generic)) {
+        // shape-generic kernel: works on the per-stream state in global memory; without a caller state a
+        // library-owned scratch state is used
+        if (!a.state) {
+            const size_t need = (size_t)n_streams * pv_state_bytes(h);
+            if (need > h->scratch_cap) {
+                cudaFree(h->d_scratch_state);
+                h->d_scratch_state = nullptr;
+                PV_CUDA(cudaMalloc(&h->d_scratch_state, need));
+                h->scratch_cap = need;
+            }
+            a.state = (unsigned char *)h->d_scratch_state;
+        }
+        PV_CUDA(pv_launch_corrected_generic(h->dev, a, st));
+    } else if (h->p.mode == PV_MODE_CORRECTED) PV_CUDA(pv_launch_corrected_fused(h->dev, h->ft, a, st));
+    else if (h->fused && !force_generic) PV_CUDA(pv_launch_compat_fused(h->dev, h->ft, a, st));
     else PV_CUDA(pv_launch_compat_generic(h->dev, a, st));
     h->launches++;
     if (h->timing) {
@@ -544,6 +563,7 @@ int pv_process_host(pv_handle *h, const float *in, int64_t n_streams, int64_t in
     if (state) {
         if ((size_t)n_streams * sb > h->state_cap) {
             cudaFree(h->d_state);
+    cudaFree(h->d_scratch_state);
             h->d_state = nullptr;
             PV_CUDA(cudaMalloc(&h->d_state, (size_t)n_streams * sb));
             h->state_cap = (size_t)n_streams * sb;

@@ -18,6 +18,8 @@
 //   G /N, half swap, win  karnel/kernel.cu:130-138, 51-59, 75-81
 //   H overlap-add         karnel/kernel.cu:111-119
 //   I emit hop            src/main.cpp:281-295
+#include <algorithm>
+
 #include "pv_internal.h"
 
 namespace {
@@ -128,14 +130,16 @@ __device__ void build_inverse_input(float2 *z, YF Y, const PvDev &d)
 }
 
 // Steps G+H for one frame: r = unnormalised packed inverse output, acc = OLA ring of N floats.
-__device__ void ola_accumulate(float *acc, const float2 *r, int pos0, bool zero_frame, const PvDev &d)
+__device__ void ola_accumulate(float *acc, const float2 *r, int pos0, bool zero_frame, const PvDev &d,
+                               float scale = 0.f)
 {
     const int N = d.N, h = N >> 1, keep = N - d.Hs;
+    if (scale == 0.f) scale = 1.0f / (float)N;      // x/N == x*(1/N) exactly for a power of two
     for (int n = threadIdx.x; n < h; n += blockDim.x) {
         const float2 v = zero_frame ? make_float2(0.f, 0.f) : r[n];
         const int i = (2 * n + h) & (N - 1);        // half swap: y'[i] = y[(i+N/2) mod N]
-        const float y0 = (v.x / (float)N) * d.win[i];
-        const float y1 = (v.y / (float)N) * d.win[i + 1];
+        const float y0 = (v.x * scale) * d.win[i];
+        const float y1 = (v.y * scale) * d.win[i + 1];
         const int p0 = (pos0 + i) & (N - 1), p1 = (pos0 + i + 1) & (N - 1);
         acc[p0] = (i < keep ? acc[p0] : 0.f) + y0;
         acc[p1] = (i + 1 < keep ? acc[p1] : 0.f) + y1;
@@ -262,7 +266,222 @@ compat_generic_kernel(PvDev d, PvProcessArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// generic fused CORRECTED stream kernel: one CTA per stream, any power-of-two window.
+// Stream state (previous phase, phase accumulators, OLA rings) lives in the per-stream state buffer in
+// global memory (L2 resident); the arithmetic is the specification of DESIGN.md "corrected mode".
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t g_phase_turns32(float re, float im)
+{
+    const float t = atan2f(im, re) * 0.15915494309189535f;
+    return (uint32_t)__float2ll_rn(t * 4294967296.0f);
+}
+
+__global__ void __launch_bounds__(kGenericThreads)
+corrected_generic_kernel(PvDev d, PvProcessArgs a)
+{
+    extern __shared__ float2 sm[];
+    const int N = d.N, M = N >> 1, NB = M + 1, V = d.V, Hs = d.Hs;
+    float2 *bufA = sm, *bufB = sm + NB, *Ys = sm + 2 * NB;
+    float *magS = reinterpret_cast<float *>(sm + 3 * NB);
+    int32_t *dS = reinterpret_cast<int32_t *>(magS + NB);
+    const PvSegment seg = a.segs[blockIdx.x];
+    const float *in = a.in + seg.stream * a.in_stride;
+    float *out = a.out + seg.stream * a.out_stream_stride;
+    unsigned char *state = a.state + seg.stream * a.state_stride;        // always present (caller or scratch)
+    uint32_t *hdr = reinterpret_cast<uint32_t *>(state);
+    uint32_t *Pprev = hdr + 2;
+    unsigned long long *psi = reinterpret_cast<unsigned long long *>(state + 8 + ((NB * 4 + 7) / 8) * 8);
+    float *acc = reinterpret_cast<float *>(psi + (size_t)V * NB);
+    const float scale = d.gain / (float)N;
+    const int lsh = 32 - d.lgN;
+
+    // The state stores each voice's accumulated frame linearly (index 0 = first sample of the LAST frame).
+    // It is used in place as a ring: the next frame starts at linear index Hs, and its last Hs samples
+    // overwrite the already-emitted entries [0, Hs) (ola_accumulate's "fresh tail" rule).
+    const bool have_prev0 = seg.carry_in ? hdr[0] != 0 : false;
+    bool have_prev = have_prev0;
+    int pos0 = seg.carry_in ? (Hs & (N - 1)) : 0;
+    if (!seg.carry_in)
+        for (int i = threadIdx.x; i < V * N; i += blockDim.x) acc[i] = 0.f;
+    __syncthreads();
+
+    for (long long k = seg.k_begin; k < seg.k_end; ++k) {
+        // ---- forward: N-point real FFT as N/2 complex points ----
+        const long long base = k * (long long)d.Ha;
+        for (int m = threadIdx.x; m < M; m += blockDim.x) {
+            const int i = (M + 2 * m) & (N - 1);
+            const long long g = base + i;
+            const float x0 = g < a.n_in ? in[g] : 0.f, x1 = g + 1 < a.n_in ? in[g + 1] : 0.f;
+            bufA[m] = make_float2(x0 * d.win[i], x1 * d.win[i + 1]);
+        }
+        __syncthreads();
+        const float2 *C = fft_stockham(bufA, bufB, M, 4, d.tw, false);
+        for (int kk = threadIdx.x; kk <= M / 2; kk += blockDim.x) {
+            float2 xk, xm;
+            if (kk == 0) {
+                xk = make_float2(C[0].x + C[0].y, 0.f);
+                xm = make_float2(C[0].x - C[0].y, 0.f);
+            } else {
+                const float2 aa = C[kk];
+                float2 bb = C[M - kk];
+                const float2 e = make_float2(0.5f * (aa.x + bb.x), 0.5f * (aa.y - bb.y));
+                const float2 o = make_float2(0.5f * (aa.y + bb.y), -0.5f * (aa.x - bb.x));
+                const float2 t = cmul(d.tw[2 * kk], o);          // W_N^k = exp(-j*pi*2k/N)
+                xk = make_float2(e.x + t.x, e.y + t.y);
+                xm = make_float2(e.x - t.x, -(e.y - t.y));
+            }
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                const int bin = side ? M - kk : kk;
+                if (side && bin == kk) break;                     // kk == M/2: self-mirrored
+                const float2 x = side ? xm : xk;
+                const uint32_t Pc = g_phase_turns32(x.x, x.y);
+                magS[bin] = sqrtf(x.x * x.x + x.y * x.y);
+                const uint32_t nomA = ((uint32_t)bin * (uint32_t)d.Ha) << lsh;
+                dS[bin] = have_prev ? (int32_t)(Pc - Pprev[bin] - nomA) : (int32_t)Pc;
+                Pprev[bin] = Pc;
+            }
+        }
+        __syncthreads();
+        // ---- synthesis per voice ----
+        for (int v = 0; v < V; v++) {
+            for (int s = threadIdx.x; s < NB; s += blockDim.x) {
+                const int lo = d.a_lo[v * NB + s], hi = d.a_hi[v * NB + s];
+                float2 y = make_float2(0.f, 0.f);
+                if (lo <= hi) {
+                    float m = 0.f;
+                    for (int b = lo; b <= hi; b++) m += magS[b];
+                    const int32_t dd = dS[hi];
+                    unsigned long long p;
+                    if (!have_prev) p = (unsigned long long)(uint32_t)dd << 32;
+                    else p = psi[(size_t)v * NB + s] + d.nomS[v * NB + s] +
+                             (unsigned long long)((long long)dd * (long long)d.Rq[v]);
+                    psi[(size_t)v * NB + s] = p;
+                    const float t = (float)(int32_t)(p >> 32) * (1.0f / 4294967296.0f);
+                    float sn, cs;
+                    sincospif(2.0f * t, &sn, &cs);
+                    y = make_float2(m * cs, m * sn);
+                }
+                Ys[s] = y;
+            }
+            __syncthreads();
+            float2 *Z = bufA;
+            build_inverse_input(Z, [&](int kk) { return Ys[kk]; }, d);
+            __syncthreads();
+            const float2 *r = fft_stockham(Z, bufB, M, 4, d.tw, true);
+            float *ac = acc + (size_t)v * N;
+            ola_accumulate(ac, r, pos0, false, d, scale);
+            __syncthreads();
+            if (k >= seg.k_emit) {
+                float *o = out + v * a.out_voice_stride + k * (long long)Hs;
+                for (int j = threadIdx.x; j < Hs; j += blockDim.x) o[j] = ac[(pos0 + j) & (N - 1)];
+            }
+            __syncthreads();
+        }
+        have_prev = true;
+        pos0 = (pos0 + Hs) & (N - 1);
+    }
+    // leave the state in its linear form: accumulated frame after the last frame at index 0
+    const int plast = (pos0 - Hs) & (N - 1);
+    if (threadIdx.x == 0) { hdr[0] = 1u; hdr[1] = 0u; }
+    for (int v = 0; v < V; v++) {
+        float *ac = acc + (size_t)v * N;
+        // rotate the ring by plast through shared memory
+        float *tmp = reinterpret_cast<float *>(sm);
+        for (int i = threadIdx.x; i < N; i += blockDim.x) tmp[i] = ac[(plast + i) & (N - 1)];
+        __syncthreads();
+        for (int i = threadIdx.x; i < N; i += blockDim.x) ac[i] = tmp[i];
+        __syncthreads();
+    }
+}
+
+// generic phase-carry aggregate (analysis only), one CTA per stream -- see pv_corrected_aggregate
+__global__ void __launch_bounds__(kGenericThreads)
+aggregate_generic_kernel(PvDev d, const float *__restrict__ in_all, long long in_stride, long long n_in,
+                         long long n_frames, const uint32_t *P_prev, long long *sumD, uint32_t *P_first, uint32_t *P_last)
+{
+    extern __shared__ float2 sm[];
+    const int N = d.N, M = N >> 1, NB = M + 1, lsh = 32 - d.lgN;
+    float2 *bufA = sm, *bufB = sm + NB;
+    uint32_t *Pp = reinterpret_cast<uint32_t *>(sm + 2 * NB);
+    const long long s = blockIdx.x;
+    const float *in = in_all + s * in_stride;
+    bool have_prev = P_prev != nullptr;
+    for (int b = threadIdx.x; b < NB; b += blockDim.x) {
+        Pp[b] = have_prev ? P_prev[s * NB + b] : 0u;
+        sumD[s * NB + b] = 0;
+        if (P_first) P_first[s * NB + b] = 0u;
+    }
+    __syncthreads();
+    for (long long k = 0; k < n_frames; ++k) {
+        const long long base = k * (long long)d.Ha;
+        for (int m = threadIdx.x; m < M; m += blockDim.x) {
+            const int i = (M + 2 * m) & (N - 1);
+            const long long g = base + i;
+            const float x0 = g < n_in ? in[g] : 0.f, x1 = g + 1 < n_in ? in[g + 1] : 0.f;
+            bufA[m] = make_float2(x0 * d.win[i], x1 * d.win[i + 1]);
+        }
+        __syncthreads();
+        const float2 *C = fft_stockham(bufA, bufB, M, 4, d.tw, false);
+        for (int kk = threadIdx.x; kk <= M / 2; kk += blockDim.x) {
+            float2 xk, xm;
+            if (kk == 0) {
+                xk = make_float2(C[0].x + C[0].y, 0.f);
+                xm = make_float2(C[0].x - C[0].y, 0.f);
+            } else {
+                const float2 aa = C[kk], bb = C[M - kk];
+                const float2 e = make_float2(0.5f * (aa.x + bb.x), 0.5f * (aa.y - bb.y));
+                const float2 o = make_float2(0.5f * (aa.y + bb.y), -0.5f * (aa.x - bb.x));
+                const float2 t = cmul(d.tw[2 * kk], o);
+                xk = make_float2(e.x + t.x, e.y + t.y);
+                xm = make_float2(e.x - t.x, -(e.y - t.y));
+            }
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                const int bin = side ? M - kk : kk;
+                if (side && bin == kk) break;
+                const float2 x = side ? xm : xk;
+                const uint32_t Pc = g_phase_turns32(x.x, x.y);
+                const uint32_t nomA = ((uint32_t)bin * (uint32_t)d.Ha) << lsh;
+                if (have_prev) sumD[s * NB + bin] += (long long)(int32_t)(Pc - Pp[bin] - nomA);
+                else if (P_first) P_first[s * NB + bin] = Pc;
+                Pp[bin] = Pc;
+            }
+        }
+        have_prev = true;
+        __syncthreads();
+    }
+    if (P_last)
+        for (int b = threadIdx.x; b < NB; b += blockDim.x) P_last[s * NB + b] = Pp[b];
+}
+
 }  // namespace
+
+cudaError_t pv_launch_aggregate_generic(const PvDev &d, const float *in, int64_t n_streams, int64_t in_stride, int64_t n_in,
+                                        int64_t n_frames, const uint32_t *P_prev, int64_t *sumD, uint32_t *P_first,
+                                        uint32_t *P_last, cudaStream_t st)
+{
+    if (n_streams <= 0) return cudaSuccess;
+    const size_t NB = d.N / 2 + 1;
+    const size_t smem = sizeof(float2) * 2 * NB + sizeof(uint32_t) * NB;
+    cudaError_t e = cudaFuncSetAttribute(aggregate_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    aggregate_generic_kernel<<<(unsigned)n_streams, kGenericThreads, smem, st>>>(
+        d, in, in_stride, n_in, n_frames, P_prev, reinterpret_cast<long long *>(sumD), P_first, P_last);
+    return cudaGetLastError();
+}
+
+cudaError_t pv_launch_corrected_generic(const PvDev &d, const PvProcessArgs &a, cudaStream_t st)
+{
+    if (a.n_segs <= 0) return cudaSuccess;
+    const size_t NB = d.N / 2 + 1;
+    const size_t smem = std::max(sizeof(float2) * 3 * NB + sizeof(float) * 2 * NB, sizeof(float) * (size_t)d.N);
+    cudaError_t e = cudaFuncSetAttribute(corrected_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    corrected_generic_kernel<<<a.n_segs, kGenericThreads, smem, st>>>(d, a);
+    return cudaGetLastError();
+}
 
 cudaError_t pv_launch_analysis_batch(const PvDev &d, const float *in, int64_t n_in, int64_t n_frames,
                                      float *out_magphase, cudaStream_t st)

@@ -77,3 +77,8 @@ cudaError_t pv_launch_test_overlap_add(const PvDev &d, const float *in, const fl
                                        cudaStream_t st);
 // generic (any N / hop) fused compat path
 cudaError_t pv_launch_compat_generic(const PvDev &d, const PvProcessArgs &a, cudaStream_t st);
+cudaError_t pv_launch_aggregate_generic(const PvDev &d, const float *in, int64_t n_streams, int64_t in_stride, int64_t n_in,
+                                        int64_t n_frames, const uint32_t *P_prev, int64_t *sumD, uint32_t *P_first,
+                                        uint32_t *P_last, cudaStream_t st);
+// generic (any window) fused corrected path; a.state must be non-null (caller's or library scratch)
+cudaError_t pv_launch_corrected_generic(const PvDev &d, const PvProcessArgs &a, cudaStream_t st);

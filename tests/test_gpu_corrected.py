@@ -51,6 +51,9 @@ CASES = [
     (512, 128, 128, [0.75], 80, 0.0),
     (1024, 256, 256, [1.0, 1.5], 50, 0.0),
     (2048, 512, 256, [1.0], 40, 0.0),                                  # time compression
+    (4096, 1024, 1024, [1.0, 2.0], 24, 1e-3),                          # C5 shape (generic kernel)
+    (4096, 1024, 1024, [SEMI7], 24, 0.0),
+    (128, 32, 32, [1.0, 1.5], 100, 0.0),                               # small window (generic kernel)
     (2048, 512, 512, [1.0, 2.0], 60, 1e-3),                            # integer R: noise floor is harmless
     (256, 64, 128, [1.0], 150, 1e-3),                                  # x2 stretch, R = 2
 ]
@@ -159,3 +162,20 @@ def test_corrected_many_streams_host_path():
     for s in (0, 151, 299):
         want, _ = po.process_corrected(x[s], N, H, H, win, [1.0, 1.5], nf)
         assert snr_db(want[0], d[s, 0]) > 100 and snr_db(want[1], d[s, 1]) > 60
+
+
+def test_generic_corrected_kernel_matches_fused(monkeypatch):
+    """The shape-generic corrected kernel (windows outside 256..2048) against the tuned one, incl. state carry."""
+    N, Ha, Hs, nf = 1024, 256, 256, 50
+    betas = [1.0, f32(1.5)]
+    x = multitone(N + nf * Ha, seed=12, noise=0.0)
+    xd = dev(x)[None, :]
+    fused = make(N, Ha, Hs, betas).process(xd, nf).cpu().numpy()
+    monkeypatch.setenv("PV_FORCE_GENERIC", "1")
+    pv = make(N, Ha, Hs, betas)
+    gen = pv.process(xd, nf).cpu().numpy()
+    assert snr_db(fused[0, 0], gen[0, 0]) > 100 and snr_db(fused[0, 1], gen[0, 1]) > 60
+    st = torch.zeros(pv.state_bytes(), dtype=torch.uint8, device="cuda")
+    a = pv.process(xd, 21, state=st, flags=pvb200.CARRY_OUT).cpu().numpy()
+    b = pv.process(xd[:, 21 * Ha:], nf - 21, state=st, flags=pvb200.CARRY_IN | pvb200.CARRY_OUT).cpu().numpy()
+    assert np.array_equal(np.concatenate([a, b], axis=2), gen)

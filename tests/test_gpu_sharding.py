@@ -35,6 +35,7 @@ def _run_ranks(world, fn):
 
 
 @pytest.mark.parametrize("N,Ha,Hs,betas,nf,world", [(2048, 512, 512, [1.4983071], 203, 4), (256, 64, 64, [1.0, 1.5, 2.0], 1001, 4),
+                                                    (4096, 1024, 1024, [1.4983071], 81, 4),          # C5 shape
                                                     (1024, 256, 512, [1.0], 150, 3)])
 def test_corrected_frame_sharding_is_bit_exact(N, Ha, Hs, betas, nf, world):
     x = torch.from_numpy(multitone(N + nf * Ha, seed=8, noise=1e-3)).cuda()
