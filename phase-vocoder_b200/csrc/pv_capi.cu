@@ -36,6 +36,7 @@ struct pv_handle {
     PvFusedTables ft;
     float2 *d_ft[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // segment plan cache
+    std::vector<PvSegment> h_segs;
     PvSegment *d_segs = nullptr;
     size_t segs_cap = 0;
     int32_t n_segs = 0;
@@ -48,7 +49,7 @@ struct pv_handle {
     size_t state_cap = 0;
     void *d_scratch_state = nullptr;
     size_t scratch_cap = 0;
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
     // accounting
     int64_t launches = 0;
     bool timing = false;
@@ -160,7 +161,8 @@ int plan_segments(pv_handle *h, int64_t n_streams, int64_t n_frames, int64_t ski
     int64_t seg_len = (n_frames + per_stream - 1) / per_stream;
     const int64_t min_len = std::max<int64_t>(32 * halo, 32);
     if (seg_len < min_len) seg_len = min_len;
-    std::vector<PvSegment> segs;
+    std::vector<PvSegment> &segs = h->h_segs;       // kept alive in the handle: the upload is asynchronous
+    segs.clear();
     for (int64_t s = 0; s < n_streams; s++) {
         for (int64_t k0 = skip; k0 < n_frames; k0 += seg_len) {
             PvSegment g{};
@@ -180,9 +182,9 @@ int plan_segments(pv_handle *h, int64_t n_streams, int64_t n_frames, int64_t ski
         PV_CUDA(cudaMalloc((void **)&h->d_segs, sizeof(PvSegment) * segs.size()));
         h->segs_cap = segs.size();
     }
-    // pageable source: the runtime stages it before returning, so `segs` may die afterwards
-    PV_CUDA(cudaMemcpyAsync(h->d_segs, segs.data(), sizeof(PvSegment) * segs.size(), cudaMemcpyHostToDevice, st));
-    PV_CUDA(cudaStreamSynchronize(st));
+    // One blocking upload per new shape; every later launch of the same shape (any stream) reuses it.
+    (void)st;
+    PV_CUDA(cudaMemcpy(h->d_segs, segs.data(), sizeof(PvSegment) * segs.size(), cudaMemcpyHostToDevice));
     h->n_segs = (int32_t)segs.size();
     h->plan_streams = n_streams;
     h->plan_frames = n_frames;
@@ -342,6 +344,8 @@ void pv_destroy(pv_handle *h)
     cudaFree(h->d_out);
     cudaFree(h->d_state);
     cudaFree(h->d_scratch_state);
+    for (auto ps : h->pipe)
+        if (ps) cudaStreamDestroy(ps);
     for (auto &e : h->events) {
         cudaEventDestroy(e.first);
         cudaEventDestroy(e.second);
@@ -483,10 +487,26 @@ int pv_corrected_state_from_carry(pv_handle *h, int64_t n_streams, const uint32_
     return PV_OK;
 }
 
+static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_t plan_streams, int64_t in_stride,
+                        int64_t n_in, int64_t n_analysed, int64_t n_frames, int64_t skip_frames, float *out,
+                        int64_t out_stream_stride, int64_t out_voice_stride, void *state, int32_t flags,
+                        void *cuda_stream);
+
 int pv_process_device_ex(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride, int64_t n_in,
                          int64_t n_analysed, int64_t n_frames, int64_t skip_frames, float *out,
                          int64_t out_stream_stride, int64_t out_voice_stride, void *state, int32_t flags,
                          void *cuda_stream)
+{
+    return process_impl(h, in, n_streams, n_streams, in_stride, n_in, n_analysed, n_frames, skip_frames, out,
+                        out_stream_stride, out_voice_stride, state, flags, cuda_stream);
+}
+
+// `plan_streams` >= n_streams: the segment table is planned (and cached) for plan_streams streams; a call
+// with fewer streams uses its stream-major prefix.  Lets the pipelined host path reuse one plan for all chunks.
+static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_t plan_streams, int64_t in_stride,
+                        int64_t n_in, int64_t n_analysed, int64_t n_frames, int64_t skip_frames, float *out,
+                        int64_t out_stream_stride, int64_t out_voice_stride, void *state, int32_t flags,
+                        void *cuda_stream)
 {
     if (!h || !in || !out) return fail(PV_ERR_PARAM, "pv_process: null argument");
     if (skip_frames < 0 || skip_frames > n_frames) return fail(PV_ERR_PARAM, "pv_process: bad skip_frames");
@@ -501,7 +521,7 @@ int pv_process_device_ex(pv_handle *h, const float *in, int64_t n_streams, int64
     if (n_streams == 0 || n_frames == skip_frames) return PV_OK;
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    int rc = plan_segments(h, n_streams, n_frames, skip_frames, flags, st);
+    int rc = plan_segments(h, plan_streams, n_frames, skip_frames, flags, st);
     if (rc != PV_OK) return rc;
     PvProcessArgs a{};
     a.in = in;
@@ -515,7 +535,7 @@ int pv_process_device_ex(pv_handle *h, const float *in, int64_t n_streams, int64
     a.state = (unsigned char *)state;
     a.state_stride = (int64_t)pv_state_bytes(h);
     a.segs = h->d_segs;
-    a.n_segs = h->n_segs;
+    a.n_segs = (int32_t)((int64_t)h->n_segs / plan_streams * n_streams);      // stream-major table
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->timing) {
         PV_CUDA(cudaEventCreate(&e0));
@@ -554,36 +574,57 @@ int pv_process_host(pv_handle *h, const float *in, int64_t n_streams, int64_t in
 {
     if (!h || !in || !out) return fail(PV_ERR_PARAM, "pv_process_host: null argument");
     if (n_streams <= 0 || n_frames <= 0) return PV_OK;
+    if ((flags & (PV_PROCESS_CARRY_IN | PV_PROCESS_CARRY_OUT)) && !state)
+        return fail(PV_ERR_PARAM, "pv_process_host: carry requested without a state buffer");
     DeviceGuard guard(h->device);
     const int64_t V = h->p.n_voices, n_out = n_frames * h->p.hop_out;
     int rc = ensure(&h->d_in, &h->in_cap, (size_t)(n_streams * n_in));
     if (rc == PV_OK) rc = ensure(&h->d_out, &h->out_cap, (size_t)(n_streams * V * n_out));
     if (rc != PV_OK) return rc;
     const size_t sb = pv_state_bytes(h);
-    if (state) {
-        if ((size_t)n_streams * sb > h->state_cap) {
-            cudaFree(h->d_state);
-    cudaFree(h->d_scratch_state);
-            h->d_state = nullptr;
-            PV_CUDA(cudaMalloc(&h->d_state, (size_t)n_streams * sb));
-            h->state_cap = (size_t)n_streams * sb;
-        }
-        if (flags & PV_PROCESS_CARRY_IN)
-            PV_CUDA(cudaMemcpyAsync(h->d_state, state, (size_t)n_streams * sb, cudaMemcpyHostToDevice, nullptr));
+    // the shape-generic corrected kernel works in a per-stream state buffer: give every chunk its own slice
+    const bool dev_state = state != nullptr || (h->p.mode == PV_MODE_CORRECTED && (!h->fused || getenv("PV_FORCE_GENERIC")));
+    if (dev_state && (size_t)n_streams * sb > h->state_cap) {
+        cudaFree(h->d_state);
+        h->d_state = nullptr;
+        h->state_cap = 0;
+        PV_CUDA(cudaMalloc(&h->d_state, (size_t)n_streams * sb));
+        h->state_cap = (size_t)n_streams * sb;
     }
-    PV_CUDA(cudaMemcpy2DAsync(h->d_in, sizeof(float) * n_in, in, sizeof(float) * in_stride, sizeof(float) * n_in,
-                              (size_t)n_streams, cudaMemcpyHostToDevice, nullptr));
-    rc = pv_process_device(h, h->d_in, n_streams, n_in, n_in, n_analysed, n_frames, h->d_out, V * n_out, n_out,
-                           state ? h->d_state : nullptr, flags, nullptr);
-    if (rc != PV_OK) return rc;
-    for (int64_t v = 0; v < V; v++)
-        PV_CUDA(cudaMemcpy2DAsync(out + v * out_voice_stride, sizeof(float) * out_stream_stride, h->d_out + v * n_out,
-                                  sizeof(float) * V * n_out, sizeof(float) * n_out, (size_t)n_streams,
-                                  cudaMemcpyDeviceToHost, nullptr));
-    if (state && (flags & PV_PROCESS_CARRY_OUT))
-        PV_CUDA(cudaMemcpyAsync(state, h->d_state, (size_t)n_streams * sb, cudaMemcpyDeviceToHost, nullptr));
-    PV_CUDA(cudaStreamSynchronize(nullptr));
-    return PV_OK;
+    for (auto &ps : h->pipe)
+        if (!ps) PV_CUDA(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+    // Software pipeline over chunks of streams on three CUDA streams: the H2D copy of chunk c+1, the kernel
+    // of chunk c and the D2H copy of chunk c-1 overlap (PCIe is full duplex), so a large batch costs about
+    // max(H2D, D2H, kernel) instead of their sum.  Pinned host buffers are needed for real overlap.
+    const int64_t bytes_in = n_streams * n_in * 4;
+    int64_t n_chunks = std::min<int64_t>(16, std::max<int64_t>(1, bytes_in / (64ll << 20)));
+    n_chunks = std::min(n_chunks, n_streams);
+    const int64_t cs = (n_streams + n_chunks - 1) / n_chunks;
+    int c = 0;
+    for (int64_t s0 = 0; s0 < n_streams; s0 += cs, ++c) {
+        const int64_t ns = std::min(cs, n_streams - s0);
+        cudaStream_t st = h->pipe[c % 3];
+        float *di = h->d_in + s0 * n_in, *dout = h->d_out + s0 * V * n_out;
+        unsigned char *dst = dev_state ? (unsigned char *)h->d_state + s0 * sb : nullptr;
+        unsigned char *hst = state ? (unsigned char *)state + s0 * sb : nullptr;
+        if (state && (flags & PV_PROCESS_CARRY_IN))
+            PV_CUDA(cudaMemcpyAsync(dst, hst, (size_t)ns * sb, cudaMemcpyHostToDevice, st));
+        PV_CUDA(cudaMemcpy2DAsync(di, sizeof(float) * n_in, in + s0 * in_stride, sizeof(float) * in_stride,
+                                  sizeof(float) * n_in, (size_t)ns, cudaMemcpyHostToDevice, st));
+        rc = process_impl(h, di, ns, cs, n_in, n_in, n_analysed, n_frames, 0, dout, V * n_out, n_out, dst, flags, st);
+        if (rc != PV_OK) break;
+        for (int64_t v = 0; v < V; v++)
+            PV_CUDA(cudaMemcpy2DAsync(out + s0 * out_stream_stride + v * out_voice_stride, sizeof(float) * out_stream_stride,
+                                      dout + v * n_out, sizeof(float) * V * n_out, sizeof(float) * n_out, (size_t)ns,
+                                      cudaMemcpyDeviceToHost, st));
+        if (state && (flags & PV_PROCESS_CARRY_OUT))
+            PV_CUDA(cudaMemcpyAsync(hst, dst, (size_t)ns * sb, cudaMemcpyDeviceToHost, st));
+    }
+    for (auto &ps : h->pipe) {
+        cudaError_t e = cudaStreamSynchronize(ps);
+        if (e != cudaSuccess && rc == PV_OK) rc = fail(PV_ERR_CUDA, "pipeline stream: %s", cudaGetErrorString(e));
+    }
+    return rc;
 }
 
 int64_t pv_launch_count(const pv_handle *h) { return h ? h->launches : 0; }
