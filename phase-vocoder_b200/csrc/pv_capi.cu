@@ -37,6 +37,16 @@ struct pv_handle {
     float2 *d_ft[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // segment plan cache
     std::vector<PvSegment> h_segs;
+    // split of corrected streams into frame-range parts (intra-GPU phase-carry scan)
+    PvSegment *d_agg_segs = nullptr, *d_api_segs = nullptr;
+    size_t agg_cap = 0, api_cap = 0;
+    int32_t split_parts = 0;
+    int64_t split_streams = -1, split_frames = -1;
+    int64_t *d_S = nullptr, *d_H = nullptr;
+    uint32_t *d_Pf = nullptr;
+    size_t carry_cap = 0;
+    unsigned char *d_slots = nullptr;
+    size_t slots_cap = 0;
     PvSegment *d_segs = nullptr;
     size_t segs_cap = 0;
     int32_t n_segs = 0;
@@ -167,6 +177,7 @@ int plan_segments(pv_handle *h, int64_t n_streams, int64_t n_frames, int64_t ski
         for (int64_t k0 = skip; k0 < n_frames; k0 += seg_len) {
             PvSegment g{};
             g.stream = (int32_t)s;
+            g.state_idx = (int32_t)s;
             g.k_emit = k0;
             g.k_end = std::min(n_frames, k0 + seg_len);
             // the first segment also computes the caller's skipped (halo) frames from frame 0
@@ -186,10 +197,82 @@ int plan_segments(pv_handle *h, int64_t n_streams, int64_t n_frames, int64_t ski
     (void)st;
     PV_CUDA(cudaMemcpy(h->d_segs, segs.data(), sizeof(PvSegment) * segs.size(), cudaMemcpyHostToDevice));
     h->n_segs = (int32_t)segs.size();
+    h->split_streams = -1;           // d_segs now holds this plan, not a corrected split
     h->plan_streams = n_streams;
     h->plan_frames = n_frames;
     h->plan_skip = skip;
     h->plan_flags = flags;
+    return PV_OK;
+}
+
+// Corrected mode with few streams: cut every stream into `parts` frame ranges so that the grid fills the
+// machine.  Two tables (index = stream*parts + part): the analysis ranges for the phase-carry aggregate
+// and the processing ranges (halo + owned frames) that start from the rebuilt state of each part.
+int plan_corrected_split(pv_handle *h, int64_t n_streams, int64_t n_frames, int32_t parts)
+{
+    if (h->split_streams == n_streams && h->split_frames == n_frames && h->split_parts == parts) return PV_OK;
+    const int N = h->p.window, Hs = h->p.hop_out;
+    const int64_t halo = (N - 1) / Hs;
+    const int64_t L = (n_frames + parts - 1) / parts;
+    std::vector<PvSegment> agg((size_t)(n_streams * parts)), proc((size_t)(n_streams * parts));
+    for (int64_t s = 0; s < n_streams; s++)
+        for (int32_t p = 0; p < parts; p++) {
+            const int64_t k0 = std::min<int64_t>(n_frames, p * L), k1 = std::min<int64_t>(n_frames, k0 + L);
+            const int64_t ks = std::max<int64_t>(0, k0 - halo);
+            const size_t i = (size_t)(s * parts + p);
+            PvSegment a{}, q{};
+            a.stream = q.stream = (int32_t)s;
+            a.state_idx = q.state_idx = (int32_t)i;
+            a.k_begin = std::max<int64_t>(0, ks - 1);       // the frame before ks supplies P_prev
+            a.k_emit = k0;
+            a.k_end = k1;
+            q.k_begin = ks;
+            q.k_emit = k0;
+            q.k_end = k1;
+            q.carry_in = ks >= 1 ? 1 : 0;                   // parts that reach frame 0 start fresh
+            q.carry_out = (p == parts - 1) ? 1 : 0;         // the last part leaves the stream's final state in its slot
+            agg[i] = a;
+            proc[i] = q;
+        }
+    const size_t n = agg.size();
+    if (n > h->agg_cap) {
+        cudaFree(h->d_agg_segs);
+        h->d_agg_segs = nullptr;
+        h->agg_cap = 0;
+        PV_CUDA(cudaMalloc((void **)&h->d_agg_segs, sizeof(PvSegment) * n));
+        h->agg_cap = n;
+    }
+    if (n > h->segs_cap) {
+        cudaFree(h->d_segs);
+        h->d_segs = nullptr;
+        h->segs_cap = 0;
+        PV_CUDA(cudaMalloc((void **)&h->d_segs, sizeof(PvSegment) * n));
+        h->segs_cap = n;
+    }
+    PV_CUDA(cudaMemcpy(h->d_agg_segs, agg.data(), sizeof(PvSegment) * n, cudaMemcpyHostToDevice));
+    PV_CUDA(cudaMemcpy(h->d_segs, proc.data(), sizeof(PvSegment) * n, cudaMemcpyHostToDevice));
+    const size_t nb = (size_t)N / 2 + 1;
+    if (n * nb > h->carry_cap) {
+        cudaFree(h->d_S); cudaFree(h->d_H); cudaFree(h->d_Pf);
+        h->d_S = h->d_H = nullptr; h->d_Pf = nullptr; h->carry_cap = 0;
+        PV_CUDA(cudaMalloc((void **)&h->d_S, sizeof(int64_t) * n * nb));
+        PV_CUDA(cudaMalloc((void **)&h->d_H, sizeof(int64_t) * n * nb));
+        PV_CUDA(cudaMalloc((void **)&h->d_Pf, sizeof(uint32_t) * n * nb));
+        h->carry_cap = n * nb;
+    }
+    const size_t sb = pv_state_bytes(h);
+    if (n * sb > h->slots_cap) {
+        cudaFree(h->d_slots);
+        h->d_slots = nullptr;
+        h->slots_cap = 0;
+        PV_CUDA(cudaMalloc((void **)&h->d_slots, n * sb));
+        h->slots_cap = n * sb;
+    }
+    h->split_streams = n_streams;
+    h->split_frames = n_frames;
+    h->split_parts = parts;
+    h->n_segs = (int32_t)n;
+    h->plan_streams = -1;            // the shared d_segs table no longer holds a plan_segments() plan
     return PV_OK;
 }
 
@@ -340,6 +423,12 @@ void pv_destroy(pv_handle *h)
     cudaFree(h->d_gather);
     for (auto p : h->d_ft) cudaFree(p);
     cudaFree(h->d_segs);
+    cudaFree(h->d_agg_segs);
+    cudaFree(h->d_api_segs);
+    cudaFree(h->d_S);
+    cudaFree(h->d_H);
+    cudaFree(h->d_Pf);
+    cudaFree(h->d_slots);
     cudaFree(h->d_in);
     cudaFree(h->d_out);
     cudaFree(h->d_state);
@@ -462,13 +551,30 @@ int pv_corrected_aggregate(pv_handle *h, const float *in, int64_t n_streams, int
 {
     if (!h || !in || !sumD || n_streams < 0 || n_frames < 0) return fail(PV_ERR_PARAM, "pv_corrected_aggregate: bad argument");
     if (h->p.mode != PV_MODE_CORRECTED) return fail(PV_ERR_PARAM, "pv_corrected_aggregate needs a corrected-mode handle");
+    if (n_streams == 0) return PV_OK;
     DeviceGuard guard(h->device);
-    if (h->fused && !getenv("PV_FORCE_GENERIC"))
-        PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, in, n_streams, in_stride, n_in, n_frames, P_prev, sumD,
-                                              P_first, P_last, (cudaStream_t)cuda_stream));
-    else
-        PV_CUDA(pv_launch_aggregate_generic(h->dev, in, n_streams, in_stride, n_in, n_frames, P_prev, sumD, P_first,
-                                            P_last, (cudaStream_t)cuda_stream));
+    std::vector<PvSegment> segs((size_t)n_streams);
+    for (int64_t s = 0; s < n_streams; s++) {
+        PvSegment g{};
+        g.stream = (int32_t)s;
+        g.state_idx = (int32_t)s;
+        g.carry_in = P_prev != nullptr;
+        g.k_begin = 0;
+        g.k_emit = 0;
+        g.k_end = n_frames;
+        segs[(size_t)s] = g;
+    }
+    if (segs.size() > h->api_cap) {
+        cudaFree(h->d_api_segs);
+        h->d_api_segs = nullptr;
+        h->api_cap = 0;
+        PV_CUDA(cudaMalloc((void **)&h->d_api_segs, sizeof(PvSegment) * segs.size()));
+        h->api_cap = segs.size();
+    }
+    PV_CUDA(cudaMemcpy(h->d_api_segs, segs.data(), sizeof(PvSegment) * segs.size(), cudaMemcpyHostToDevice));
+    PvAggArgs a{in, in_stride, n_in, h->d_api_segs, (int32_t)n_streams, P_prev, sumD, nullptr, P_first, P_last};
+    if (h->fused && !getenv("PV_FORCE_GENERIC")) PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, a, (cudaStream_t)cuda_stream));
+    else PV_CUDA(pv_launch_aggregate_generic(h->dev, a, (cudaStream_t)cuda_stream));
     h->launches++;
     return PV_OK;
 }
@@ -521,6 +627,64 @@ static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_
     if (n_streams == 0 || n_frames == skip_frames) return PV_OK;
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    // ---- corrected mode, few streams: split into frame-range parts with an on-device phase-carry scan ----
+    const bool force_generic0 = getenv("PV_FORCE_GENERIC") != nullptr;
+    if (h->p.mode == PV_MODE_CORRECTED && skip_frames == 0 && !(flags & PV_PROCESS_CARRY_IN) &&
+        plan_streams == n_streams && !getenv("PV_NO_SPLIT")) {
+        const int N = h->p.window;
+        const int64_t halo = (N - 1) / h->p.hop_out;
+        const int64_t min_len = std::max<int64_t>(16 * (halo + 1), 32);     // keep the extra analysis + halo small
+        int64_t parts = std::min<int64_t>(n_frames / min_len, (h->capacity * 2 + n_streams - 1) / n_streams);
+        if (parts >= 2) {
+            const int64_t L = (n_frames + parts - 1) / parts;
+            parts = (n_frames + L - 1) / L;                                  // no empty trailing part
+        }
+        if (parts >= 2 && n_streams * parts <= 1 << 20) {
+            int rc0 = plan_corrected_split(h, n_streams, n_frames, (int32_t)parts);
+            if (rc0 != PV_OK) return rc0;
+            const bool fused_ok = h->fused && !force_generic0;
+            PvAggArgs ag{in, in_stride, n_in, h->d_agg_segs, h->n_segs, nullptr, h->d_S, h->d_H, h->d_Pf, nullptr};
+            if (fused_ok) PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, ag, st));
+            else PV_CUDA(pv_launch_aggregate_generic(h->dev, ag, st));
+            const int64_t sb = (int64_t)pv_state_bytes(h);
+            PV_CUDA(pv_launch_split_states(h->dev, n_streams, (int32_t)parts, h->d_segs, h->d_S, h->d_H, h->d_Pf,
+                                           h->d_slots, sb, st));
+            PvProcessArgs a{};
+            a.in = in;
+            a.in_stride = in_stride;
+            a.n_in = n_in;
+            a.n_analysed = n_analysed;
+            a.n_frames = n_frames;
+            a.out = out;
+            a.out_stream_stride = out_stream_stride;
+            a.out_voice_stride = out_voice_stride;
+            a.state = h->d_slots;
+            a.state_stride = sb;
+            a.segs = h->d_segs;
+            a.n_segs = h->n_segs;
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (h->timing) {
+                PV_CUDA(cudaEventCreate(&e0));
+                PV_CUDA(cudaEventCreate(&e1));
+                PV_CUDA(cudaEventRecord(e0, st));
+            }
+            if (fused_ok) PV_CUDA(pv_launch_corrected_fused(h->dev, h->ft, a, st));
+            else PV_CUDA(pv_launch_corrected_generic(h->dev, a, st));
+            if (h->timing) {
+                PV_CUDA(cudaEventRecord(e1, st));
+                h->events.emplace_back(e0, e1);
+            }
+            h->launches += 3;
+            if ((flags & PV_PROCESS_CARRY_OUT) && state) {
+                // the last part of every stream holds the stream's final state (the generic kernel always
+                // leaves it in the slot; the fused kernel writes it when carry_out is set -> set below)
+                const size_t last = (size_t)(parts - 1);
+                PV_CUDA(cudaMemcpy2DAsync(state, (size_t)sb, h->d_slots + last * (size_t)sb, (size_t)sb * (size_t)parts, (size_t)sb,
+                                          (size_t)n_streams, cudaMemcpyDeviceToDevice, st));
+            }
+            return PV_OK;
+        }
+    }
     int rc = plan_segments(h, plan_streams, n_frames, skip_frames, flags, st);
     if (rc != PV_OK) return rc;
     PvProcessArgs a{};

@@ -69,7 +69,7 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
     const PvSegment seg = a.segs[seg_idx];
     const float *in = a.in + seg.stream * a.in_stride;
     float *out = a.out + seg.stream * a.out_stream_stride;
-    unsigned char *state = a.state ? a.state + seg.stream * a.state_stride : nullptr;
+    unsigned char *state = a.state ? a.state + (long long)seg.state_idx * a.state_stride : nullptr;
     const int Hs = d.Hs;
 
     // state layout: [have_prev u32][pad][P_prev u32 x NB (8-byte padded)][psi u64 x V*NB][acc f32 x V*N]
@@ -143,48 +143,49 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
     }
 }
 
-// ---- phase-carry aggregate: analysis only, one group per stream ----
-// sumD[stream][bin] = sum over frames k >= 1 (k >= 0 when P_prev is given) of the unwrapped phase
-// difference D_k; P_first = phase of the first frame, P_last = phase of the last frame.
+// ---- phase-carry aggregate: analysis only, one group per frame-range segment (PvAggArgs) ----
 template <int LOG2N>
 __global__ void __launch_bounds__(CLaunch<LOG2N>::THREADS)
-corrected_aggregate_kernel(PvDev d, CTables tb, const float *in, long long n_streams, long long in_stride,
-                           long long n_in, long long n_frames, const uint32_t *P_prev, long long *sumD,
-                           uint32_t *P_first, uint32_t *P_last, int vec_in_ok)
+corrected_aggregate_kernel(PvDev d, CTables tb, PvAggArgs a, int vec_in_ok)
 {
     using C = CShape<LOG2N>;
     using L = CLaunch<LOG2N>;
     constexpr int T = C::T, G = L::G, NB = C::NB, B3 = C::B3;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int g = threadIdx.x / T, tid = threadIdx.x % T;
-    const long long s = (long long)blockIdx.x * G + g;
-    if (s >= n_streams) return;
+    const long long sg = (long long)blockIdx.x * G + g;
+    if (sg >= a.n_segs) return;
+    const PvSegment seg = a.segs[sg];
     float2 *bufA = reinterpret_cast<float2 *>(smem_raw) + (size_t)g * (C::BUF_A + C::BUF_B);
     float2 *bufB = bufA + C::BUF_A;
     CGroupSync<T, G> sync{g, T >= 32 ? 0xffffffffu : (((1u << (T & 31)) - 1u) << ((threadIdx.x & 31) / T * T))};
     const CThreadTw tt = load_cthread_tw<LOG2N>(tid, tb);
     CState st;
-    long long acc[9];
+    long long accS[9], accH[9];
     uint32_t pf[9];
-    st.have_prev = P_prev != nullptr;
+    const bool carried = seg.carry_in && a.P_prev != nullptr;
+    st.have_prev = carried;
 #pragma unroll
     for (int sl = 0; sl < 9; sl++) {
-        acc[sl] = 0;
+        accS[sl] = 0;
+        accH[sl] = 0;
         pf[sl] = 0;
-        st.Pprev[sl] = (P_prev && (sl < 8 || tid == 0)) ? P_prev[s * NB + slot_bin<B3>(tid, sl)] : 0u;
+        st.Pprev[sl] = (carried && (sl < 8 || tid == 0)) ? a.P_prev[(long long)seg.stream * NB + slot_bin<B3>(tid, sl)] : 0u;
     }
-    const bool had_prev = st.have_prev;
-    for (long long k = 0; k < n_frames; ++k) {
-        FrameIO io{in + s * in_stride, n_in, k * (long long)d.Ha, true, vec_in_ok != 0};
-        frame_aggregate<LOG2N>(tid, io, tb, tt, bufA, bufB, st, acc, pf, sync);
+    const float *in = a.in + seg.stream * a.in_stride;
+    for (long long k = seg.k_begin; k < seg.k_end; ++k) {
+        FrameIO io{in, a.n_in, k * (long long)d.Ha, true, vec_in_ok != 0};
+        if (k < seg.k_emit) frame_aggregate<LOG2N>(tid, io, tb, tt, bufA, bufB, st, accH, pf, sync);
+        else frame_aggregate<LOG2N>(tid, io, tb, tt, bufA, bufB, st, accS, pf, sync);
     }
 #pragma unroll
     for (int sl = 0; sl < 9; sl++) {
         if (sl == 8 && tid != 0) break;
-        const int bin = slot_bin<B3>(tid, sl);
-        sumD[s * NB + bin] = acc[sl];
-        if (P_first) P_first[s * NB + bin] = had_prev ? 0u : pf[sl];
-        if (P_last) P_last[s * NB + bin] = st.Pprev[sl];
+        const long long o = sg * NB + slot_bin<B3>(tid, sl);
+        a.S[o] = accS[sl];
+        if (a.H) a.H[o] = accH[sl];
+        if (a.P_first) a.P_first[o] = carried ? 0u : pf[sl];
+        if (a.P_last) a.P_last[o] = st.Pprev[sl];
     }
 }
 
@@ -283,9 +284,7 @@ static CTables make_ctables(const PvDev &d, const PvFusedTables &t)
 }
 
 template <int LOG2N>
-static cudaError_t agg_launch(const PvDev &d, const CTables &tb, const float *in, int64_t n_streams, int64_t in_stride,
-                              int64_t n_in, int64_t n_frames, const uint32_t *P_prev, int64_t *sumD, uint32_t *P_first,
-                              uint32_t *P_last, cudaStream_t st)
+static cudaError_t agg_launch(const PvDev &d, const CTables &tb, const PvAggArgs &a, cudaStream_t st)
 {
     using L = CLaunch<LOG2N>;
     using C = CShape<LOG2N>;
@@ -293,26 +292,78 @@ static cudaError_t agg_launch(const PvDev &d, const CTables &tb, const float *in
     const size_t smem = (size_t)L::G * (C::BUF_A + C::BUF_B) * sizeof(float2);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const bool in_ok = (d.Ha % 2 == 0) && (in_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & 7) == 0);
-    const int grid = (int)((n_streams + L::G - 1) / L::G);
-    kern<<<grid, L::THREADS, smem, st>>>(d, tb, in, n_streams, in_stride, n_in, n_frames, P_prev,
-                                          reinterpret_cast<long long *>(sumD), P_first, P_last, in_ok);
+    const bool in_ok = (d.Ha % 2 == 0) && (a.in_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 7) == 0);
+    const int grid = (a.n_segs + L::G - 1) / L::G;
+    kern<<<grid, L::THREADS, smem, st>>>(d, tb, a, in_ok);
     return cudaGetLastError();
 }
 
-cudaError_t pv_launch_corrected_aggregate(const PvDev &d, const PvFusedTables &t, const float *in, int64_t n_streams,
-                                          int64_t in_stride, int64_t n_in, int64_t n_frames, const uint32_t *P_prev,
-                                          int64_t *sumD, uint32_t *P_first, uint32_t *P_last, cudaStream_t st)
+cudaError_t pv_launch_corrected_aggregate(const PvDev &d, const PvFusedTables &t, const PvAggArgs &a, cudaStream_t st)
 {
-    if (n_streams <= 0) return cudaSuccess;
+    if (a.n_segs <= 0) return cudaSuccess;
     const CTables tb = make_ctables(d, t);
     switch (d.N) {
-        case 256: return agg_launch<8>(d, tb, in, n_streams, in_stride, n_in, n_frames, P_prev, sumD, P_first, P_last, st);
-        case 512: return agg_launch<9>(d, tb, in, n_streams, in_stride, n_in, n_frames, P_prev, sumD, P_first, P_last, st);
-        case 1024: return agg_launch<10>(d, tb, in, n_streams, in_stride, n_in, n_frames, P_prev, sumD, P_first, P_last, st);
-        case 2048: return agg_launch<11>(d, tb, in, n_streams, in_stride, n_in, n_frames, P_prev, sumD, P_first, P_last, st);
+        case 256: return agg_launch<8>(d, tb, a, st);
+        case 512: return agg_launch<9>(d, tb, a, st);
+        case 1024: return agg_launch<10>(d, tb, a, st);
+        case 2048: return agg_launch<11>(d, tb, a, st);
         default: return cudaErrorInvalidValue;
     }
+}
+
+// One block per stream walks its parts in order: running = sum_{q<p} S_q (per bin, int64 in shared memory).
+__global__ void split_states_kernel(PvDev d, CTables tb, int parts, const PvSegment *segs, const long long *S,
+                                    const long long *H, const uint32_t *P_first, unsigned char *slots, long long slot_stride)
+{
+    extern __shared__ long long sh[];
+    const int NB = d.N / 2 + 1, V = tb.V, N = d.N;
+    long long *run = sh, *pre = sh + NB;
+    const long long s = blockIdx.x;
+    for (int b = threadIdx.x; b < NB; b += blockDim.x) run[b] = 0;
+    __syncthreads();
+    const uint32_t *P0 = P_first + (s * parts) * NB;
+    for (int p = 0; p < parts; p++) {
+        const long long gidx = s * parts + p;
+        const PvSegment seg = segs[gidx];
+        if (seg.k_end <= seg.k_emit) break;                        // unused trailing part
+        if (seg.carry_in) {
+            for (int b = threadIdx.x; b < NB; b += blockDim.x) pre[b] = run[b] - H[gidx * NB + b];
+            __syncthreads();
+            unsigned char *st = slots + (long long)seg.state_idx * slot_stride;
+            uint32_t *hdr = reinterpret_cast<uint32_t *>(st);
+            uint32_t *stP = hdr + 2;
+            unsigned long long *psi = reinterpret_cast<unsigned long long *>(st + 8 + ((NB * 4 + 7) / 8) * 8);
+            float *acc = reinterpret_cast<float *>(psi + (size_t)V * NB);
+            if (threadIdx.x == 0) { hdr[0] = 1u; hdr[1] = 0u; }
+            for (int b = threadIdx.x; b < NB; b += blockDim.x) stP[b] = P_first[gidx * NB + b];
+            const unsigned long long nb4 = (unsigned long long)(seg.k_begin - 1);
+            for (int i = threadIdx.x; i < V * NB; i += blockDim.x) {
+                const int v = i / NB;
+                const int lo = tb.a_lo[i], hi = tb.a_hi[i];
+                unsigned long long ps = 0;
+                if (lo <= hi)
+                    ps = ((unsigned long long)P0[hi] << 32) + nb4 * tb.nomS[i] + (unsigned long long)(pre[hi] * (long long)tb.Rq[v]);
+                psi[i] = ps;
+            }
+            for (int i = threadIdx.x; i < V * N; i += blockDim.x) acc[i] = 0.f;
+            __syncthreads();
+        }
+        for (int b = threadIdx.x; b < NB; b += blockDim.x) run[b] += S[gidx * NB + b];
+        __syncthreads();
+    }
+}
+
+cudaError_t pv_launch_split_states(const PvDev &d, int64_t n_streams, int32_t parts, const PvSegment *proc_segs,
+                                   const int64_t *S, const int64_t *H, const uint32_t *P_first, unsigned char *slots,
+                                   int64_t slot_stride, cudaStream_t st)
+{
+    if (n_streams <= 0) return cudaSuccess;
+    PvFusedTables none;
+    const CTables tb = make_ctables(d, none);
+    const size_t smem = sizeof(long long) * 2 * (size_t)(d.N / 2 + 1);
+    split_states_kernel<<<(unsigned)n_streams, 256, smem, st>>>(d, tb, parts, proc_segs, reinterpret_cast<const long long *>(S),
+                                                               reinterpret_cast<const long long *>(H), P_first, slots, slot_stride);
+    return cudaGetLastError();
 }
 
 cudaError_t pv_launch_state_from_carry(const PvDev &d, const PvFusedTables &t, int64_t n_streams, const uint32_t *P_first,

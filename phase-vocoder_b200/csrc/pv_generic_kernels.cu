@@ -288,7 +288,7 @@ corrected_generic_kernel(PvDev d, PvProcessArgs a)
     const PvSegment seg = a.segs[blockIdx.x];
     const float *in = a.in + seg.stream * a.in_stride;
     float *out = a.out + seg.stream * a.out_stream_stride;
-    unsigned char *state = a.state + seg.stream * a.state_stride;        // always present (caller or scratch)
+    unsigned char *state = a.state + (long long)seg.state_idx * a.state_stride;   // always present (caller or scratch)
     uint32_t *hdr = reinterpret_cast<uint32_t *>(state);
     uint32_t *Pprev = hdr + 2;
     unsigned long long *psi = reinterpret_cast<unsigned long long *>(state + 8 + ((NB * 4 + 7) / 8) * 8);
@@ -396,30 +396,33 @@ corrected_generic_kernel(PvDev d, PvProcessArgs a)
     }
 }
 
-// generic phase-carry aggregate (analysis only), one CTA per stream -- see pv_corrected_aggregate
+// generic phase-carry aggregate (analysis only), one CTA per frame-range segment (PvAggArgs)
 __global__ void __launch_bounds__(kGenericThreads)
-aggregate_generic_kernel(PvDev d, const float *__restrict__ in_all, long long in_stride, long long n_in,
-                         long long n_frames, const uint32_t *P_prev, long long *sumD, uint32_t *P_first, uint32_t *P_last)
+aggregate_generic_kernel(PvDev d, PvAggArgs a)
 {
     extern __shared__ float2 sm[];
     const int N = d.N, M = N >> 1, NB = M + 1, lsh = 32 - d.lgN;
     float2 *bufA = sm, *bufB = sm + NB;
     uint32_t *Pp = reinterpret_cast<uint32_t *>(sm + 2 * NB);
-    const long long s = blockIdx.x;
-    const float *in = in_all + s * in_stride;
-    bool have_prev = P_prev != nullptr;
+    const long long sg = blockIdx.x;
+    const PvSegment seg = a.segs[sg];
+    const float *in = a.in + seg.stream * a.in_stride;
+    const bool carried = seg.carry_in && a.P_prev != nullptr;
+    bool have_prev = carried;
     for (int b = threadIdx.x; b < NB; b += blockDim.x) {
-        Pp[b] = have_prev ? P_prev[s * NB + b] : 0u;
-        sumD[s * NB + b] = 0;
-        if (P_first) P_first[s * NB + b] = 0u;
+        Pp[b] = carried ? a.P_prev[(long long)seg.stream * NB + b] : 0u;
+        a.S[sg * NB + b] = 0;
+        if (a.H) a.H[sg * NB + b] = 0;
+        if (a.P_first) a.P_first[sg * NB + b] = 0u;
     }
     __syncthreads();
-    for (long long k = 0; k < n_frames; ++k) {
+    for (long long k = seg.k_begin; k < seg.k_end; ++k) {
         const long long base = k * (long long)d.Ha;
+        long long *dst = reinterpret_cast<long long *>((k < seg.k_emit) ? a.H : a.S);
         for (int m = threadIdx.x; m < M; m += blockDim.x) {
             const int i = (M + 2 * m) & (N - 1);
             const long long g = base + i;
-            const float x0 = g < n_in ? in[g] : 0.f, x1 = g + 1 < n_in ? in[g + 1] : 0.f;
+            const float x0 = g < a.n_in ? in[g] : 0.f, x1 = g + 1 < a.n_in ? in[g + 1] : 0.f;
             bufA[m] = make_float2(x0 * d.win[i], x1 * d.win[i + 1]);
         }
         __syncthreads();
@@ -444,31 +447,28 @@ aggregate_generic_kernel(PvDev d, const float *__restrict__ in_all, long long in
                 const float2 x = side ? xm : xk;
                 const uint32_t Pc = g_phase_turns32(x.x, x.y);
                 const uint32_t nomA = ((uint32_t)bin * (uint32_t)d.Ha) << lsh;
-                if (have_prev) sumD[s * NB + bin] += (long long)(int32_t)(Pc - Pp[bin] - nomA);
-                else if (P_first) P_first[s * NB + bin] = Pc;
+                if (have_prev) { if (dst) dst[sg * NB + bin] += (long long)(int32_t)(Pc - Pp[bin] - nomA); }
+                else if (a.P_first) a.P_first[sg * NB + bin] = Pc;
                 Pp[bin] = Pc;
             }
         }
         have_prev = true;
         __syncthreads();
     }
-    if (P_last)
-        for (int b = threadIdx.x; b < NB; b += blockDim.x) P_last[s * NB + b] = Pp[b];
+    if (a.P_last)
+        for (int b = threadIdx.x; b < NB; b += blockDim.x) a.P_last[sg * NB + b] = Pp[b];
 }
 
 }  // namespace
 
-cudaError_t pv_launch_aggregate_generic(const PvDev &d, const float *in, int64_t n_streams, int64_t in_stride, int64_t n_in,
-                                        int64_t n_frames, const uint32_t *P_prev, int64_t *sumD, uint32_t *P_first,
-                                        uint32_t *P_last, cudaStream_t st)
+cudaError_t pv_launch_aggregate_generic(const PvDev &d, const PvAggArgs &a, cudaStream_t st)
 {
-    if (n_streams <= 0) return cudaSuccess;
+    if (a.n_segs <= 0) return cudaSuccess;
     const size_t NB = d.N / 2 + 1;
     const size_t smem = sizeof(float2) * 2 * NB + sizeof(uint32_t) * NB;
     cudaError_t e = cudaFuncSetAttribute(aggregate_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    aggregate_generic_kernel<<<(unsigned)n_streams, kGenericThreads, smem, st>>>(
-        d, in, in_stride, n_in, n_frames, P_prev, reinterpret_cast<long long *>(sumD), P_first, P_last);
+    aggregate_generic_kernel<<<(unsigned)a.n_segs, kGenericThreads, smem, st>>>(d, a);
     return cudaGetLastError();
 }
 

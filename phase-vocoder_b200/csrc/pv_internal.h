@@ -32,7 +32,7 @@ struct PvSegment {
     int32_t stream;
     int32_t carry_in;     // 1: k_begin == 0 and the accumulator starts from the stream state
     int32_t carry_out;    // 1: this segment holds the last frame and writes the stream state
-    int32_t pad;
+    int32_t state_idx;    // state slot (stream index, or a per-part slot when a corrected stream is split)
     int64_t k_begin, k_emit, k_end;
 };
 
@@ -61,9 +61,21 @@ cudaError_t pv_launch_compat_fused(const PvDev &d, const PvFusedTables &t, const
 bool pv_fused_corrected_supported(int N, int Ha, int Hs);
 int pv_fused_corrected_capacity(int N, int V, int sm_count);
 cudaError_t pv_launch_corrected_fused(const PvDev &d, const PvFusedTables &t, const PvProcessArgs &a, cudaStream_t st);
-cudaError_t pv_launch_corrected_aggregate(const PvDev &d, const PvFusedTables &t, const float *in, int64_t n_streams,
-                                          int64_t in_stride, int64_t n_in, int64_t n_frames, const uint32_t *P_prev,
-                                          int64_t *sumD, uint32_t *P_first, uint32_t *P_last, cudaStream_t st);
+// Analysis-only pass over a table of frame ranges.  For segment g: frames [k_begin, k_end) of stream
+// segs[g].stream are analysed; the unwrapped phase differences D_k (defined when a previous phase exists:
+// k > k_begin, or k == k_begin with carry_in and P_prev[stream]) are summed into H[g] for k < k_emit and
+// into S[g] for k >= k_emit.  P_first[g] / P_last[g] = phase of the first / last analysed frame.
+// H, P_first, P_last may be null.  Outputs are indexed by segment.
+struct PvAggArgs {
+    const float *in;
+    int64_t in_stride, n_in;
+    const PvSegment *segs;
+    int32_t n_segs;
+    const uint32_t *P_prev;   // [stream][nb], used by segments with carry_in
+    int64_t *S, *H;
+    uint32_t *P_first, *P_last;
+};
+cudaError_t pv_launch_corrected_aggregate(const PvDev &d, const PvFusedTables &t, const PvAggArgs &a, cudaStream_t st);
 cudaError_t pv_launch_state_from_carry(const PvDev &d, const PvFusedTables &t, int64_t n_streams, const uint32_t *P_first,
                                        const int64_t *sumD, int64_t n_before, const uint32_t *P_prev, void *state,
                                        int64_t state_stride, cudaStream_t st);
@@ -77,8 +89,12 @@ cudaError_t pv_launch_test_overlap_add(const PvDev &d, const float *in, const fl
                                        cudaStream_t st);
 // generic (any N / hop) fused compat path
 cudaError_t pv_launch_compat_generic(const PvDev &d, const PvProcessArgs &a, cudaStream_t st);
-cudaError_t pv_launch_aggregate_generic(const PvDev &d, const float *in, int64_t n_streams, int64_t in_stride, int64_t n_in,
-                                        int64_t n_frames, const uint32_t *P_prev, int64_t *sumD, uint32_t *P_first,
-                                        uint32_t *P_last, cudaStream_t st);
+cudaError_t pv_launch_aggregate_generic(const PvDev &d, const PvAggArgs &a, cudaStream_t st);
+// Turns the per-part aggregates of split corrected streams into the carried state of every part:
+// part p of stream s (parts_per_stream each, table index s*parts + p) starts computing at frame ks[p];
+// its state slot gets psi = (P0[a] << 32) + (ks-1)*nomS + Rq*(sum_{q<p} S_q - H_p)[a], P_prev = P_first[p].
+cudaError_t pv_launch_split_states(const PvDev &d, int64_t n_streams, int32_t parts, const PvSegment *proc_segs,
+                                   const int64_t *S, const int64_t *H, const uint32_t *P_first, unsigned char *slots,
+                                   int64_t slot_stride, cudaStream_t st);
 // generic (any window) fused corrected path; a.state must be non-null (caller's or library scratch)
 cudaError_t pv_launch_corrected_generic(const PvDev &d, const PvProcessArgs &a, cudaStream_t st);

@@ -179,3 +179,22 @@ def test_generic_corrected_kernel_matches_fused(monkeypatch):
     a = pv.process(xd, 21, state=st, flags=pvb200.CARRY_OUT).cpu().numpy()
     b = pv.process(xd[:, 21 * Ha:], nf - 21, state=st, flags=pvb200.CARRY_IN | pvb200.CARRY_OUT).cpu().numpy()
     assert np.array_equal(np.concatenate([a, b], axis=2), gen)
+
+
+@pytest.mark.parametrize("N,Ha,Hs,betas,nf,S", [(2048, 512, 512, [SEMI7], 3000, 1), (256, 64, 64, [1.0, SEMI4, 2.0], 6890, 2),
+                                                (1024, 102, 512, [1.0], 4300, 1), (4096, 1024, 1024, [SEMI7], 2000, 2)])
+def test_corrected_intra_gpu_split_is_bit_exact(monkeypatch, N, Ha, Hs, betas, nf, S):
+    """Few long streams are cut into frame-range parts on ONE GPU (aggregate -> per-part state -> process);
+    the result and the carried-out state are bit-identical to the sequential single-segment run."""
+    x = torch.from_numpy(np.stack([multitone(N + nf * Ha, seed=60 + s, noise=1e-3) for s in range(S)])).cuda()
+    pv = make(N, Ha, Hs, betas)
+    st_a = torch.zeros((S, pv.state_bytes()), dtype=torch.uint8, device="cuda")
+    split = pv.process(x, nf, state=st_a, flags=pvb200.CARRY_OUT).cpu().numpy()
+    assert pv.launch_count() == 3                      # aggregate + state build + process
+    monkeypatch.setenv("PV_NO_SPLIT", "1")
+    pv2 = make(N, Ha, Hs, betas)
+    st_b = torch.zeros((S, pv2.state_bytes()), dtype=torch.uint8, device="cuda")
+    seq = pv2.process(x, nf, state=st_b, flags=pvb200.CARRY_OUT).cpu().numpy()
+    assert pv2.launch_count() == 1
+    assert np.array_equal(split, seq)
+    assert torch.equal(st_a, st_b)

@@ -56,7 +56,7 @@ def test_corrected_frame_sharding_is_bit_exact(N, Ha, Hs, betas, nf, world):
     parts = _run_ranks(world, fn)
     got = np.concatenate(parts, axis=2)
     assert np.array_equal(got, full)
-    assert launches0 == 1
+    assert launches0 in (1, 3)        # 3 when the single stream is split on the GPU (aggregate + states + process)
 
 
 @pytest.mark.parametrize("N,Ha,Hs,nf,world", [(2048, 512, 512, 203, 4), (256, 64, 64, 999, 8), (4096, 1024, 1024, 50, 2)])

@@ -1,0 +1,93 @@
+#!/usr/bin/env python
+"""Runs the five BASELINE.json configs (C1..C5) on one GPU: parity against the oracle on a
+bounded sample of each and device-resident throughput.  Prints a markdown table (kept in
+profiles/r01_configs.md).  Usage on the GPU box: python tools/run_configs.py"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "phase-vocoder_b200"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import numpy as np
+import torch
+
+import pv_oracle as po
+import pvb200
+from signals import c3_multitone, multitone, snr_db
+
+f32 = lambda b: float(np.float32(b))
+
+
+def timed(fn, n=5):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def run(name, N, Ha, Hs, mode, betas, streams, frames, fs, gen, check_streams=2, check_frames=None):
+    corrected = mode == "corrected"
+    wt = pvb200.WIN_HANN_PERIODIC if corrected else pvb200.WIN_HAMMING
+    pv = pvb200.PhaseVocoder(N, hop_in=Ha, hop_out=Hs, mode=pvb200.MODE_CORRECTED if corrected else pvb200.MODE_COMPAT,
+                             window_type=wt, pitch=tuple(betas))
+    n_in = N + (frames - 1) * Ha
+    xs = np.stack([gen(n_in, s) for s in range(min(streams, 16))])
+    x = torch.from_numpy(np.tile(xs, ((streams + len(xs) - 1) // len(xs), 1))[:streams]).cuda()
+    out = torch.empty((streams, len(betas) if corrected else 1, frames * Hs), device="cuda")
+    ms = timed(lambda: pv.process(x, frames, out=out))
+    got = out[:check_streams].cpu().numpy()
+    cf = frames if check_frames is None else min(frames, check_frames)
+    worst = 1e9
+    win = po.window(po.WIN_HANN_PERIODIC if corrected else po.WIN_HAMMING, N)
+    for s in range(check_streams):
+        if corrected:
+            want, _ = po.process_corrected(xs[s], N, Ha, Hs, win, betas, cf)
+        else:
+            w, _ = po.process_compat(xs[s], N, Ha, Hs, win, cf, cf)
+            want = w[None]
+        for v in range(want.shape[0]):
+            worst = min(worst, snr_db(want[v], got[s, v, :cf * Hs]))
+    fps = streams * frames / (ms * 1e-3)
+    V = len(betas) if corrected else 1
+    gbs = fps * (4 * Ha + 4 * V * Hs) / 1e9
+    print(f"| {name} | {N} | {Ha}/{Hs} | {mode} | {V} | {streams} x {frames} | {ms:.3f} | {fps/1e6:.2f} M | "
+          f"{fps*Ha/fs:,.0f} | {gbs:.0f} | {worst:.1f} |", flush=True)
+
+
+def main():
+    print("| config | window | Ha/Hs | mode | voices | streams x frames | ms/launch | frames/s | audio-s/s (input) | "
+          "algorithmic GB/s | worst SNR vs fp64 oracle (dB) |")
+    print("|---|---|---|---|---|---|---|---|---|---|---|")
+    tone = lambda n, s: multitone(n, seed=s, noise=0.0)
+    noisy = lambda n, s: multitone(n, seed=s, noise=1e-3)
+    semi = lambda k: f32(2 ** (k / 12))
+    # C1: 440sine-like, window 256 hop 64: compat plumbing + pitch x1.5 corrected (10 s = 6890 frames)
+    sine = lambda n, s: (0.25 * np.sin(2 * np.pi * 440 * np.arange(n) / 44100)).astype(np.float32)
+    run("C1 compat", 256, 64, 64, "compat", [1.0], 2, 6890, 44100, sine)
+    run("C1 pitch x1.5", 256, 64, 64, "corrected", [1.5], 2, 6890, 44100, sine, check_frames=2000)
+    # C2: window 2048 hop 512, +7 semitones (5.58 s stereo = 2 x 480 frames; and the headline batch)
+    run("C2 file-sized", 2048, 512, 512, "corrected", [semi(7)], 2, 480, 44100, tone)
+    run("C2 headline batch", 2048, 512, 512, "corrected", [semi(7)], 1184, 860, 44100, noisy, check_frames=120)
+    run("C2 headline batch", 2048, 512, 512, "compat", [1.0], 1184, 860, 44100, noisy, check_frames=120)
+    # C3: window 1024, time stretch "in-hop 10 / out-hop 2": hop divisors (102/512) and literal samples (10/2)
+    c3 = lambda n, s: c3_multitone(n)
+    run("C3 divisors 10/2", 1024, 102, 512, "compat", [1.0], 1, 4300, 44100, c3, check_streams=1, check_frames=300)
+    run("C3 divisors 10/2", 1024, 102, 512, "corrected", [1.0], 1, 4300, 44100, c3, check_streams=1, check_frames=300)
+    run("C3 literal 10/2", 1024, 10, 2, "compat", [1.0], 1, 44000, 44100, c3, check_streams=1, check_frames=1500)
+    # C4: 4096 streams x window 256 hop 64 x 4 voices, 10 s each
+    run("C4 harmoniser", 256, 64, 64, "corrected", [1.0, semi(4), semi(7), 2.0], 4096, 6890, 44100, noisy, check_frames=400)
+    # C5: 1 h, 48 kHz, stereo, window 4096 hop 1024 (168 750 frames per channel)
+    run("C5 long file", 4096, 1024, 1024, "compat", [1.0], 2, 168750, 48000, noisy, check_frames=300)
+    run("C5 long file", 4096, 1024, 1024, "corrected", [semi(7)], 2, 20000, 48000, tone, check_frames=100)
+
+
+if __name__ == "__main__":
+    main()
