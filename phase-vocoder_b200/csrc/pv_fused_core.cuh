@@ -58,7 +58,7 @@ struct Tables {
     const float2 *tw2n;   // [N]            exp(-j*pi*k/N) (2N-th roots) for the split / pack steps
     const float2 *itw1;   // [3][B3]        exp(+2 pi i m1 t1 / (N/2))
     const float2 *itw2;   // [(R1-1)][R2]   exp(+2 pi i m2 n3 / B3)
-    const float *win;     // [N]
+    const float *win;     // [N]   analysis window
 };
 
 // Loop-invariant per-thread twiddles kept in registers (used when every thread owns exactly one
@@ -227,11 +227,13 @@ PV_DEV void forward_3(int u, const float2 *bufB, float2 (&P)[8], float2 (&Q)[8])
     dft<8, -1>(Q);
 }
 
-// X[k] of the 2N-point real spectrum from a = C[k], b = C[N-k], w = exp(-j*pi*k/N)
+// 2*X[k] of the 2N-point real spectrum from a = C[k], b = C[N-k], w = exp(-j*pi*k/N).  The factor 2 is
+// carried through the (degree-1 homogeneous) compat map and the linear Hermitian pack and removed by the
+// pre-scaled synthesis window w/(2N): exact, power of two.
 PV_DEV float2 split(float2 a, float2 b, float2 w)
 {
-    const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
-    const float2 o = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));   // (a - conj b)/(2j)
+    const float2 e = make_float2(a.x + b.x, a.y - b.y);
+    const float2 o = make_float2(a.y + b.y, b.x - a.x);          // (a - conj b)/j
     return cadd(e, cmul(w, o));
 }
 
@@ -377,20 +379,29 @@ PV_DEV void inverse_23_ola(int tid, const Tables &tb, float2 *bufA, float2 *bufB
     static_assert(C3 >= T || 2 * C3 == T, "pass 3 cover");
     constexpr bool SPLIT2 = (2 * C2 == T) && (R1 == 16);   // two threads per radix-16 butterfly
     constexpr bool SPLIT3 = (2 * C3 == T) && (R2 == 16);
-    const int keep = N - Hs;
-    // steps G+H for complex output n (samples 2n, 2n+1)
+    // steps G+H for complex output n (samples 2n, 2n+1).  The last Hs slots of the frame are "fresh": the
+    // caller zeroes every hop right after emitting it, so the overlap-add is a plain accumulate.
     auto ola = [&](int n, float2 v) {
         const int i = (2 * n + N / 2) & (N - 1);       // half swap (kernel.cu:51-59)
-        const float2 w = PV_LDG(reinterpret_cast<const float2 *>(tb.win + i));
-        // cudaDivVec kernel.cu:130-138 (x/N == x*(1/N) exactly, N a power of two), cudaWindow :75-81
-        const float y0 = (v.x * scale) * w.x;
-        const float y1 = (v.y * scale) * w.y;
+        // cudaDivVec kernel.cu:130-138 (x/N == x*(1/N) exactly, N a power of two) and cudaWindow :75-81.
+        // One window table serves analysis and synthesis: with 4 CTAs x 51 KB of shared memory only ~24 KB
+        // of L1 remain per SM, and a second (pre-scaled) 8 KB table measurably thrashes it.
+        float2 w = PV_LDG(reinterpret_cast<const float2 *>(tb.win + i));
+        w.x *= scale;
+        w.y *= scale;
         float2 *slot = reinterpret_cast<float2 *>(acc + ((pos0 + i) & (N - 1)));
         float2 a = *slot;
-        a.x = (i < keep ? a.x : 0.f) + y0;             // cudaOverlapAdd kernel.cu:111-119
-        a.y = (i + 1 < keep ? a.y : 0.f) + y1;
+#ifdef PV_EXP_SELECT_OLA
+        const int keep = N - Hs;
+        a.x = (i < keep ? a.x : 0.f) + v.x * w.x;
+        a.y = (i + 1 < keep ? a.y : 0.f) + v.y * w.y;
+#else
+        a.x += v.x * w.x;                              // cudaOverlapAdd kernel.cu:111-119
+        a.y += v.y * w.y;
+#endif
         *slot = a;
     };
+    (void)Hs;
     if (!zero_frame) {
         sync();
         if constexpr (SPLIT2) {
@@ -492,7 +503,8 @@ PV_DEV void frame_compat(int tid, const FrameIO &io, const Tables &tb, const Thr
         hook();
         sync();
     }
-    inverse_23_ola<LOG2N>(tid, tb, bufA, bufB, acc, pos0, Hs, !io.analysed, 1.0f / (float)S::N, sync, []() {});
+    // 1/(2N): the split step above works with 2*X (see split())
+    inverse_23_ola<LOG2N>(tid, tb, bufA, bufB, acc, pos0, Hs, !io.analysed, 0.5f / (float)S::N, sync, []() {});
 }
 
 }  // namespace pvfused

@@ -9,6 +9,12 @@
 #include "pv_fused_corrected.cuh"
 #include "pv_internal.h"
 
+#ifdef PV_EXP_SELECT_OLA
+#define PV_ZERO_ON_EMIT false
+#else
+#define PV_ZERO_ON_EMIT true
+#endif
+
 namespace {
 
 using namespace pvfused;
@@ -102,16 +108,23 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
     }
     sync();
 
-    auto emit = [&](long long kk, int pp) {
-        if (kk < seg.k_emit) return;
+    auto emit = [&](long long kk, int pp, bool zero) {
+        const bool wr = kk >= seg.k_emit;
         for (int v = 0; v < V; v++) {
             float *o = out + v * a.out_voice_stride + kk * (long long)Hs;
-            const float *ac = acc + (size_t)v * N;
-            if (vec_out_ok) {
-                for (int j = 4 * tid; j < Hs; j += 4 * T)
-                    *reinterpret_cast<float4 *>(o + j) = *reinterpret_cast<const float4 *>(ac + ((pp + j) & (N - 1)));
+            float *ac = acc + (size_t)v * N;
+            if (vec_out_ok && (Hs & 3) == 0) {
+                for (int j = 4 * tid; j < Hs; j += 4 * T) {
+                    float4 *sl = reinterpret_cast<float4 *>(ac + ((pp + j) & (N - 1)));
+                    if (wr) *reinterpret_cast<float4 *>(o + j) = *sl;
+                    if (zero) *sl = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             } else {
-                for (int j = tid; j < Hs; j += T) o[j] = ac[(pp + j) & (N - 1)];
+                for (int j = tid; j < Hs; j += T) {
+                    float *sl = ac + ((pp + j) & (N - 1));
+                    if (wr) o[j] = *sl;
+                    if (zero) *sl = 0.f;
+                }
             }
         }
     };
@@ -124,7 +137,7 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
                 FrameIO nx{in, a.n_in, (k + 1) * (long long)d.Ha, true, true};
                 ring_prefetch_coop<N, T>(tid, nx, ring, N - d.Ha);
             }
-            if (k > seg.k_begin) emit(k - 1, (pos0 - Hs) & (N - 1));
+            if (k > seg.k_begin) emit(k - 1, (pos0 - Hs) & (N - 1), PV_ZERO_ON_EMIT);
         };
         frame_corrected<LOG2N>(tid, io, tb, tt, ring, bufA, bufB, magS, dS, psi, acc, st, pos0, Hs, sync, hook,
                                [&]() { if (use_ring) cp_async_wait_all(); });
@@ -132,7 +145,7 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
     }
     sync();
     const int plast = (pos0 - Hs) & (N - 1);
-    emit(seg.k_end - 1, plast);
+    emit(seg.k_end - 1, plast, false);
     if (seg.carry_out && state) {
         if (tid == 0) { st_hdr[0] = (uint32_t)st.have_prev; st_hdr[1] = 0; }
 #pragma unroll

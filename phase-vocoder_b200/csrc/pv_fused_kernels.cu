@@ -13,6 +13,12 @@
 #include "pv_fused_core.cuh"
 #include "pv_internal.h"
 
+#ifdef PV_EXP_SELECT_OLA
+#define PV_ZERO_ON_EMIT false
+#else
+#define PV_ZERO_ON_EMIT true
+#endif
+
 namespace {
 
 using namespace pvfused;
@@ -71,14 +77,23 @@ compat_fused_kernel(PvDev d, Tables tb, PvProcessArgs a, int vec_in_ok, int vec_
     sync();
 
     // emits the output hop of frame kk whose ring position is pp (src/main.cpp:281-295)
-    auto emit = [&](long long kk, int pp) {
-        if (kk < seg.k_emit) return;
+    // `zero`: clear the hop after reading it -- it becomes the fresh tail of the next frame, which lets the
+    // overlap-add be a plain accumulate (no per-sample "first writer" test)
+    auto emit = [&](long long kk, int pp, bool zero) {
+        const bool wr = kk >= seg.k_emit;
         float *o = out + kk * (long long)Hs;
-        if (vec_out_ok) {
-            for (int j = 4 * tid; j < Hs; j += 4 * T)
-                *reinterpret_cast<float4 *>(o + j) = *reinterpret_cast<const float4 *>(acc + ((pp + j) & (N - 1)));
+        if (vec_out_ok && (Hs & 3) == 0) {
+            for (int j = 4 * tid; j < Hs; j += 4 * T) {
+                float4 *sl = reinterpret_cast<float4 *>(acc + ((pp + j) & (N - 1)));
+                if (wr) *reinterpret_cast<float4 *>(o + j) = *sl;
+                if (zero) *sl = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         } else {
-            for (int j = tid; j < Hs; j += T) o[j] = acc[(pp + j) & (N - 1)];
+            for (int j = tid; j < Hs; j += T) {
+                float *sl = acc + ((pp + j) & (N - 1));
+                if (wr) o[j] = *sl;
+                if (zero) *sl = 0.f;
+            }
         }
     };
 
@@ -100,7 +115,7 @@ compat_fused_kernel(PvDev d, Tables tb, PvProcessArgs a, int vec_in_ok, int vec_
                 FrameIO nx{in, a.n_in, (k + 1) * (long long)d.Ha, true, true};
                 ring_prefetch<LOG2N>(tid, nx, ring, N - d.Ha);
             }
-            if (k > seg.k_begin) emit(k - 1, (pos0 - Hs) & (N - 1));
+            if (k > seg.k_begin) emit(k - 1, (pos0 - Hs) & (N - 1), PV_ZERO_ON_EMIT);
         };
         if (RING) cp_async_wait_all();
         frame_compat<LOG2N, TWREG>(tid, io, tb, tt, nan_compat, ring, bufA, bufB, acc, pos0, Hs, sync, hook);
@@ -108,7 +123,7 @@ compat_fused_kernel(PvDev d, Tables tb, PvProcessArgs a, int vec_in_ok, int vec_
     }
     sync();
     const int plast = (pos0 - Hs) & (N - 1);
-    emit(seg.k_end - 1, plast);
+    emit(seg.k_end - 1, plast, false);
     if (seg.carry_out && state)
         for (int i = tid; i < N; i += T) state[i] = acc[(plast + i) & (N - 1)];
 }

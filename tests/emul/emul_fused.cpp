@@ -43,7 +43,10 @@ static int run(const float *x, long n_in, int Ha, int Hs, const float *win, long
                 }
                 if (k > 0) {
                     const int pp = (pos0 - Hs) & (N - 1);
-                    for (int j = tid; j < Hs; j += T) out[(k - 1) * (long)Hs + j] = acc[(pp + j) & (N - 1)];
+                    for (int j = tid; j < Hs; j += T) {
+                        out[(k - 1) * (long)Hs + j] = acc[(pp + j) & (N - 1)];
+                        acc[(pp + j) & (N - 1)] = 0.f;         // emitted hop becomes the fresh tail
+                    }
                 }
             };
             cp_async_wait_all();
@@ -90,6 +93,7 @@ static int run_corrected(const float *x, long n_in, int Ha, int Hs, const float 
     CTables tb{};
     tb.ctw1 = ht.ctw1.data(); tb.ctw2 = ht.ctw2.data(); tb.tw2n = ht.tw2n.data();
     tb.itw1 = ht.itw1.data(); tb.itw2 = ht.itw2.data(); tb.win = win;
+
     tb.nomA = nomA; tb.a_lo = a_lo; tb.a_hi = a_hi; tb.nomS = nomS;
     for (int v = 0; v < V; v++) tb.Rq[v] = Rq[v];
     tb.scale = gain / (float)N;
@@ -126,8 +130,10 @@ static int run_corrected(const float *x, long n_in, int Ha, int Hs, const float 
                 if (k > 0) {
                     const int pp = (pos0 - Hs) & (N - 1);
                     for (int v = 0; v < V; v++)
-                        for (int j = tid; j < Hs; j += T)
+                        for (int j = tid; j < Hs; j += T) {
                             out[v * out_stride + (k - 1) * (long)Hs + j] = acc[(size_t)v * N + ((pp + j) & (N - 1))];
+                            acc[(size_t)v * N + ((pp + j) & (N - 1))] = 0.f;
+                        }
                 }
             };
             frame_corrected<LOG2N>(tid, io, tb, tt, ring, bufA.data(), bufB.data(), magS.data(), dS.data(), psi.data(),
