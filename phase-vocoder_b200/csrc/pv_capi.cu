@@ -359,9 +359,11 @@ int pv_create(const pv_params *params, pv_handle **out)
         for (int b = 0; b < nb; b++) nomA[b] = (uint32_t)(((uint64_t)b * (uint64_t)p.hop_in) << (32 - lg));
         std::vector<int32_t> alo((size_t)V * nb), ahi((size_t)V * nb);
         std::vector<uint64_t> nomS((size_t)V * nb);
-        for (int v = 0; v < V; v++)
+        for (int v = 0; v < V; v++) {
             corrected_tables(N, p.hop_in, p.hop_out, (double)p.pitch[v], &d.Rq[v], &alo[(size_t)v * nb],
                              &ahi[(size_t)v * nb], &nomS[(size_t)v * nb]);
+            d.beta_q[v] = (uint64_t)llround((double)p.pitch[v] * 4294967296.0);
+        }
         double s2 = 0;
         for (int i = 0; i < N; i++) s2 += (double)h->h_win[i] * (double)h->h_win[i];
         d.gain = (float)((double)p.hop_out / s2);
@@ -371,7 +373,7 @@ int pv_create(const pv_params *params, pv_handle **out)
         if (rc == PV_OK) rc = upload(&h->d_nomS, nomS);
         if (rc == PV_OK && N >= 256 && N <= 2048) {
             std::vector<uint32_t> gath;
-            build_gather_table(N, V, alo.data(), ahi.data(), nomS.data(), gath);
+            build_gather_table(N, V, alo.data(), ahi.data(), gath);
             rc = upload(&h->d_gather, gath);
         }
     }

@@ -129,6 +129,35 @@ PV_DEV void cp_async8(float *dst, const float *src, int src_bytes)
 PV_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #endif
 
+#if defined(PV_HOST_EMUL)
+PV_DEV void cp_async16(float *dst, const float *src, int src_bytes)
+{
+    for (int j = 0; j < 4; j++) dst[j] = src_bytes >= 4 * (j + 1) ? src[j] : 0.f;
+}
+#else
+// 16-byte copy through L2 only (.cg): the input stream is consumed once per SM and must not evict the
+// window / twiddle tables from the ~24 KB of L1 that remain next to 204 KB of shared memory
+PV_DEV void cp_async16(float *dst, const float *src, int src_bytes)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+#endif
+
+// Cooperative refill with 16-byte pieces: samples [lo, N) (frame coordinates, multiples of 4) of the frame at
+// io.base, spread over T threads.  Issue after a barrier that follows the last read of the replaced samples;
+// complete with cp_async_wait_all() + a barrier before the first read of the new ones.
+template <int N, int T>
+PV_DEV void ring_prefetch_coop16(int tid, const FrameIO &io, float *ring, int lo)
+{
+    for (int i = lo + 4 * tid; i < N; i += 4 * T) {
+        const long long g = io.base + i;
+        const long long left = (io.n_in - g) * 4;
+        const int bytes = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
+        cp_async16(ring + ((int)(g & (N - 1))), io.in + (bytes > 0 ? g : 0), bytes);
+    }
+}
+
 // Copies samples [i, i+2) (frame coordinates) of the frame starting at io.base into the ring.
 template <int N>
 PV_DEV void ring_fetch(const FrameIO &io, float *ring, int i)
@@ -478,10 +507,10 @@ PV_DEV void inverse_23_ola(int tid, const Tables &tb, float2 *bufA, float2 *bufB
 // `hook` runs once per frame at a point where (a) every thread has finished the overlap-add of the
 // PREVIOUS frame and (b) the next write to the accumulator is at least one barrier away: the caller
 // uses it to emit the previous frame's output hop without dedicated barriers.
-template <int LOG2N, bool TWREG, class Sync, class Hook>
+template <int LOG2N, bool TWREG, class Sync, class Hook, class PreLast>
 PV_DEV void frame_compat(int tid, const FrameIO &io, const Tables &tb, const ThreadTw &tt, bool nan_compat,
                          const float *ring, float2 *bufA, float2 *bufB, float *acc, int pos0, int Hs, Sync sync,
-                         Hook hook)
+                         Hook hook, PreLast pre_last_sync)
 {
     using S = Shape<LOG2N>;
     if (io.analysed) {
@@ -504,7 +533,7 @@ PV_DEV void frame_compat(int tid, const FrameIO &io, const Tables &tb, const Thr
         sync();
     }
     // 1/(2N): the split step above works with 2*X (see split())
-    inverse_23_ola<LOG2N>(tid, tb, bufA, bufB, acc, pos0, Hs, !io.analysed, 0.5f / (float)S::N, sync, []() {});
+    inverse_23_ola<LOG2N>(tid, tb, bufA, bufB, acc, pos0, Hs, !io.analysed, 0.5f / (float)S::N, sync, pre_last_sync);
 }
 
 }  // namespace pvfused

@@ -49,8 +49,10 @@ struct CTables {
     const int32_t *a_lo;    // [V][NB]
     const int32_t *a_hi;    // [V][NB]
     const unsigned long long *nomS;   // [V][NB]
-    const uint4 *gather;    // [V][T][9] per-thread packed {a_lo, a_hi, nomS lo, nomS hi} in slot order
+    const uint32_t *gather; // [V][T][9] per-thread packed a_lo | a_hi << 16 in slot order (4.6 KB per voice at N = 2048:
+                            // small on purpose -- only ~24 KB of L1 remain next to the shared-memory carve-out)
     unsigned long long Rq[8];
+    unsigned long long beta_q[8];   // pitch ratio, Q32.32: nomS[s] = (beta_q * a_hi * Hs) << (32 - lgN) is recomputed
     float scale;            // gain / N
     int V;
     int Ha;
@@ -355,7 +357,8 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
     sync();
     // ---- synthesis, one voice at a time ----
     for (int v = 0; v < tb.V; v++) {
-        const uint4 *gt = tb.gather + ((size_t)v * C::T + u) * 9;
+        const uint32_t *gt = tb.gather + ((size_t)v * C::T + u) * 9;
+        const unsigned long long bq = tb.beta_q[v];
         unsigned long long *ps = psi + (size_t)v * NB;
         const unsigned long long Rq = tb.Rq[v];
         float2 Y[9];
@@ -364,15 +367,16 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
             Y[sl] = make_float2(0.f, 0.f);
             if (sl == 8 && u != 0) break;
             const int s = slot_bin<B3>(u, sl);
-            const uint4 ge = PV_LDG(gt + sl);            // {a_lo, a_hi, nomS}
-            const int lo = (int)ge.x, hi = (int)ge.y;
+            const uint32_t ge = PV_LDG(gt + sl);         // a_lo | a_hi << 16
+            const int lo = (int)(ge & 0xffffu), hi = (int)(ge >> 16);
             if (lo > hi) continue;                       // no analysis bin maps here
             float m = 0.f;
             for (int a = lo; a <= hi; a++) m += magS[a];
             const int32_t d = dS[hi];
             unsigned long long p;
             if (first) p = (unsigned long long)(uint32_t)d << 32;
-            else p = ps[s] + (((unsigned long long)ge.w << 32) | ge.z) + (unsigned long long)((long long)d * (long long)Rq);
+            else p = ps[s] + ((bq * (unsigned long long)(uint32_t)(hi * Hs)) << (32 - LOG2N)) +
+                     (unsigned long long)((long long)d * (long long)Rq);
             ps[s] = p;
             const float2 cs = cis_turns64(p);
             Y[sl] = make_float2(m * cs.x, m * cs.y);

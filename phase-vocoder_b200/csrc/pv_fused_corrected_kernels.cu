@@ -103,7 +103,8 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
     }
     if (use_ring) {
         FrameIO io0{in, a.n_in, seg.k_begin * (long long)d.Ha, true, true};
-        ring_prefetch_coop<N, T>(tid, io0, ring, 0);
+        if (use_ring == 2) ring_prefetch_coop16<N, T>(tid, io0, ring, 0);
+        else ring_prefetch_coop<N, T>(tid, io0, ring, 0);
         cp_async_wait_all();
     }
     sync();
@@ -135,7 +136,8 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
         auto hook = [&]() {
             if (use_ring && k + 1 < seg.k_end) {
                 FrameIO nx{in, a.n_in, (k + 1) * (long long)d.Ha, true, true};
-                ring_prefetch_coop<N, T>(tid, nx, ring, N - d.Ha);
+                if (use_ring == 2) ring_prefetch_coop16<N, T>(tid, nx, ring, N - d.Ha);
+                else ring_prefetch_coop<N, T>(tid, nx, ring, N - d.Ha);
             }
             if (k > seg.k_begin) emit(k - 1, (pos0 - Hs) & (N - 1), PV_ZERO_ON_EMIT);
         };
@@ -238,7 +240,10 @@ cudaError_t claunch(const PvDev &d, const CTables &tb, const PvProcessArgs &a, c
     const bool in_ok = (d.Ha % 2 == 0) && (a.in_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 7) == 0);
     const bool out_ok = (d.Hs % 4 == 0) && (a.out_stream_stride % 4 == 0) && (a.out_voice_stride % 4 == 0) &&
                         ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
-    const bool ring = in_ok && d.Ha <= d.N;
+    // 2: 16-byte cp.async.cg pieces (L1 bypass) when rows and hops are 16-byte aligned, 1: 8-byte pieces
+    const bool al16 = in_ok && (d.Ha % 4 == 0) && (a.in_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0);
+    static const char *variant = getenv("PV_VARIANT");
+    const int ring = (in_ok && d.Ha <= d.N) ? ((al16 && !(variant && variant[0] == '1')) ? 2 : 1) : 0;
     const size_t gb = L::group_bytes(tb.V);
     const size_t smem = gb * L::G;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -292,7 +297,8 @@ static CTables make_ctables(const PvDev &d, const PvFusedTables &t)
     tb.scale = d.gain / (float)d.N;
     tb.V = d.V;
     tb.Ha = d.Ha;
-    tb.gather = reinterpret_cast<const uint4 *>(d.gather);
+    tb.gather = d.gather;
+    for (int v = 0; v < d.V; v++) tb.beta_q[v] = d.beta_q[v];
     return tb;
 }
 

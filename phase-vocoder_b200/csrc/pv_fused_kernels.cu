@@ -46,7 +46,9 @@ struct GroupSync {
     }
 };
 
-template <int LOG2N, int MINB, bool RING>
+// RING: 0 = inputs straight from global memory, 1 = private 8-byte cp.async ring (each thread copies exactly
+// the samples it consumes, no barrier), 2 = cooperative 16-byte cp.async.cg ring (L1 bypass)
+template <int LOG2N, int MINB, int RING>
 __global__ void __launch_bounds__(Launch<LOG2N>::THREADS, MINB)
 compat_fused_kernel(PvDev d, Tables tb, PvProcessArgs a, int vec_in_ok, int vec_out_ok)
 {
@@ -100,7 +102,12 @@ compat_fused_kernel(PvDev d, Tables tb, PvProcessArgs a, int vec_in_ok, int vec_
     const long long k_an_end = seg.k_end < a.n_analysed ? seg.k_end : a.n_analysed;   // frames >= this are zero spectra
     if (RING && seg.k_begin < k_an_end) {
         FrameIO io0{in, a.n_in, seg.k_begin * (long long)d.Ha, true, true};
-        ring_prefetch<LOG2N>(tid, io0, ring, 0);
+        if (RING == 1) ring_prefetch<LOG2N>(tid, io0, ring, 0);
+        else {
+            ring_prefetch_coop16<N, T>(tid, io0, ring, 0);
+            cp_async_wait_all();
+            sync();
+        }
     }
     // per-thread twiddle bases live in registers for the whole segment
     constexpr bool TWREG = (S::S1 == S::T) && (S::R1 == 16);
@@ -113,12 +120,14 @@ compat_fused_kernel(PvDev d, Tables tb, PvProcessArgs a, int vec_in_ok, int vec_
         auto hook = [&]() {
             if (RING && k + 1 < k_an_end) {
                 FrameIO nx{in, a.n_in, (k + 1) * (long long)d.Ha, true, true};
-                ring_prefetch<LOG2N>(tid, nx, ring, N - d.Ha);
+                if (RING == 1) ring_prefetch<LOG2N>(tid, nx, ring, N - d.Ha);
+                else ring_prefetch_coop16<N, T>(tid, nx, ring, N - d.Ha);
             }
             if (k > seg.k_begin) emit(k - 1, (pos0 - Hs) & (N - 1), PV_ZERO_ON_EMIT);
         };
-        if (RING) cp_async_wait_all();
-        frame_compat<LOG2N, TWREG>(tid, io, tb, tt, nan_compat, ring, bufA, bufB, acc, pos0, Hs, sync, hook);
+        if (RING == 1) cp_async_wait_all();
+        frame_compat<LOG2N, TWREG>(tid, io, tb, tt, nan_compat, ring, bufA, bufB, acc, pos0, Hs, sync, hook,
+                                   [&]() { if (RING == 2) cp_async_wait_all(); });
         pos0 = (pos0 + Hs) & (N - 1);
     }
     sync();
@@ -133,13 +142,13 @@ compat_fused_kernel(PvDev d, Tables tb, PvProcessArgs a, int vec_in_ok, int vec_
 template <int LOG2N>
 bool ring_ok(const PvDev &d, bool vec_in_ok) { return vec_in_ok && d.Ha <= d.N && (d.Ha % (2 * Shape<LOG2N>::S1)) == 0; }
 
-template <int LOG2N, int MINB, bool RING>
+template <int LOG2N, int MINB, int RING>
 cudaError_t launch2(const PvDev &d, const Tables &tb, const PvProcessArgs &a, int vec_in_ok, int vec_out_ok,
                     cudaStream_t st)
 {
     using L = Launch<LOG2N>;
     auto kern = compat_fused_kernel<LOG2N, MINB, RING>;
-    const size_t smem = L::smem(RING);
+    const size_t smem = L::smem(RING != 0);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -154,9 +163,13 @@ cudaError_t launch(const PvDev &d, const Tables &tb, const PvProcessArgs &a, int
                    cudaStream_t st)
 {
     static const char *variant = getenv("PV_VARIANT");      // experiment switch
-    if (variant && variant[0] == '5') return launch2<LOG2N, 5, false>(d, tb, a, vec_in_ok, vec_out_ok, st);
-    if (ring_ok<LOG2N>(d, vec_in_ok != 0)) return launch2<LOG2N, MINB, true>(d, tb, a, vec_in_ok, vec_out_ok, st);
-    return launch2<LOG2N, MINB, false>(d, tb, a, vec_in_ok, vec_out_ok, st);
+    if (variant && variant[0] == '5') return launch2<LOG2N, 5, 0>(d, tb, a, vec_in_ok, vec_out_ok, st);
+    // 16-byte cooperative ring needs 16-byte aligned rows and hops
+    const bool al16 = vec_in_ok && d.Ha <= d.N && (d.Ha % 4 == 0) && (a.in_stride % 4 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0);
+    if (al16 && !(variant && variant[0] == '1')) return launch2<LOG2N, MINB, 2>(d, tb, a, vec_in_ok, vec_out_ok, st);
+    if (ring_ok<LOG2N>(d, vec_in_ok != 0)) return launch2<LOG2N, MINB, 1>(d, tb, a, vec_in_ok, vec_out_ok, st);
+    return launch2<LOG2N, MINB, 0>(d, tb, a, vec_in_ok, vec_out_ok, st);
 }
 
 }  // namespace
@@ -167,7 +180,7 @@ template <int LOG2N, int MINB>
 static int capacity(int sm_count)
 {
     using L = Launch<LOG2N>;
-    auto kern = compat_fused_kernel<LOG2N, MINB, true>;
+    auto kern = compat_fused_kernel<LOG2N, MINB, 2>;
     const size_t smem = L::smem(true);
     int nb = 0;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||

@@ -52,24 +52,19 @@ inline void build_tables(int log2n, HostTables &t)
         for (int n3 = 0; n3 < R2; n3++) t.itw2[(size_t)(m2 - 1) * R2 + n3] = pv_cis((double)(m2 * n3) / B3);
 }
 
-// Per-thread packed gather table of the corrected kernel: entry [v][u][slot] = {a_lo, a_hi, nomS lo, nomS hi}
-// for the synthesis bin owned by slot `slot` of thread `u` (pvfused::slot_bin).  Returned as 4 x uint32.
-inline void build_gather_table(int N, int V, const int32_t *a_lo, const int32_t *a_hi, const uint64_t *nomS,
-                               std::vector<uint32_t> &out)
+// Per-thread packed gather table of the corrected kernel: entry [v][u][slot] = a_lo | a_hi << 16 for the
+// synthesis bin owned by slot `slot` of thread `u` (pvfused::slot_bin); empty range = 1 | 0 << 16.
+inline void build_gather_table(int N, int V, const int32_t *a_lo, const int32_t *a_hi, std::vector<uint32_t> &out)
 {
     const int T = N / 16, B3 = N / 8, NB = N / 2 + 1;
-    out.assign((size_t)V * T * 9 * 4, 0u);
+    out.assign((size_t)V * T * 9, 1u);
     for (int v = 0; v < V; v++)
         for (int u = 0; u < T; u++)
             for (int sl = 0; sl < 9; sl++) {
-                uint32_t *e = &out[(((size_t)v * T + u) * 9 + sl) * 4];
-                if (sl == 8 && u != 0) { e[0] = 1; e[1] = 0; continue; }       // empty range
+                if (sl == 8 && u != 0) continue;                                   // empty range
                 const int j = sl & 3;
                 const int bin = (sl == 8) ? 4 * B3 : (sl < 4 ? u + B3 * j : (u == 0 ? B3 / 2 : B3 - u) + B3 * j);
                 const size_t i = (size_t)v * NB + bin;
-                e[0] = (uint32_t)a_lo[i];
-                e[1] = (uint32_t)a_hi[i];
-                e[2] = (uint32_t)(nomS[i] & 0xffffffffull);
-                e[3] = (uint32_t)(nomS[i] >> 32);
+                out[((size_t)v * T + u) * 9 + sl] = (uint32_t)a_lo[i] | ((uint32_t)a_hi[i] << 16);
             }
 }

@@ -22,7 +22,8 @@ struct PvDev {
     const int32_t *a_lo;  // V*nb
     const int32_t *a_hi;  // V*nb
     const uint64_t *nomS; // V*nb
-    const uint32_t *gather; // V*T*9*4: per-thread packed {a_lo, a_hi, nomS} (pv_fused_tables.h)
+    const uint32_t *gather; // V*T*9: per-thread packed a_lo | a_hi << 16 (pv_fused_tables.h)
+    uint64_t beta_q[PV_MAX_VOICES];
     uint64_t Rq[PV_MAX_VOICES];
 };
 

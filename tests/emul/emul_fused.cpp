@@ -53,7 +53,7 @@ static int run(const float *x, long n_in, int Ha, int Hs, const float *win, long
             constexpr bool TWREG = (S::S1 == S::T) && (S::R1 == 16);
             const ThreadTw tt = load_thread_tw<LOG2N>(tid, tb);
             frame_compat<LOG2N, TWREG>(tid, io, tb, tt, nan_compat != 0, ring, bufA.data(), bufB.data(), acc.data(),
-                                       pos0, Hs, sync, hook);
+                                       pos0, Hs, sync, hook, []() {});
             pos0 = (pos0 + Hs) & (N - 1);
         }
         sync();
@@ -84,7 +84,8 @@ extern "C" int emul_compat(int log2n, const float *x, long n_in, int Ha, int Hs,
 template <int LOG2N>
 static int run_corrected(const float *x, long n_in, int Ha, int Hs, const float *win, int V, const uint32_t *nomA,
                          const int32_t *a_lo, const int32_t *a_hi, const unsigned long long *nomS,
-                         const unsigned long long *Rq, float gain, long n_frames, float *out, long out_stride)
+                         const unsigned long long *Rq, const unsigned long long *beta_q, float gain, long n_frames,
+                         float *out, long out_stride)
 {
     using C = CShape<LOG2N>;
     constexpr int N = C::N, T = C::T, NB = C::NB;
@@ -100,8 +101,9 @@ static int run_corrected(const float *x, long n_in, int Ha, int Hs, const float 
     tb.V = V;
     tb.Ha = Ha;
     std::vector<uint32_t> gath;
-    build_gather_table(N, V, a_lo, a_hi, (const uint64_t *)nomS, gath);
-    tb.gather = reinterpret_cast<const uint4 *>(gath.data());
+    build_gather_table(N, V, a_lo, a_hi, gath);
+    tb.gather = gath.data();
+    for (int v = 0; v < V; v++) tb.beta_q[v] = beta_q[v];
     std::vector<float2> bufA(C::BUF_A), bufB(C::BUF_B);
     std::vector<float> acc((size_t)V * N, 0.f), ringbuf(N, 0.f), magS(NB);
     std::vector<int32_t> dS(NB);
@@ -154,10 +156,10 @@ static int run_corrected(const float *x, long n_in, int Ha, int Hs, const float 
 
 extern "C" int emul_corrected(int log2n, const float *x, long n_in, int Ha, int Hs, const float *win, int V,
                               const uint32_t *nomA, const int32_t *a_lo, const int32_t *a_hi,
-                              const unsigned long long *nomS, const unsigned long long *Rq, float gain, long n_frames,
-                              float *out, long out_stride)
+                              const unsigned long long *nomS, const unsigned long long *Rq,
+                              const unsigned long long *beta_q, float gain, long n_frames, float *out, long out_stride)
 {
-#define RC(L) case L: return run_corrected<L>(x, n_in, Ha, Hs, win, V, nomA, a_lo, a_hi, nomS, Rq, gain, n_frames, out, out_stride)
+#define RC(L) case L: return run_corrected<L>(x, n_in, Ha, Hs, win, V, nomA, a_lo, a_hi, nomS, Rq, beta_q, gain, n_frames, out, out_stride)
     switch (log2n) {
         RC(8); RC(9); RC(10); RC(11);
         default: return -1;

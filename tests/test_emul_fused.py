@@ -51,8 +51,8 @@ def test_fused_body_matches_oracle(emul, N, Ha, Hs, nf):
 ])
 def test_corrected_body_matches_oracle(emul, N, Ha, Hs, betas, nf):
     emul.emul_corrected.argtypes = [C.c_int, C.POINTER(C.c_float), C.c_long, C.c_int, C.c_int, C.POINTER(C.c_float),
-                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
-                                    C.c_long, C.POINTER(C.c_float), C.c_long]
+                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_float, C.c_long, C.POINTER(C.c_float), C.c_long]
     n_in = N + (nf - 1) * Ha - 3
     x = multitone(n_in, seed=N + Ha)
     win = po.window(po.WIN_HANN_PERIODIC, N)
@@ -62,12 +62,13 @@ def test_corrected_body_matches_oracle(emul, N, Ha, Hs, betas, nf):
     a_hi = np.concatenate([t["a_hi"] for t in tabs]).astype(np.int32)
     nomS = np.concatenate([t["nomS"] for t in tabs]).astype(np.uint64)
     Rq = np.array([t["Rq"] for t in tabs], np.uint64)
+    bq = np.array([t["beta_q"] for t in tabs], np.uint64)
     nomA = tabs[0]["nomA"]
     out = np.zeros((V, nf * Hs), np.float32)
     fp = C.POINTER(C.c_float)
     rc = emul.emul_corrected(int(np.log2(N)), x.ctypes.data_as(fp), n_in, Ha, Hs, win.ctypes.data_as(fp), V,
                              nomA.ctypes.data, a_lo.ctypes.data, a_hi.ctypes.data, nomS.ctypes.data, Rq.ctypes.data,
-                             po.corrected_gain(win, Hs), nf, out.ctypes.data_as(fp), nf * Hs)
+                             bq.ctypes.data, po.corrected_gain(win, Hs), nf, out.ctypes.data_as(fp), nf * Hs)
     assert rc == 0
     want, _ = po.process_corrected(x, N, Ha, Hs, win, betas, nf)
     for v in range(V):
