@@ -38,16 +38,18 @@ struct Shape {
     static constexpr int S1 = N / R1;             // = R2*8
     static constexpr int PAD1 = 16 / R1;          // exchange-1 row padding (float2 units)
     static constexpr int LD1 = S1 + PAD1;
-    static constexpr int LD2 = 9;                 // exchange-2: t3*9 + n3
+    // exchange 2 is done IN PLACE in the exchange-1 buffer: a pass-2 butterfly (k1, n3) reads the 16
+    // addresses k1*LD1 + n2*8 + n3 and writes its outputs k2 back to the same addresses (k2 in the place
+    // of n2); no other thread touches them, so no barrier and no second buffer are needed
     static constexpr int EX1 = R1 * LD1;          // float2 elements
-    static constexpr int EX2 = B3 * LD2;
     // inverse: M' = 4*B3, B3 = R1*R2
     static constexpr int ILD1 = B3 + (R2 < 16 ? R2 : 0);   // exchange-3 rows (m1): m1*ILD1 + t1
     static constexpr int IEX1 = 4 * ILD1;
     static constexpr int ILD2 = R2 + 1;           // exchange-4: (m1 + 4*m2)*(R2+1) + n3
     static constexpr int IEX2 = 4 * R1 * ILD2;
-    static constexpr int BUF_A = (EX1 > IEX1 ? EX1 : IEX1);     // exchanges 1 and 3
-    static constexpr int BUF_B = (EX2 > IEX2 ? EX2 : IEX2);     // exchanges 2 and 4
+    // compat kernel: A = exchanges 1, 2 (in place) and 4, B = exchange 3
+    static constexpr int BUF_A = (EX1 > IEX2 ? EX1 : IEX2);
+    static constexpr int BUF_B = IEX1;
     static_assert(R1 * R2 == B3 && R2 >= 4, "shape");
 };
 
@@ -233,24 +235,25 @@ PV_DEV void forward_12(int tid, const FrameIO &io, const Tables &tb, const Threa
 #pragma unroll
         for (int n2 = 0; n2 < R2; n2++) v[n2] = bufA[k1 * S::LD1 + n2 * 8 + n3];
         dft<R2, -1>(v);
-        bufB[k1 * S::LD2 + n3] = v[0];
+        bufA[k1 * S::LD1 + n3] = v[0];
 #pragma unroll
         for (int k2 = 1; k2 < R2; k2++)
-            bufB[(k1 + R1 * k2) * S::LD2 + n3] = cmul(v[k2], PV_LDG(tb.tw2 + (k2 - 1) * 8 + n3));
+            bufA[k1 * S::LD1 + k2 * 8 + n3] = cmul(v[k2], PV_LDG(tb.tw2 + (k2 - 1) * 8 + n3));
     }
     sync();
 }
 
 // ---- forward pass 3 for the butterfly pair of thread u: P[j] = C[tP + B3*j], Q[j] = C[tQ + B3*j] ----
 template <int LOG2N>
-PV_DEV void forward_3(int u, const float2 *bufB, float2 (&P)[8], float2 (&Q)[8])
+PV_DEV void forward_3(int u, const float2 *bufA, float2 (&P)[8], float2 (&Q)[8])
 {
     using S = Shape<LOG2N>;
-    const int tP = u, tQ = (u == 0) ? S::B3 / 2 : S::B3 - u;
+    const int tP = u, tQ = (u == 0) ? S::B3 / 2 : S::B3 - u;        // t3 = k1 + R1*k2
+    const int oP = (tP % S::R1) * S::LD1 + (tP / S::R1) * 8, oQ = (tQ % S::R1) * S::LD1 + (tQ / S::R1) * 8;
 #pragma unroll
     for (int n3 = 0; n3 < 8; n3++) {
-        P[n3] = bufB[tP * S::LD2 + n3];
-        Q[n3] = bufB[tQ * S::LD2 + n3];
+        P[n3] = bufA[oP + n3];
+        Q[n3] = bufA[oQ + n3];
     }
     dft<8, -1>(P);
     dft<8, -1>(Q);
@@ -516,16 +519,19 @@ PV_DEV void frame_compat(int tid, const FrameIO &io, const Tables &tb, const Thr
     if (io.analysed) {
         forward_12<LOG2N, TWREG>(tid, io, tb, tt, ring, bufA, bufB, sync, hook);
         float2 P[8], Q[8], Zp[4], Zq[4];
-        forward_3<LOG2N>(tid, bufB, P, Q);
+        forward_3<LOG2N>(tid, bufA, P, Q);
         middle_compat<LOG2N, TWREG>(tid, tb, tt, nan_compat, P, Q, Zp, Zq);
+        // Exchange 3 goes to B (other threads may still be reading A in pass 3); exchange 4 goes back to A.
+        // The caller puts one barrier at the end of the frame so that the next frame's pass 1 cannot
+        // overwrite A while the last inverse pass still reads it.
         if (TWREG && tid != 0) {
             // exp(+2 pi i m1 u/(N/2)) = conj(W_N^{2 m1 u}); for t1 = B3-u: j^m1 * W_N^{2 m1 u}
             const float2 w6 = cmul(tt.w2, tt.w4);
-            inverse_1_tw<LOG2N>(tid, cconj(tt.w2), cconj(tt.w4), cconj(w6), Zp, bufA);
-            inverse_1_tw<LOG2N>(S::B3 - tid, mul_pj(tt.w2), make_float2(-tt.w4.x, -tt.w4.y), mul_mj(w6), Zq, bufA);
+            inverse_1_tw<LOG2N>(tid, cconj(tt.w2), cconj(tt.w4), cconj(w6), Zp, bufB);
+            inverse_1_tw<LOG2N>(S::B3 - tid, mul_pj(tt.w2), make_float2(-tt.w4.x, -tt.w4.y), mul_mj(w6), Zq, bufB);
         } else {
-            inverse_1<LOG2N>(tid, tb, Zp, bufA);
-            inverse_1<LOG2N>(tid == 0 ? S::B3 / 2 : S::B3 - tid, tb, Zq, bufA);
+            inverse_1<LOG2N>(tid, tb, Zp, bufB);
+            inverse_1<LOG2N>(tid == 0 ? S::B3 / 2 : S::B3 - tid, tb, Zq, bufB);
         }
     } else {
         sync();
@@ -533,7 +539,8 @@ PV_DEV void frame_compat(int tid, const FrameIO &io, const Tables &tb, const Thr
         sync();
     }
     // 1/(2N): the split step above works with 2*X (see split())
-    inverse_23_ola<LOG2N>(tid, tb, bufA, bufB, acc, pos0, Hs, !io.analysed, 0.5f / (float)S::N, sync, pre_last_sync);
+    inverse_23_ola<LOG2N>(tid, tb, bufB, bufA, acc, pos0, Hs, !io.analysed, 0.5f / (float)S::N, sync, pre_last_sync);
+    sync();
 }
 
 }  // namespace pvfused

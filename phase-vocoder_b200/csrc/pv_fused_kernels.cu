@@ -167,7 +167,9 @@ cudaError_t launch(const PvDev &d, const Tables &tb, const PvProcessArgs &a, int
     // 16-byte cooperative ring needs 16-byte aligned rows and hops
     const bool al16 = vec_in_ok && d.Ha <= d.N && (d.Ha % 4 == 0) && (a.in_stride % 4 == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0);
-    if (al16 && !(variant && variant[0] == '1')) return launch2<LOG2N, MINB, 2>(d, tb, a, vec_in_ok, vec_out_ok, st);
+    // 5 CTAs/SM: with exchange 2 in place a group needs 40.7 KB of shared memory at N = 2048 and 96 registers
+    if (al16 && variant && variant[0] == '4') return launch2<LOG2N, 4, 2>(d, tb, a, vec_in_ok, vec_out_ok, st);
+    if (al16 && !(variant && variant[0] == '1')) return launch2<LOG2N, 5, 2>(d, tb, a, vec_in_ok, vec_out_ok, st);
     if (ring_ok<LOG2N>(d, vec_in_ok != 0)) return launch2<LOG2N, MINB, 1>(d, tb, a, vec_in_ok, vec_out_ok, st);
     return launch2<LOG2N, MINB, 0>(d, tb, a, vec_in_ok, vec_out_ok, st);
 }
@@ -180,7 +182,7 @@ template <int LOG2N, int MINB>
 static int capacity(int sm_count)
 {
     using L = Launch<LOG2N>;
-    auto kern = compat_fused_kernel<LOG2N, MINB, 2>;
+    auto kern = compat_fused_kernel<LOG2N, 5, 2>;
     const size_t smem = L::smem(true);
     int nb = 0;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
