@@ -99,6 +99,18 @@ PV_DEV uint32_t phase_turns32(float re, float im)
 #endif
 }
 
+// |X|: one MUFU (sqrt.approx.ftz, 1 ulp) instead of the IEEE sqrtf sequence
+PV_DEV float fast_sqrt(float v)
+{
+#ifdef PV_HOST_EMUL
+    return sqrtf(v);
+#else
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+#endif
+}
+
 PV_DEV float2 cis_turns64(unsigned long long psi)
 {
     // top 32 bits as signed turns in [-0.5, 0.5)
@@ -347,7 +359,7 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
         const int bin = slot_bin<B3>(u, sl);
         const float2 x = X[sl];
         const uint32_t Pc = phase_turns32(x.x, x.y);
-        magS[bin] = sqrtf(x.x * x.x + x.y * x.y);
+        magS[bin] = fast_sqrt(x.x * x.x + x.y * x.y);
         // nomA[bin] = (bin*Ha*2^32/N) mod 2^32 (see pv_capi.cu): two integer ops instead of a table load
         const uint32_t nomA = ((uint32_t)bin * (uint32_t)tb.Ha) << (32 - LOG2N);
         dS[bin] = first ? (int32_t)Pc : (int32_t)(Pc - st.Pprev[sl] - nomA);
@@ -369,17 +381,20 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
             const int s = slot_bin<B3>(u, sl);
             const uint32_t ge = PV_LDG(gt + sl);         // a_lo | a_hi << 16
             const int lo = (int)(ge & 0xffffu), hi = (int)(ge >> 16);
-            if (lo > hi) continue;                       // no analysis bin maps here
-            float m = 0.f;
-            for (int a = lo; a <= hi; a++) m += magS[a];
-            const int32_t d = dS[hi];
+            // straight-line for the common case (one source bin); an empty range (lo > hi: no analysis bin
+            // maps here) keeps the slot at zero and leaves the accumulator untouched
+            const bool has = lo <= hi;
+            const int l0 = has ? lo : 0, h0 = has ? hi : 0;
+            float m = magS[l0];
+            for (int a = l0 + 1; a <= h0; a++) m += magS[a];        // ascending, as the specification sums
+            const int32_t d = dS[h0];
             unsigned long long p;
             if (first) p = (unsigned long long)(uint32_t)d << 32;
-            else p = ps[s] + ((bq * (unsigned long long)(uint32_t)(hi * Hs)) << (32 - LOG2N)) +
+            else p = ps[s] + ((bq * (unsigned long long)(uint32_t)(h0 * Hs)) << (32 - LOG2N)) +
                      (unsigned long long)((long long)d * (long long)Rq);
-            ps[s] = p;
+            if (has) ps[s] = p;
             const float2 cs = cis_turns64(p);
-            Y[sl] = make_float2(m * cs.x, m * cs.y);
+            Y[sl] = has ? make_float2(m * cs.x, m * cs.y) : make_float2(0.f, 0.f);
         }
         // Hermitian pack (same register pattern as the compat kernel); exp(+2 pi i k/N) = conj(W_N^k)
         float2 Zp[4], Zq[4];
