@@ -67,9 +67,14 @@ struct Tables {
 // pass-1 butterfly, S1 == T, so that t1 == u == tid for the whole segment).  All other twiddles of
 // the thread are products of these with compile-time constants, which removes ~37 L1 loads and
 // their address arithmetic per thread and frame.
+// Thread 0 owns the two self-paired columns t3 = 0 and t3 = B3/2.  Its "p side" behaves like a regular
+// thread with u = 0 and its "q side" like a regular thread with u = B3/2 (B3 - B3/2 = B3/2), so giving every
+// thread separate p-side and q-side bases (equal for tid != 0) lets ONE code path serve all threads: warp 0
+// no longer executes a divergent copy of the middle section on the critical path of every frame.
 struct ThreadTw {
-    float2 w1, w2, w4, w8;   // W_N^{u}, ^2u, ^4u, ^8u      (W_N = exp(-2 pi i / N))
-    float2 h;                // exp(-j*pi*u/N)              (the 2N-th root)
+    float2 w1, w2, w4, w8;   // W_N^{u}, ^2u, ^4u, ^8u  for u = tid  (pass-1 twiddles, p side)
+    float2 hp, hq;           // exp(-j*pi*u/N) for u = tid and for u_q = tid ? tid : B3/2
+    float2 q1, q2, q4;       // W_N^{u_q}, ^2u_q, ^4u_q
 };
 
 template <int LOG2N>
@@ -81,7 +86,12 @@ PV_DEV ThreadTw load_thread_tw(int u, const Tables &tb)
     t.w2 = PV_LDG(tb.tw1 + 1 * S::S1 + u);
     t.w4 = PV_LDG(tb.tw1 + 3 * S::S1 + u);
     t.w8 = (S::R1 > 8) ? PV_LDG(tb.tw1 + 7 * S::S1 + u) : make_float2(1.f, 0.f);
-    t.h = PV_LDG(tb.tw2n + u);
+    const int uq = u ? u : S::B3 / 2;
+    t.hp = PV_LDG(tb.tw2n + u);
+    t.hq = PV_LDG(tb.tw2n + uq);
+    t.q1 = PV_LDG(tb.tw2n + 2 * uq);
+    t.q2 = PV_LDG(tb.tw2n + 4 * uq);
+    t.q4 = cmul(t.q2, t.q2);
     return t;
 }
 
@@ -309,28 +319,39 @@ PV_DEV void middle_compat(int u, const Tables &tb, const ThreadTw &tt, bool nan_
     using S = Shape<LOG2N>;
     constexpr int N = S::N, B3 = S::B3;
     float2 Yp[5], Yq[4];
-    if (u != 0) {
-        if constexpr (TWREG) {
-            // tw2n[u + B3 j] = h * W16^j ; tw2n[B3 - u + B3 j] = conj(h) * W16^(j+1)
-            const float2 hc = cconj(tt.h), w1c = cconj(tt.w1);
-            Yp[0] = compat_map(split(P[0], Q[7], tt.h), nan_compat);
-            Yp[1] = compat_map(split(P[1], Q[6], rot16<1>(tt.h)), nan_compat);
-            Yp[2] = compat_map(split(P[2], Q[5], rot16<2>(tt.h)), nan_compat);
-            Yp[3] = compat_map(split(P[3], Q[4], rot16<3>(tt.h)), nan_compat);
-            Yq[0] = compat_map(split(Q[0], P[7], rot16<1>(hc)), nan_compat);
-            Yq[1] = compat_map(split(Q[1], P[6], rot16<2>(hc)), nan_compat);
-            Yq[2] = compat_map(split(Q[2], P[5], rot16<3>(hc)), nan_compat);
-            Yq[3] = compat_map(split(Q[3], P[4], rot16<4>(hc)), nan_compat);
-            // exp(+2 pi i k/N) = conj(tw2n[2k]); tw2n[2(u + B3 j)] = w1 * W16^(2j); tw2n[2(B3-u+B3 j)] = conj(w1) * W16^(2j+2)
-            Zp[0] = herm_pack(Yp[0], Yq[3], cconj(tt.w1));
-            Zp[1] = herm_pack(Yp[1], Yq[2], cconj(rot16<2>(tt.w1)));
-            Zp[2] = herm_pack(Yp[2], Yq[1], cconj(rot16<4>(tt.w1)));
-            Zp[3] = herm_pack(Yp[3], Yq[0], cconj(rot16<6>(tt.w1)));
-            Zq[0] = herm_pack(Yq[0], Yp[3], cconj(rot16<2>(w1c)));
-            Zq[1] = herm_pack(Yq[1], Yp[2], cconj(rot16<4>(w1c)));
-            Zq[2] = herm_pack(Yq[2], Yp[1], cconj(rot16<6>(w1c)));
-            Zq[3] = herm_pack(Yq[3], Yp[0], cconj(rot16<8>(w1c)));
-        } else {
+    if constexpr (TWREG) {
+        // one path for all threads (see ThreadTw): selects instead of a divergent copy for thread 0
+        const bool u0 = (u == 0);
+        auto sel = [&](float2 a, float2 b) { return u0 ? a : b; };
+        // partners: regular thread (P[j], Q[7-j]) and (Q[j], P[7-j]); thread 0 (P[j], P[(8-j)&7]) and (Q[j], Q[7-j])
+        const float2 b1_7 = sel(P[0], Q[7]), b1_6 = sel(P[7], Q[6]), b1_5 = sel(P[6], Q[5]), b1_4 = sel(P[5], Q[4]);
+        const float2 b2_7 = sel(Q[7], P[7]), b2_6 = sel(Q[6], P[6]), b2_5 = sel(Q[5], P[5]), b2_4 = sel(Q[4], P[4]);
+        const float2 hc = cconj(tt.hq), q1c = cconj(tt.q1);
+        Yp[0] = compat_map(split(P[0], b1_7, tt.hp), nan_compat);
+        Yp[1] = compat_map(split(P[1], b1_6, rot16<1>(tt.hp)), nan_compat);
+        Yp[2] = compat_map(split(P[2], b1_5, rot16<2>(tt.hp)), nan_compat);
+        Yp[3] = compat_map(split(P[3], b1_4, rot16<3>(tt.hp)), nan_compat);
+        Yq[0] = compat_map(split(Q[0], b2_7, rot16<1>(hc)), nan_compat);
+        Yq[1] = compat_map(split(Q[1], b2_6, rot16<2>(hc)), nan_compat);
+        Yq[2] = compat_map(split(Q[2], b2_5, rot16<3>(hc)), nan_compat);
+        Yq[3] = compat_map(split(Q[3], b2_4, rot16<4>(hc)), nan_compat);
+        Yp[4] = make_float2(0.f, 0.f);
+        if (u0) {               // bin N/2 and the real-only DC / Nyquist of the C2R (cuFFT, kernel.cu:366)
+            Yp[4] = compat_map(split(P[4], P[4], make_float2(0.f, -1.f)), nan_compat);
+            Yp[0].y = 0.f;
+            Yp[4].y = 0.f;
+        }
+        // exp(+2 pi i k/N) = conj(W_N^k): W_N^(u + B3 j) = w1 * W16^(2j); W_N^(B3 - u_q + B3 j) = conj(q1) * W16^(2j+2)
+        Zp[0] = herm_pack(Yp[0], sel(Yp[4], Yq[3]), cconj(tt.w1));
+        Zp[1] = herm_pack(Yp[1], sel(Yp[3], Yq[2]), cconj(rot16<2>(tt.w1)));
+        Zp[2] = herm_pack(Yp[2], sel(Yp[2], Yq[1]), cconj(rot16<4>(tt.w1)));
+        Zp[3] = herm_pack(Yp[3], sel(Yp[1], Yq[0]), cconj(rot16<6>(tt.w1)));
+        Zq[0] = herm_pack(Yq[0], sel(Yq[3], Yp[3]), cconj(rot16<2>(q1c)));
+        Zq[1] = herm_pack(Yq[1], sel(Yq[2], Yp[2]), cconj(rot16<4>(q1c)));
+        Zq[2] = herm_pack(Yq[2], sel(Yq[1], Yp[1]), cconj(rot16<6>(q1c)));
+        Zq[3] = herm_pack(Yq[3], sel(Yq[0], Yp[0]), cconj(rot16<8>(q1c)));
+    } else if (u != 0) {
+        {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int kp = u + B3 * j, kq = (B3 - u) + B3 * j;
@@ -524,11 +545,12 @@ PV_DEV void frame_compat(int tid, const FrameIO &io, const Tables &tb, const Thr
         // Exchange 3 goes to B (other threads may still be reading A in pass 3); exchange 4 goes back to A.
         // The caller puts one barrier at the end of the frame so that the next frame's pass 1 cannot
         // overwrite A while the last inverse pass still reads it.
-        if (TWREG && tid != 0) {
-            // exp(+2 pi i m1 u/(N/2)) = conj(W_N^{2 m1 u}); for t1 = B3-u: j^m1 * W_N^{2 m1 u}
-            const float2 w6 = cmul(tt.w2, tt.w4);
+        if (TWREG) {
+            // exp(+2 pi i m1 u/(N/2)) = conj(W_N^{2 m1 u}); for t1 = B3-u_q: j^m1 * W_N^{2 m1 u_q}
+            const float2 w6 = cmul(tt.w2, tt.w4), q6 = cmul(tt.q2, tt.q4);
             inverse_1_tw<LOG2N>(tid, cconj(tt.w2), cconj(tt.w4), cconj(w6), Zp, bufB);
-            inverse_1_tw<LOG2N>(S::B3 - tid, mul_pj(tt.w2), make_float2(-tt.w4.x, -tt.w4.y), mul_mj(w6), Zq, bufB);
+            inverse_1_tw<LOG2N>(tid == 0 ? S::B3 / 2 : S::B3 - tid, mul_pj(tt.q2), make_float2(-tt.q4.x, -tt.q4.y),
+                                mul_mj(q6), Zq, bufB);
         } else {
             inverse_1<LOG2N>(tid, tb, Zp, bufB);
             inverse_1<LOG2N>(tid == 0 ? S::B3 / 2 : S::B3 - tid, tb, Zq, bufB);
