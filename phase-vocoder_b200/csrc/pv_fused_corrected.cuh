@@ -156,7 +156,9 @@ PV_DEV void tw_expand(const TwBase4 &b, float2 (&e)[8])
 
 struct CThreadTw {
     TwBase4 p1, p2, ip2;     // forward pass 1, forward pass 2, inverse pass 2
-    float2 wN, w2, w4;       // W_N^u, W_N^2u, W_N^4u  (split / pack / inverse pass 1)
+    float2 wN, w2, w4;       // W_N^u, W_N^2u, W_N^4u  (split / pack / inverse pass 1), p side: u = tid
+    float2 q1, q2, q4;       // same for the q side: u_q = tid ? tid : B3/2 (thread 0 owns columns 0 and B3/2, see
+                             // ThreadTw in pv_fused_core.cuh: one code path for all threads)
 };
 
 // exact table values for the bases (cis of integer fractions, rounded once)
@@ -196,6 +198,10 @@ PV_DEV CThreadTw load_cthread_tw(int tid, const CTables &tb)
     t.wN = PV_LDG(tb.tw2n + 2 * tid);
     t.w2 = PV_LDG(tb.tw2n + 4 * tid);
     t.w4 = cmul(t.w2, t.w2);
+    const int uq = tid ? tid : C::B3 / 2;
+    t.q1 = PV_LDG(tb.tw2n + 2 * uq);
+    t.q2 = PV_LDG(tb.tw2n + 4 * uq);
+    t.q4 = cmul(t.q2, t.q2);
     return t;
 }
 
@@ -317,31 +323,46 @@ PV_DEV void cforward(int tid, const FrameIO &io, const CTables &tb, const CThrea
     }
     dft<4, -1>(P);
     dft<4, -1>(Q);
-    if (u != 0) {
-#pragma unroll
+    {
+        // One path for all threads.  Regular thread: pairs (P[j], Q[3-j]) -> X[p slot j], X[q slot 3-j].
+        // Thread 0 (columns 0 and B3/2): (P0,P0) -> bins 0, N/2; (P1,P3); (P2,P2); (Q0,Q3); (Q1,Q2).
+        const bool u0 = (u == 0);
+        auto sel = [&](float2 a, float2 b) { return u0 ? a : b; };
         // W_N^{u + B3 j} = W_N^u * exp(-2 pi i j/8)
         wp[0] = tt.wN; wp[1] = twid16<2, -1>(tt.wN); wp[2] = twid16<4, -1>(tt.wN); wp[3] = twid16<6, -1>(tt.wN);
-#pragma unroll
-        for (int j = 0; j < 4; j++) split_both(P[j], Q[3 - j], wp[j], X[j], X[4 + (3 - j)]);
-        X[8] = make_float2(0.f, 0.f);
-    } else {
-        X[0] = make_float2(P[0].x + P[0].y, 0.f);
-        X[8] = make_float2(P[0].x - P[0].y, 0.f);
-        float2 dummy;
-        split_both(P[1], P[3], PV_LDG(tb.tw2n + 2 * B3), X[1], X[3]);
-        split_both(P[2], P[2], make_float2(0.f, -1.f), X[2], dummy);
-        split_both(Q[0], Q[3], PV_LDG(tb.tw2n + B3), X[4], X[7]);
-        split_both(Q[1], Q[2], PV_LDG(tb.tw2n + 3 * B3), X[5], X[6]);
-#pragma unroll
-        for (int j = 0; j < 4; j++) wp[j] = make_float2(1.f, 0.f);   // unused
+        float2 xk0, xm0, xk1, xm1, xk2, xm2, xk3, xm3;
+        split_both(P[0], sel(P[0], Q[3]), wp[0], xk0, xm0);
+        split_both(P[1], sel(P[3], Q[2]), wp[1], xk1, xm1);
+        split_both(P[2], sel(P[2], Q[1]), wp[2], xk2, xm2);
+        split_both(sel(Q[0], P[3]), sel(Q[3], Q[0]), sel(tt.q1, wp[3]), xk3, xm3);
+        float2 xke = make_float2(0.f, 0.f), xme = xke;
+        if (u0) split_both(Q[1], Q[2], twid16<2, -1>(tt.q1), xke, xme);       // W_N^{3 B3/2}
+        X[0] = xk0; X[1] = xk1; X[2] = xk2;
+        X[3] = sel(xm1, xk3);
+        X[4] = sel(xk3, xm3);
+        X[5] = sel(xke, xm2);
+        X[6] = sel(xme, xm1);
+        X[7] = sel(xm3, xm0);
+        X[8] = sel(xm0, make_float2(0.f, 0.f));
     }
     (void)M;
 }
 
+// Analysis-only ("phase-carry aggregate") mode of the SAME frame body.  The aggregate and the processing pass
+// must produce bit-identical phases P (the split / sharded result is bit-identical to the sequential one only
+// then), so they share one kernel instantiation and therefore one compiled copy of the forward transform: two
+// separately compiled copies may contract multiply-adds differently.
+struct AggCtx {
+    bool on;                 // analysis only: no synthesis, no barriers after the forward transform
+    long long *sum;          // [NB] per-bin running sum of D for this frame (shared memory, thread-private slots)
+    uint32_t *P_first;       // global [NB] or null: phase of the first analysed frame of the segment
+};
+
 template <int LOG2N, class Sync, class Hook, class PreLast>
 PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const CThreadTw &tt, const float *ring,
                             float2 *bufA, float2 *bufB, float *magS, int32_t *dS, unsigned long long *psi, float *acc,
-                            CState &st, int pos0, int Hs, Sync sync, Hook hook, PreLast pre_last_sync)
+                            CState &st, int pos0, int Hs, Sync sync, Hook hook, PreLast pre_last_sync,
+                            const AggCtx agg = AggCtx{false, nullptr, nullptr})
 {
     using C = CShape<LOG2N>;
     using S = Shape<LOG2N>;
@@ -353,6 +374,20 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
     cforward<LOG2N, TWREG>(tid, io, tb, tt, ring, bufA, bufB, sync, hook, X, wp);
     // ---- analysis: magnitude, phase (turns*2^32), unwrapped phase difference ----
     const bool first = st.have_prev == 0;
+    if (agg.on) {
+#pragma unroll
+        for (int sl = 0; sl < 9; sl++) {
+            if (sl == 8 && u != 0) break;
+            const int bin = slot_bin<B3>(u, sl);
+            const uint32_t Pc = phase_turns32(X[sl].x, X[sl].y);
+            const uint32_t nomA = ((uint32_t)bin * (uint32_t)tb.Ha) << (32 - LOG2N);
+            if (!first) agg.sum[bin] += (long long)(int32_t)(Pc - st.Pprev[sl] - nomA);
+            else if (agg.P_first) agg.P_first[bin] = Pc;
+            st.Pprev[sl] = Pc;
+        }
+        st.have_prev = 1;
+        return;          // the next frame's first barrier orders the reuse of the exchange buffers
+    }
 #pragma unroll
     for (int sl = 0; sl < 9; sl++) {
         if (sl == 8 && u != 0) break;
@@ -398,34 +433,29 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
         }
         // Hermitian pack (same register pattern as the compat kernel); exp(+2 pi i k/N) = conj(W_N^k)
         float2 Zp[4], Zq[4];
-        if (u != 0) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                // q-side bin (B3-u)+B3 j = M - (u + B3(3-j)): W_N^{M-k} = -conj(W_N^k)
-                const float2 wq = make_float2(-wp[3 - j].x, wp[3 - j].y);
-                Zp[j] = herm_pack(Y[j], Y[4 + (3 - j)], cconj(wp[j]));
-                Zq[j] = herm_pack(Y[4 + j], Y[3 - j], cconj(wq));
-            }
-        } else {
-            Y[0].y = 0.f;
-            Y[8].y = 0.f;
-            const float2 Yp4[5] = {Y[0], Y[1], Y[2], Y[3], Y[8]};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float2 w0 = (j == 0) ? make_float2(1.f, 0.f) : cconj(PV_LDG(tb.tw2n + 2 * B3 * j));
-                Zp[j] = herm_pack(Yp4[j], Yp4[4 - j], w0);
-                Zq[j] = herm_pack(Y[4 + j], Y[4 + (3 - j)], cconj(PV_LDG(tb.tw2n + B3 + 2 * B3 * j)));
-            }
+        {
+            const bool u0 = (u == 0);
+            auto sel = [&](float2 a, float2 b) { return u0 ? a : b; };
+            if (u0) { Y[0].y = 0.f; Y[8].y = 0.f; }          // the Hermitian inverse ignores Im of bins 0 and N/2
+            const float2 q1c = cconj(tt.q1);
+            // p side: Z[u + B3 j] pairs with bin M - (u + B3 j): q slot 3-j (thread 0: p slot 4-j, slot "4" = bin N/2)
+            Zp[0] = herm_pack(Y[0], sel(Y[8], Y[7]), cconj(wp[0]));
+            Zp[1] = herm_pack(Y[1], sel(Y[3], Y[6]), cconj(wp[1]));
+            Zp[2] = herm_pack(Y[2], sel(Y[2], Y[5]), cconj(wp[2]));
+            Zp[3] = herm_pack(Y[3], sel(Y[1], Y[4]), cconj(wp[3]));
+            // q side: bin (B3 - u_q) + B3 j, W_N^bin = conj(W_N^{u_q}) * exp(-2 pi i (j+1)/8); partner p slot 3-j
+            // (thread 0: q slot 3-j)
+            Zq[0] = herm_pack(Y[4], sel(Y[7], Y[3]), cconj(twid16<2, -1>(q1c)));
+            Zq[1] = herm_pack(Y[5], sel(Y[6], Y[2]), cconj(twid16<4, -1>(q1c)));
+            Zq[2] = herm_pack(Y[6], sel(Y[5], Y[1]), cconj(twid16<6, -1>(q1c)));
+            Zq[3] = herm_pack(Y[7], sel(Y[4], Y[0]), cconj(twid16<8, -1>(q1c)));
         }
         Tables itb{nullptr, nullptr, tb.tw2n, tb.itw1, tb.itw2, tb.win};
-        if (u != 0) {
-            // exp(+2 pi i m1 u/(N/2)) = conj(W_N^{2 m1 u}); for t1 = B3-u: j^m1 * W_N^{2 m1 u}
-            const float2 w6 = cmul(tt.w2, tt.w4);
+        {
+            // exp(+2 pi i m1 u/(N/2)) = conj(W_N^{2 m1 u}); for t1 = B3-u_q: j^m1 * W_N^{2 m1 u_q}
+            const float2 w6 = cmul(tt.w2, tt.w4), q6 = cmul(tt.q2, tt.q4);
             inverse_1_tw<LOG2N>(tP, cconj(tt.w2), cconj(tt.w4), cconj(w6), Zp, bufA);
-            inverse_1_tw<LOG2N>(tQ, mul_pj(tt.w2), make_float2(-tt.w4.x, -tt.w4.y), mul_mj(w6), Zq, bufA);
-        } else {
-            inverse_1<LOG2N>(tP, itb, Zp, bufA);
-            inverse_1<LOG2N>(tQ, itb, Zq, bufA);
+            inverse_1_tw<LOG2N>(tQ, mul_pj(tt.q2), make_float2(-tt.q4.x, -tt.q4.y), mul_mj(q6), Zq, bufA);
         }
         if constexpr (TWREG) {
             float2 e[8];
@@ -439,28 +469,6 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
         (void)S::T;
     }
     (void)M;
-}
-
-// Analysis-only frame for the phase-carry aggregate: updates P_prev and sum += D (k >= 1).
-template <int LOG2N, class Sync>
-PV_DEV void frame_aggregate(int tid, const FrameIO &io, const CTables &tb, const CThreadTw &tt, float2 *bufA,
-                            float2 *bufB, CState &st, long long (&sumD)[9], uint32_t (&Pfirst)[9], Sync sync)
-{
-    using C = CShape<LOG2N>;
-    constexpr bool TWREG = (2 * C::C1 == C::T) && (2 * C::C2 == C::T);
-    float2 X[9], wp[4];
-    cforward<LOG2N, TWREG>(tid, io, tb, tt, nullptr, bufA, bufB, sync, []() {}, X, wp);
-#pragma unroll
-    for (int sl = 0; sl < 9; sl++) {
-        if (sl == 8 && tid != 0) break;
-        const int bin = slot_bin<C::B3>(tid, sl);
-        const uint32_t Pc = phase_turns32(X[sl].x, X[sl].y);
-        const uint32_t nomA = ((uint32_t)bin * (uint32_t)tb.Ha) << (32 - LOG2N);
-        if (st.have_prev) sumD[sl] += (long long)(int32_t)(Pc - st.Pprev[sl] - nomA);
-        else Pfirst[sl] = Pc;
-        st.Pprev[sl] = Pc;
-    }
-    st.have_prev = 1;   // no trailing barrier: the next frame's first barrier orders the buffer reuse
 }
 
 }  // namespace pvfused

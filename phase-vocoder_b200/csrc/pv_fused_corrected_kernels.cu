@@ -48,7 +48,7 @@ struct CGroupSync {
 template <int LOG2N, int MINB>
 __global__ void __launch_bounds__(CLaunch<LOG2N>::THREADS, MINB)
 corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int vec_out_ok, int use_ring,
-                       unsigned group_bytes)
+                       unsigned group_bytes, PvAggArgs ag)
 {
     using C = CShape<LOG2N>;
     using L = CLaunch<LOG2N>;
@@ -74,9 +74,18 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
 
     const PvSegment seg = a.segs[seg_idx];
     const float *in = a.in + seg.stream * a.in_stride;
-    float *out = a.out + seg.stream * a.out_stream_stride;
-    unsigned char *state = a.state ? a.state + (long long)seg.state_idx * a.state_stride : nullptr;
     const int Hs = d.Hs;
+
+    // Analysis-only mode (phase-carry aggregate, PvAggArgs): the frame loop below is shared with the processing
+    // mode -- ONE call site of frame_corrected, hence one compiled copy of the forward transform, so both modes
+    // compute bit-identical phases.  The per-bin sums live in shared memory (psi / mag+D regions, unused then).
+    const bool agg_mode = ag.S != nullptr;
+    long long *sumS = reinterpret_cast<long long *>(psi);      // NB x 8 B
+    long long *sumH = reinterpret_cast<long long *>(magS);     // mag + D regions: 2 x NB x 4 B
+    uint32_t *agg_pf = (agg_mode && ag.P_first) ? ag.P_first + (long long)seg_idx * NB : nullptr;
+
+    float *out = agg_mode ? nullptr : a.out + seg.stream * a.out_stream_stride;
+    unsigned char *state = (a.state && !agg_mode) ? a.state + (long long)seg.state_idx * a.state_stride : nullptr;
 
     // state layout: [have_prev u32][pad][P_prev u32 x NB (8-byte padded)][psi u64 x V*NB][acc f32 x V*N]
     uint32_t *st_hdr = reinterpret_cast<uint32_t *>(state);
@@ -96,10 +105,24 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
         for (int sl = 0; sl < 9; sl++)
             if (sl < 8 || tid == 0) st.Pprev[sl] = st_P[slot_bin<B3>(tid, sl)];
     }
-    for (int i = tid; i < V * NB; i += T) psi[i] = cin ? st_psi[i] : 0ull;
-    for (int i = tid; i < V * N; i += T) {
-        const int ii = i & (N - 1);
-        acc[i] = (cin && ii + Hs < N) ? st_acc[i + Hs] : 0.f;
+    if (agg_mode) {
+        const bool carried = seg.carry_in && ag.P_prev != nullptr;
+        st.have_prev = carried;
+#pragma unroll
+        for (int sl = 0; sl < 9; sl++) {
+            if (sl == 8 && tid != 0) break;
+            const int bin = slot_bin<B3>(tid, sl);
+            st.Pprev[sl] = carried ? ag.P_prev[(long long)seg.stream * NB + bin] : 0u;
+            sumS[bin] = 0;
+            sumH[bin] = 0;
+            if (agg_pf) agg_pf[bin] = 0u;
+        }
+    } else {
+        for (int i = tid; i < V * NB; i += T) psi[i] = cin ? st_psi[i] : 0ull;
+        for (int i = tid; i < V * N; i += T) {
+            const int ii = i & (N - 1);
+            acc[i] = (cin && ii + Hs < N) ? st_acc[i + Hs] : 0.f;
+        }
     }
     if (use_ring) {
         FrameIO io0{in, a.n_in, seg.k_begin * (long long)d.Ha, true, true};
@@ -139,11 +162,24 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
                 if (use_ring == 2) ring_prefetch_coop16<N, T>(tid, nx, ring, N - d.Ha);
                 else ring_prefetch_coop<N, T>(tid, nx, ring, N - d.Ha);
             }
-            if (k > seg.k_begin) emit(k - 1, (pos0 - Hs) & (N - 1), PV_ZERO_ON_EMIT);
+            if (!agg_mode && k > seg.k_begin) emit(k - 1, (pos0 - Hs) & (N - 1), PV_ZERO_ON_EMIT);
         };
+        const AggCtx ac{agg_mode, k < seg.k_emit ? sumH : sumS, agg_pf};
         frame_corrected<LOG2N>(tid, io, tb, tt, ring, bufA, bufB, magS, dS, psi, acc, st, pos0, Hs, sync, hook,
-                               [&]() { if (use_ring) cp_async_wait_all(); });
+                               [&]() { if (use_ring) cp_async_wait_all(); }, ac);
         pos0 = (pos0 + Hs) & (N - 1);
+    }
+    if (agg_mode) {
+#pragma unroll
+        for (int sl = 0; sl < 9; sl++) {
+            if (sl == 8 && tid != 0) break;
+            const int bin = slot_bin<B3>(tid, sl);
+            const long long o = (long long)seg_idx * NB + bin;
+            ag.S[o] = sumS[bin];
+            if (ag.H) ag.H[o] = sumH[bin];
+            if (ag.P_last) ag.P_last[o] = st.Pprev[sl];
+        }
+        return;
     }
     sync();
     const int plast = (pos0 - Hs) & (N - 1);
@@ -155,52 +191,6 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
             if (sl < 8 || tid == 0) st_P[slot_bin<B3>(tid, sl)] = st.Pprev[sl];
         for (int i = tid; i < V * NB; i += T) st_psi[i] = psi[i];
         for (int i = tid; i < V * N; i += T) st_acc[i] = acc[(i & ~(N - 1)) + ((plast + i) & (N - 1))];
-    }
-}
-
-// ---- phase-carry aggregate: analysis only, one group per frame-range segment (PvAggArgs) ----
-template <int LOG2N>
-__global__ void __launch_bounds__(CLaunch<LOG2N>::THREADS)
-corrected_aggregate_kernel(PvDev d, CTables tb, PvAggArgs a, int vec_in_ok)
-{
-    using C = CShape<LOG2N>;
-    using L = CLaunch<LOG2N>;
-    constexpr int T = C::T, G = L::G, NB = C::NB, B3 = C::B3;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int g = threadIdx.x / T, tid = threadIdx.x % T;
-    const long long sg = (long long)blockIdx.x * G + g;
-    if (sg >= a.n_segs) return;
-    const PvSegment seg = a.segs[sg];
-    float2 *bufA = reinterpret_cast<float2 *>(smem_raw) + (size_t)g * (C::BUF_A + C::BUF_B);
-    float2 *bufB = bufA + C::BUF_A;
-    CGroupSync<T, G> sync{g, T >= 32 ? 0xffffffffu : (((1u << (T & 31)) - 1u) << ((threadIdx.x & 31) / T * T))};
-    const CThreadTw tt = load_cthread_tw<LOG2N>(tid, tb);
-    CState st;
-    long long accS[9], accH[9];
-    uint32_t pf[9];
-    const bool carried = seg.carry_in && a.P_prev != nullptr;
-    st.have_prev = carried;
-#pragma unroll
-    for (int sl = 0; sl < 9; sl++) {
-        accS[sl] = 0;
-        accH[sl] = 0;
-        pf[sl] = 0;
-        st.Pprev[sl] = (carried && (sl < 8 || tid == 0)) ? a.P_prev[(long long)seg.stream * NB + slot_bin<B3>(tid, sl)] : 0u;
-    }
-    const float *in = a.in + seg.stream * a.in_stride;
-    for (long long k = seg.k_begin; k < seg.k_end; ++k) {
-        FrameIO io{in, a.n_in, k * (long long)d.Ha, true, vec_in_ok != 0};
-        if (k < seg.k_emit) frame_aggregate<LOG2N>(tid, io, tb, tt, bufA, bufB, st, accH, pf, sync);
-        else frame_aggregate<LOG2N>(tid, io, tb, tt, bufA, bufB, st, accS, pf, sync);
-    }
-#pragma unroll
-    for (int sl = 0; sl < 9; sl++) {
-        if (sl == 8 && tid != 0) break;
-        const long long o = sg * NB + slot_bin<B3>(tid, sl);
-        a.S[o] = accS[sl];
-        if (a.H) a.H[o] = accH[sl];
-        if (a.P_first) a.P_first[o] = carried ? 0u : pf[sl];
-        if (a.P_last) a.P_last[o] = st.Pprev[sl];
     }
 }
 
@@ -251,7 +241,7 @@ cudaError_t claunch(const PvDev &d, const CTables &tb, const PvProcessArgs &a, c
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     const int grid = (a.n_segs + L::G - 1) / L::G;
-    kern<<<grid, L::THREADS, smem, st>>>(d, tb, a, in_ok, out_ok, ring, (unsigned)gb);
+    kern<<<grid, L::THREADS, smem, st>>>(d, tb, a, in_ok, out_ok, ring, (unsigned)gb, PvAggArgs{});
     return cudaGetLastError();
 }
 
@@ -302,18 +292,25 @@ static CTables make_ctables(const PvDev &d, const PvFusedTables &t)
     return tb;
 }
 
-template <int LOG2N>
-static cudaError_t agg_launch(const PvDev &d, const CTables &tb, const PvAggArgs &a, cudaStream_t st)
+// The aggregate runs in the SAME kernel instantiation as the processing pass (see AggCtx).
+template <int LOG2N, int MINB>
+static cudaError_t agg_launch(const PvDev &d, const CTables &tb, const PvAggArgs &ag, cudaStream_t st)
 {
     using L = CLaunch<LOG2N>;
-    using C = CShape<LOG2N>;
-    auto kern = corrected_aggregate_kernel<LOG2N>;
-    const size_t smem = (size_t)L::G * (C::BUF_A + C::BUF_B) * sizeof(float2);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = corrected_fused_kernel<LOG2N, MINB>;
+    const size_t gb = L::group_bytes(tb.V) - (size_t)d.N * 4;          // no input ring
+    const size_t smem = gb * L::G;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(L::group_bytes(tb.V) * L::G));
     if (e != cudaSuccess) return e;
-    const bool in_ok = (d.Ha % 2 == 0) && (a.in_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 7) == 0);
-    const int grid = (a.n_segs + L::G - 1) / L::G;
-    kern<<<grid, L::THREADS, smem, st>>>(d, tb, a, in_ok);
+    const bool in_ok = (d.Ha % 2 == 0) && (ag.in_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(ag.in) & 7) == 0);
+    PvProcessArgs a{};
+    a.in = ag.in;
+    a.in_stride = ag.in_stride;
+    a.n_in = ag.n_in;
+    a.segs = ag.segs;
+    a.n_segs = ag.n_segs;
+    const int grid = (ag.n_segs + L::G - 1) / L::G;
+    kern<<<grid, L::THREADS, smem, st>>>(d, tb, a, in_ok, 0, 0, (unsigned)gb, ag);
     return cudaGetLastError();
 }
 
@@ -322,10 +319,10 @@ cudaError_t pv_launch_corrected_aggregate(const PvDev &d, const PvFusedTables &t
     if (a.n_segs <= 0) return cudaSuccess;
     const CTables tb = make_ctables(d, t);
     switch (d.N) {
-        case 256: return agg_launch<8>(d, tb, a, st);
-        case 512: return agg_launch<9>(d, tb, a, st);
-        case 1024: return agg_launch<10>(d, tb, a, st);
-        case 2048: return agg_launch<11>(d, tb, a, st);
+        case 256: return agg_launch<8, 4>(d, tb, a, st);
+        case 512: return agg_launch<9, 4>(d, tb, a, st);
+        case 1024: return agg_launch<10, 4>(d, tb, a, st);
+        case 2048: return agg_launch<11, 4>(d, tb, a, st);
         default: return cudaErrorInvalidValue;
     }
 }
