@@ -362,8 +362,15 @@ def run_ours(args):
         bytes_per_frame = 4 * HOP + 4 * V * HOP
         kern_s = (kern_ms * 1e-3 / kern_n) if kern_n else (ms_total * 1e-3 / args.steps)
         achieved = S * F * bytes_per_frame / kern_s / 1e9
+        traffic = None          # dram__bytes_read + dram__bytes_write of one ncu --set full capture of this launch shape
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[args.mode]
+            if tr["frames_per_launch"] == S * F:
+                traffic = tr["bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "kernel": "fused stream kernel",
+                    "traffic": traffic, "algorithmic_bytes_per_launch": S * F * bytes_per_frame, "peak_source": peak_src, "kernel": "fused stream kernel",
                     "kernel_ms": kern_s * 1e3, "algorithmic_bytes_per_frame": bytes_per_frame,
                     "note": "fully fused, the path is shared-memory/fp32 bound, not HBM bound (SURVEY fact 5)"}
         line = {
