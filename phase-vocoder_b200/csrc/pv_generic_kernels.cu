@@ -53,6 +53,61 @@ __device__ float2 *fft_stockham(float2 *x, float2 *y, int M, int tws, const floa
     return x;
 }
 
+// tw[] covers exp(-j*pi*k/N) for k < N (half a circle); k in [N, 2N) is the negated first half.
+__device__ __forceinline__ float2 tw_at(const float2 *__restrict__ tw, int k, int N)
+{
+    float2 w = tw[k & (N - 1)];
+    if (k & N) { w.x = -w.x; w.y = -w.y; }
+    return w;
+}
+
+// Stockham radix-4 autosort FFT (one radix-2 stage first when log2 M is odd): half the passes, barriers and
+// shared-memory traffic of the radix-2 version.  Same contract as fft_stockham.
+__device__ float2 *fft_stockham4(float2 *x, float2 *y, int M, int tws, const float2 *__restrict__ tw, int N,
+                                 bool inverse)
+{
+    int n = M, lg_s = 0;
+    int lgM = 0;
+    while ((1 << lgM) < M) ++lgM;
+    if (lgM & 1) {                                   // one radix-2 stage
+        const int m = n >> 1;
+        for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
+            float2 w = tw_at(tw, idx * tws, N);
+            if (inverse) w.y = -w.y;
+            const float2 a = x[idx], b = x[idx + m];
+            y[2 * idx] = make_float2(a.x + b.x, a.y + b.y);
+            y[2 * idx + 1] = cmul(make_float2(a.x - b.x, a.y - b.y), w);
+        }
+        __syncthreads();
+        float2 *t = x; x = y; y = t;
+        n = m;
+        lg_s = 1;
+    }
+    for (; n > 1; n >>= 2, lg_s += 2) {
+        const int m = n >> 2, s = 1 << lg_s;
+        for (int idx = threadIdx.x; idx < (M >> 2); idx += blockDim.x) {
+            const int p = idx >> lg_s, q = idx & (s - 1);
+            const float2 a0 = x[q + s * p], a1 = x[q + s * (p + m)], a2 = x[q + s * (p + 2 * m)], a3 = x[q + s * (p + 3 * m)];
+            const float2 t0 = make_float2(a0.x + a2.x, a0.y + a2.y), t1 = make_float2(a0.x - a2.x, a0.y - a2.y);
+            const float2 t2 = make_float2(a1.x + a3.x, a1.y + a3.y);
+            const float2 d = make_float2(a1.x - a3.x, a1.y - a3.y);
+            // forward: multiply (a1 - a3) by -j, inverse: by +j
+            const float2 t3 = inverse ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
+            const int kb = (p << lg_s) * tws;                     // W_n^p = exp(-2 pi i p s / M)
+            float2 w1 = tw_at(tw, kb, N), w2 = tw_at(tw, 2 * kb, N), w3 = tw_at(tw, 3 * kb, N);
+            if (inverse) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+            float2 *o = y + q + s * (4 * p);
+            o[0] = make_float2(t0.x + t2.x, t0.y + t2.y);
+            o[s] = cmul(make_float2(t1.x + t3.x, t1.y + t3.y), w1);
+            o[2 * s] = cmul(make_float2(t0.x - t2.x, t0.y - t2.y), w2);
+            o[3 * s] = cmul(make_float2(t1.x - t3.x, t1.y - t3.y), w3);
+        }
+        __syncthreads();
+        float2 *t = x; x = y; y = t;
+    }
+    return x;
+}
+
 // Steps A+B: window, zero-phase shift, zero pad to 2N, packed as N complex points.
 __device__ void load_frame_compat(float2 *c, const float *__restrict__ in, int64_t base, int64_t n_in,
                                   const PvDev &d)
@@ -160,7 +215,7 @@ analysis_batch_kernel(PvDev d, const float *__restrict__ in, int64_t n_in, float
     const int64_t k = blockIdx.x;
     load_frame_compat(a, in, k * (int64_t)d.Ha, n_in, d);
     __syncthreads();
-    const float2 *C = fft_stockham(a, b, N, 2, d.tw, false);
+    const float2 *C = fft_stockham4(a, b, N, 2, d.tw, d.N, false);
     float2 *o = out + k * 2 * (int64_t)N;
     for (int kk = threadIdx.x; kk <= N; kk += blockDim.x) {
         float2 X;
@@ -191,7 +246,7 @@ resynthesis_batch_kernel(PvDev d, const float2 *__restrict__ spectra, int64_t n_
         const float2 *sp = spectra + k * 2 * (int64_t)N;
         build_inverse_input(a, [&](int kk) { return polar_to_rect_d2(sp[kk]); }, d);
         __syncthreads();
-        const float2 *r = fft_stockham(a, b, h, 4, d.tw, true);
+        const float2 *r = fft_stockham4(a, b, h, 4, d.tw, d.N, true);
         ola_accumulate(acc, r, pos0, false, d);
         __syncthreads();
         if (out != nullptr)
@@ -246,12 +301,12 @@ compat_generic_kernel(PvDev d, PvProcessArgs a)
         if (analysed) {
             load_frame_compat(bufA, in, k * (int64_t)d.Ha, a.n_in, d);
             __syncthreads();
-            float2 *C = fft_stockham(bufA, bufB, N, 2, d.tw, false);
+            float2 *C = fft_stockham4(bufA, bufB, N, 2, d.tw, d.N, false);
             float2 *Z = (C == bufA) ? bufB : bufA;
             build_inverse_input(Z, [&](int kk) {
                 return polar_to_rect_d2(mag_phase(split_bin(C, kk, d), d.flags)); }, d);
             __syncthreads();
-            r = fft_stockham(Z, C, h, 4, d.tw, true);
+            r = fft_stockham4(Z, C, h, 4, d.tw, d.N, true);
         }
         ola_accumulate(acc, r, pos0, !analysed, d);
         __syncthreads();
@@ -316,7 +371,7 @@ corrected_generic_kernel(PvDev d, PvProcessArgs a)
             bufA[m] = make_float2(x0 * d.win[i], x1 * d.win[i + 1]);
         }
         __syncthreads();
-        const float2 *C = fft_stockham(bufA, bufB, M, 4, d.tw, false);
+        const float2 *C = fft_stockham4(bufA, bufB, M, 4, d.tw, d.N, false);
         for (int kk = threadIdx.x; kk <= M / 2; kk += blockDim.x) {
             float2 xk, xm;
             if (kk == 0) {
@@ -369,7 +424,7 @@ corrected_generic_kernel(PvDev d, PvProcessArgs a)
             float2 *Z = bufA;
             build_inverse_input(Z, [&](int kk) { return Ys[kk]; }, d);
             __syncthreads();
-            const float2 *r = fft_stockham(Z, bufB, M, 4, d.tw, true);
+            const float2 *r = fft_stockham4(Z, bufB, M, 4, d.tw, d.N, true);
             float *ac = acc + (size_t)v * N;
             ola_accumulate(ac, r, pos0, false, d, scale);
             __syncthreads();
@@ -426,7 +481,7 @@ aggregate_generic_kernel(PvDev d, PvAggArgs a)
             bufA[m] = make_float2(x0 * d.win[i], x1 * d.win[i + 1]);
         }
         __syncthreads();
-        const float2 *C = fft_stockham(bufA, bufB, M, 4, d.tw, false);
+        const float2 *C = fft_stockham4(bufA, bufB, M, 4, d.tw, d.N, false);
         for (int kk = threadIdx.x; kk <= M / 2; kk += blockDim.x) {
             float2 xk, xm;
             if (kk == 0) {

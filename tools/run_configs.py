@@ -62,6 +62,27 @@ def run(name, N, Ha, Hs, mode, betas, streams, frames, fs, gen, check_streams=2,
           f"{fps*Ha/fs:,.0f} | {gbs:.0f} | {worst:.1f} |", flush=True)
 
 
+def realtime_step(streams=4096, N=256, H=64, betas=(1.0, 2 ** (4 / 12), 2 ** (7 / 12), 2.0), calls=300):
+    """C4 as a real-time server would run it: ONE hop per stream per call, state carried on the device
+    (PV_PROCESS_CARRY_IN | CARRY_OUT).  Reports the device time per call against the hop period."""
+    pv = pvb200.PhaseVocoder(N, hop_in=H, hop_out=H, mode=pvb200.MODE_CORRECTED, window_type=pvb200.WIN_HANN_PERIODIC,
+                             pitch=tuple(f32(b) for b in betas))
+    x = torch.randn((streams, N), device="cuda") * 0.1
+    st = torch.zeros((streams, pv.state_bytes()), dtype=torch.uint8, device="cuda")
+    out = torch.empty((streams, len(betas), H), device="cuda")
+    pv.process(x, 1, out=out, state=st, flags=pvb200.CARRY_OUT)
+    fl = pvb200.CARRY_IN | pvb200.CARRY_OUT
+    ms = timed(lambda: pv.process(x, 1, out=out, state=st, flags=fl), n=calls)
+    t0 = time.perf_counter()
+    for _ in range(calls):
+        pv.process(x, 1, out=out, state=st, flags=fl)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / calls * 1e3
+    print(f"\nC4 real-time step: {streams} streams x 1 hop ({H} samples) x {len(betas)} voices per call: "
+          f"{ms*1e3:.0f} us device time per call, {wall*1e3:.0f} us wall per call (hop period {H/44100*1e3:.2f} ms, "
+          f"window budget {N/44100*1e3:.1f} ms) -> {streams/(ms*1e-3)/1e6:.1f} M frames/s")
+
+
 def main():
     print("| config | window | Ha/Hs | mode | voices | streams x frames | ms/launch | frames/s | audio-s/s (input) | "
           "algorithmic GB/s | worst SNR vs fp64 oracle (dB) |")
@@ -87,6 +108,7 @@ def main():
     # C5: 1 h, 48 kHz, stereo, window 4096 hop 1024 (168 750 frames per channel)
     run("C5 long file", 4096, 1024, 1024, "compat", [1.0], 2, 168750, 48000, noisy, check_frames=300)
     run("C5 long file", 4096, 1024, 1024, "corrected", [semi(7)], 2, 20000, 48000, tone, check_frames=100)
+    realtime_step()
 
 
 if __name__ == "__main__":
