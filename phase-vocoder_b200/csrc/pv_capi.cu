@@ -42,6 +42,9 @@ struct pv_handle {
     size_t agg_cap = 0, api_cap = 0;
     int32_t split_parts = 0;
     int64_t split_streams = -1, split_frames = -1;
+    int split_carry = -1;
+    int64_t split_skip = -1;
+    uint32_t *d_Pl = nullptr;
     int64_t *d_S = nullptr, *d_H = nullptr;
     uint32_t *d_Pf = nullptr;
     size_t carry_cap = 0;
@@ -208,9 +211,12 @@ int plan_segments(pv_handle *h, int64_t n_streams, int64_t n_frames, int64_t ski
 // Corrected mode with few streams: cut every stream into `parts` frame ranges so that the grid fills the
 // machine.  Two tables (index = stream*parts + part): the analysis ranges for the phase-carry aggregate
 // and the processing ranges (halo + owned frames) that start from the rebuilt state of each part.
-int plan_corrected_split(pv_handle *h, int64_t n_streams, int64_t n_frames, int32_t parts)
+int plan_corrected_split(pv_handle *h, int64_t n_streams, int64_t n_frames, int32_t parts, bool user_carry,
+                         int64_t skip = 0)
 {
-    if (h->split_streams == n_streams && h->split_frames == n_frames && h->split_parts == parts) return PV_OK;
+    if (h->split_streams == n_streams && h->split_frames == n_frames && h->split_parts == parts &&
+        h->split_carry == (int)user_carry && h->split_skip == skip)
+        return PV_OK;
     const int N = h->p.window, Hs = h->p.hop_out;
     const int64_t halo = (N - 1) / Hs;
     const int64_t L = (n_frames + parts - 1) / parts;
@@ -227,9 +233,10 @@ int plan_corrected_split(pv_handle *h, int64_t n_streams, int64_t n_frames, int3
             a.k_emit = k0;
             a.k_end = k1;
             q.k_begin = ks;
-            q.k_emit = k0;
+            q.k_emit = std::min<int64_t>(k1, std::max<int64_t>(k0, skip));   // the caller's skipped frames are computed, not written
             q.k_end = k1;
-            q.carry_in = ks >= 1 ? 1 : 0;                   // parts that reach frame 0 start fresh
+            q.carry_in = (ks >= 1 || user_carry) ? 1 : 0;   // parts that reach frame 0 start fresh (or from the caller's state)
+            a.carry_in = (p == 0) ? 1 : 0;                  // effective only when the launch supplies P_prev
             q.carry_out = (p == parts - 1) ? 1 : 0;         // the last part leaves the stream's final state in its slot
             agg[i] = a;
             proc[i] = q;
@@ -253,11 +260,12 @@ int plan_corrected_split(pv_handle *h, int64_t n_streams, int64_t n_frames, int3
     PV_CUDA(cudaMemcpy(h->d_segs, proc.data(), sizeof(PvSegment) * n, cudaMemcpyHostToDevice));
     const size_t nb = (size_t)N / 2 + 1;
     if (n * nb > h->carry_cap) {
-        cudaFree(h->d_S); cudaFree(h->d_H); cudaFree(h->d_Pf);
-        h->d_S = h->d_H = nullptr; h->d_Pf = nullptr; h->carry_cap = 0;
+        cudaFree(h->d_S); cudaFree(h->d_H); cudaFree(h->d_Pf); cudaFree(h->d_Pl);
+        h->d_S = h->d_H = nullptr; h->d_Pf = h->d_Pl = nullptr; h->carry_cap = 0;
         PV_CUDA(cudaMalloc((void **)&h->d_S, sizeof(int64_t) * n * nb));
         PV_CUDA(cudaMalloc((void **)&h->d_H, sizeof(int64_t) * n * nb));
         PV_CUDA(cudaMalloc((void **)&h->d_Pf, sizeof(uint32_t) * n * nb));
+        PV_CUDA(cudaMalloc((void **)&h->d_Pl, sizeof(uint32_t) * n * nb));
         h->carry_cap = n * nb;
     }
     const size_t sb = pv_state_bytes(h);
@@ -271,9 +279,23 @@ int plan_corrected_split(pv_handle *h, int64_t n_streams, int64_t n_frames, int3
     h->split_streams = n_streams;
     h->split_frames = n_frames;
     h->split_parts = parts;
+    h->split_carry = (int)user_carry;
+    h->split_skip = skip;
     h->n_segs = (int32_t)n;
     h->plan_streams = -1;            // the shared d_segs table no longer holds a plan_segments() plan
     return PV_OK;
+}
+
+// number of frame-range parts per stream for a corrected run of few streams (1 = do not split)
+int64_t corrected_parts(const pv_handle *h, int64_t n_streams, int64_t n_frames)
+{
+    if (getenv("PV_NO_SPLIT")) return 1;
+    const int64_t halo = (h->p.window - 1) / h->p.hop_out;
+    const int64_t min_len = std::max<int64_t>(16 * (halo + 1), 32);     // keep the extra analysis + halo small
+    int64_t parts = std::min<int64_t>(n_frames / min_len, (h->capacity * 2 + n_streams - 1) / n_streams);
+    if (parts < 2 || n_streams * parts > (1 << 20)) return 1;
+    const int64_t L = (n_frames + parts - 1) / parts;
+    return (n_frames + L - 1) / L;                                       // no empty trailing part
 }
 
 int ensure(float **buf, size_t *cap, size_t need)
@@ -430,6 +452,7 @@ void pv_destroy(pv_handle *h)
     cudaFree(h->d_S);
     cudaFree(h->d_H);
     cudaFree(h->d_Pf);
+    cudaFree(h->d_Pl);
     cudaFree(h->d_slots);
     cudaFree(h->d_in);
     cudaFree(h->d_out);
@@ -555,6 +578,21 @@ int pv_corrected_aggregate(pv_handle *h, const float *in, int64_t n_streams, int
     if (h->p.mode != PV_MODE_CORRECTED) return fail(PV_ERR_PARAM, "pv_corrected_aggregate needs a corrected-mode handle");
     if (n_streams == 0) return PV_OK;
     DeviceGuard guard(h->device);
+    {   // few long streams: aggregate frame-range parts concurrently, then add the per-part sums
+        const int64_t parts = corrected_parts(h, n_streams, n_frames);
+        if (parts >= 2) {
+            int rc0 = plan_corrected_split(h, n_streams, n_frames, (int32_t)parts, false);
+            if (rc0 != PV_OK) return rc0;
+            const int nb = h->p.window / 2 + 1;
+            PvAggArgs ag{in, in_stride, n_in, h->d_agg_segs, h->n_segs, P_prev, (int64_t)nb, h->d_S, nullptr, h->d_Pf, h->d_Pl};
+            if (h->fused && !getenv("PV_FORCE_GENERIC")) PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, ag, (cudaStream_t)cuda_stream));
+            else PV_CUDA(pv_launch_aggregate_generic(h->dev, ag, (cudaStream_t)cuda_stream));
+            PV_CUDA(pv_launch_reduce_parts(nb, n_streams, (int32_t)parts, h->d_S, h->d_Pf, h->d_Pl, sumD, P_first, P_last,
+                                           (cudaStream_t)cuda_stream));
+            h->launches += 2;
+            return PV_OK;
+        }
+    }
     std::vector<PvSegment> segs((size_t)n_streams);
     for (int64_t s = 0; s < n_streams; s++) {
         PvSegment g{};
@@ -574,7 +612,7 @@ int pv_corrected_aggregate(pv_handle *h, const float *in, int64_t n_streams, int
         h->api_cap = segs.size();
     }
     PV_CUDA(cudaMemcpy(h->d_api_segs, segs.data(), sizeof(PvSegment) * segs.size(), cudaMemcpyHostToDevice));
-    PvAggArgs a{in, in_stride, n_in, h->d_api_segs, (int32_t)n_streams, P_prev, sumD, nullptr, P_first, P_last};
+    PvAggArgs a{in, in_stride, n_in, h->d_api_segs, (int32_t)n_streams, P_prev, (int64_t)(h->p.window / 2 + 1), sumD, nullptr, P_first, P_last};
     if (h->fused && !getenv("PV_FORCE_GENERIC")) PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, a, (cudaStream_t)cuda_stream));
     else PV_CUDA(pv_launch_aggregate_generic(h->dev, a, (cudaStream_t)cuda_stream));
     h->launches++;
@@ -631,33 +669,28 @@ static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_
     cudaStream_t st = (cudaStream_t)cuda_stream;
     // ---- corrected mode, few streams: split into frame-range parts with an on-device phase-carry scan ----
     const bool force_generic0 = getenv("PV_FORCE_GENERIC") != nullptr;
-    if (h->p.mode == PV_MODE_CORRECTED && skip_frames == 0 && !(flags & PV_PROCESS_CARRY_IN) &&
-        plan_streams == n_streams && !getenv("PV_NO_SPLIT")) {
-        const int N = h->p.window;
-        const int64_t halo = (N - 1) / h->p.hop_out;
-        const int64_t min_len = std::max<int64_t>(16 * (halo + 1), 32);     // keep the extra analysis + halo small
-        int64_t parts = std::min<int64_t>(n_frames / min_len, (h->capacity * 2 + n_streams - 1) / n_streams);
+    if (h->p.mode == PV_MODE_CORRECTED && plan_streams == n_streams) {
+        const bool user_carry = (flags & PV_PROCESS_CARRY_IN) != 0;
+        const int64_t parts = corrected_parts(h, n_streams, n_frames);
         if (parts >= 2) {
-            const int64_t L = (n_frames + parts - 1) / parts;
-            parts = (n_frames + L - 1) / L;                                  // no empty trailing part
-        }
-        if (parts >= 2 && n_streams * parts <= 1 << 20) {
-            int rc0 = plan_corrected_split(h, n_streams, n_frames, (int32_t)parts);
+            int rc0 = plan_corrected_split(h, n_streams, n_frames, (int32_t)parts, user_carry, skip_frames);
             if (rc0 != PV_OK) return rc0;
             const bool fused_ok = h->fused && !force_generic0;
-            PvAggArgs ag{in, in_stride, n_in, h->d_agg_segs, h->n_segs, nullptr, h->d_S, h->d_H, h->d_Pf, nullptr};
+            const int64_t sb = (int64_t)pv_state_bytes(h);
+            PvAggArgs ag{in, in_stride, n_in, h->d_agg_segs, h->n_segs,
+                         user_carry ? reinterpret_cast<const uint32_t *>((const unsigned char *)state + 8) : nullptr, sb / 4,
+                         h->d_S, h->d_H, h->d_Pf, nullptr};
             if (fused_ok) PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, ag, st));
             else PV_CUDA(pv_launch_aggregate_generic(h->dev, ag, st));
-            const int64_t sb = (int64_t)pv_state_bytes(h);
             PV_CUDA(pv_launch_split_states(h->dev, n_streams, (int32_t)parts, h->d_segs, h->d_S, h->d_H, h->d_Pf,
-                                           h->d_slots, sb, st));
+                                           h->d_slots, sb, user_carry ? (const unsigned char *)state : nullptr, st));
             PvProcessArgs a{};
             a.in = in;
             a.in_stride = in_stride;
             a.n_in = n_in;
             a.n_analysed = n_analysed;
             a.n_frames = n_frames;
-            a.out = out;
+            a.out = out - skip_frames * (int64_t)h->p.hop_out;     // kernels index the output by frame number
             a.out_stream_stride = out_stream_stride;
             a.out_voice_stride = out_voice_stride;
             a.state = h->d_slots;

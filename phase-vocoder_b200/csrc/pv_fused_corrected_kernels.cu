@@ -112,7 +112,7 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
         for (int sl = 0; sl < 9; sl++) {
             if (sl == 8 && tid != 0) break;
             const int bin = slot_bin<B3>(tid, sl);
-            st.Pprev[sl] = carried ? ag.P_prev[(long long)seg.stream * NB + bin] : 0u;
+            st.Pprev[sl] = carried ? ag.P_prev[(long long)seg.stream * ag.P_prev_stride + bin] : 0u;
             sumS[bin] = 0;
             sumH[bin] = 0;
             if (agg_pf) agg_pf[bin] = 0u;
@@ -329,7 +329,8 @@ cudaError_t pv_launch_corrected_aggregate(const PvDev &d, const PvFusedTables &t
 
 // One block per stream walks its parts in order: running = sum_{q<p} S_q (per bin, int64 in shared memory).
 __global__ void split_states_kernel(PvDev d, CTables tb, int parts, const PvSegment *segs, const long long *S,
-                                    const long long *H, const uint32_t *P_first, unsigned char *slots, long long slot_stride)
+                                    const long long *H, const uint32_t *P_first, unsigned char *slots, long long slot_stride,
+                                    const unsigned char *state_in)
 {
     extern __shared__ long long sh[];
     const int NB = d.N / 2 + 1, V = tb.V, N = d.N;
@@ -338,11 +339,19 @@ __global__ void split_states_kernel(PvDev d, CTables tb, int parts, const PvSegm
     for (int b = threadIdx.x; b < NB; b += blockDim.x) run[b] = 0;
     __syncthreads();
     const uint32_t *P0 = P_first + (s * parts) * NB;
+    // carried-in stream: psi continues from the caller's accumulators and frame 0 has a phase difference too
+    const unsigned char *sin = state_in ? state_in + s * slot_stride : nullptr;
+    const bool cont = sin && reinterpret_cast<const uint32_t *>(sin)[0] != 0;
+    const unsigned long long *psi_in = sin ? reinterpret_cast<const unsigned long long *>(sin + 8 + ((NB * 4 + 7) / 8) * 8) : nullptr;
+    if (sin) {      // part 0 starts from the caller's state as it is
+        unsigned char *dst = slots + (long long)segs[s * parts].state_idx * slot_stride;
+        for (long long i = threadIdx.x; i < slot_stride / 4; i += blockDim.x)
+            reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(sin)[i];
+    }
     for (int p = 0; p < parts; p++) {
         const long long gidx = s * parts + p;
         const PvSegment seg = segs[gidx];
-        if (seg.k_end <= seg.k_emit) break;                        // unused trailing part
-        if (seg.carry_in) {
+        if (seg.carry_in && p > 0) {
             for (int b = threadIdx.x; b < NB; b += blockDim.x) pre[b] = run[b] - H[gidx * NB + b];
             __syncthreads();
             unsigned char *st = slots + (long long)seg.state_idx * slot_stride;
@@ -352,13 +361,14 @@ __global__ void split_states_kernel(PvDev d, CTables tb, int parts, const PvSegm
             float *acc = reinterpret_cast<float *>(psi + (size_t)V * NB);
             if (threadIdx.x == 0) { hdr[0] = 1u; hdr[1] = 0u; }
             for (int b = threadIdx.x; b < NB; b += blockDim.x) stP[b] = P_first[gidx * NB + b];
-            const unsigned long long nb4 = (unsigned long long)(seg.k_begin - 1);
+            const unsigned long long nb4 = (unsigned long long)(cont ? seg.k_begin : seg.k_begin - 1);
             for (int i = threadIdx.x; i < V * NB; i += blockDim.x) {
                 const int v = i / NB;
                 const int lo = tb.a_lo[i], hi = tb.a_hi[i];
                 unsigned long long ps = 0;
                 if (lo <= hi)
-                    ps = ((unsigned long long)P0[hi] << 32) + nb4 * tb.nomS[i] + (unsigned long long)(pre[hi] * (long long)tb.Rq[v]);
+                    ps = (cont ? psi_in[i] : ((unsigned long long)P0[hi] << 32)) + nb4 * tb.nomS[i] +
+                         (unsigned long long)(pre[hi] * (long long)tb.Rq[v]);
                 psi[i] = ps;
             }
             for (int i = threadIdx.x; i < V * N; i += blockDim.x) acc[i] = 0.f;
@@ -369,16 +379,39 @@ __global__ void split_states_kernel(PvDev d, CTables tb, int parts, const PvSegm
     }
 }
 
+__global__ void reduce_parts_kernel(int nb, int parts, const long long *S, const uint32_t *Pf, const uint32_t *Pl,
+                                    long long *sumD, uint32_t *P_first, uint32_t *P_last)
+{
+    const long long s = blockIdx.x;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        long long acc = 0;
+        for (int p = 0; p < parts; p++) acc += S[(s * parts + p) * nb + b];
+        sumD[s * nb + b] = acc;
+        if (P_first) P_first[s * nb + b] = Pf[(s * parts) * nb + b];
+        if (P_last) P_last[s * nb + b] = Pl[(s * parts + parts - 1) * nb + b];
+    }
+}
+
+cudaError_t pv_launch_reduce_parts(int nb, int64_t n_streams, int32_t parts, const int64_t *S, const uint32_t *Pf,
+                                   const uint32_t *Pl, int64_t *sumD, uint32_t *P_first, uint32_t *P_last, cudaStream_t st)
+{
+    if (n_streams <= 0) return cudaSuccess;
+    reduce_parts_kernel<<<(unsigned)n_streams, 256, 0, st>>>(nb, parts, reinterpret_cast<const long long *>(S), Pf, Pl,
+                                                            reinterpret_cast<long long *>(sumD), P_first, P_last);
+    return cudaGetLastError();
+}
+
 cudaError_t pv_launch_split_states(const PvDev &d, int64_t n_streams, int32_t parts, const PvSegment *proc_segs,
                                    const int64_t *S, const int64_t *H, const uint32_t *P_first, unsigned char *slots,
-                                   int64_t slot_stride, cudaStream_t st)
+                                   int64_t slot_stride, const unsigned char *state_in, cudaStream_t st)
 {
     if (n_streams <= 0) return cudaSuccess;
     PvFusedTables none;
     const CTables tb = make_ctables(d, none);
     const size_t smem = sizeof(long long) * 2 * (size_t)(d.N / 2 + 1);
     split_states_kernel<<<(unsigned)n_streams, 256, smem, st>>>(d, tb, parts, proc_segs, reinterpret_cast<const long long *>(S),
-                                                               reinterpret_cast<const long long *>(H), P_first, slots, slot_stride);
+                                                               reinterpret_cast<const long long *>(H), P_first, slots, slot_stride,
+                                                               state_in);
     return cudaGetLastError();
 }
 

@@ -465,7 +465,7 @@ aggregate_generic_kernel(PvDev d, PvAggArgs a)
     const bool carried = seg.carry_in && a.P_prev != nullptr;
     bool have_prev = carried;
     for (int b = threadIdx.x; b < NB; b += blockDim.x) {
-        Pp[b] = carried ? a.P_prev[(long long)seg.stream * NB + b] : 0u;
+        Pp[b] = carried ? a.P_prev[(long long)seg.stream * a.P_prev_stride + b] : 0u;
         a.S[sg * NB + b] = 0;
         if (a.H) a.H[sg * NB + b] = 0;
         if (a.P_first) a.P_first[sg * NB + b] = 0u;

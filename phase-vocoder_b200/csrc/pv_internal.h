@@ -72,7 +72,8 @@ struct PvAggArgs {
     int64_t in_stride, n_in;
     const PvSegment *segs;
     int32_t n_segs;
-    const uint32_t *P_prev;   // [stream][nb], used by segments with carry_in
+    const uint32_t *P_prev;   // per stream, used by segments with carry_in: P_prev + stream*P_prev_stride
+    int64_t P_prev_stride;    // in uint32 units (nb for a dense array, state_bytes/4 inside state blobs)
     int64_t *S, *H;
     uint32_t *P_first, *P_last;
 };
@@ -94,8 +95,12 @@ cudaError_t pv_launch_aggregate_generic(const PvDev &d, const PvAggArgs &a, cuda
 // Turns the per-part aggregates of split corrected streams into the carried state of every part:
 // part p of stream s (parts_per_stream each, table index s*parts + p) starts computing at frame ks[p];
 // its state slot gets psi = (P0[a] << 32) + (ks-1)*nomS + Rq*(sum_{q<p} S_q - H_p)[a], P_prev = P_first[p].
+// state_in (or null): the caller's carried-in state per stream; then psi starts from it and frame 0 counts.
 cudaError_t pv_launch_split_states(const PvDev &d, int64_t n_streams, int32_t parts, const PvSegment *proc_segs,
                                    const int64_t *S, const int64_t *H, const uint32_t *P_first, unsigned char *slots,
-                                   int64_t slot_stride, cudaStream_t st);
+                                   int64_t slot_stride, const unsigned char *state_in, cudaStream_t st);
+// sumD[s] = sum over the parts of stream s of S; P_first from part 0; P_last from the last part.
+cudaError_t pv_launch_reduce_parts(int nb, int64_t n_streams, int32_t parts, const int64_t *S, const uint32_t *Pf,
+                                   const uint32_t *Pl, int64_t *sumD, uint32_t *P_first, uint32_t *P_last, cudaStream_t st);
 // generic (any window) fused corrected path; a.state must be non-null (caller's or library scratch)
 cudaError_t pv_launch_corrected_generic(const PvDev &d, const PvProcessArgs &a, cudaStream_t st);

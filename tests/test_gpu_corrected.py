@@ -198,3 +198,25 @@ def test_corrected_intra_gpu_split_is_bit_exact(monkeypatch, N, Ha, Hs, betas, n
     assert pv2.launch_count() == 1
     assert np.array_equal(split, seq)
     assert torch.equal(st_a, st_b)
+
+
+def test_corrected_split_with_carry_in_and_skip_is_bit_exact(monkeypatch):
+    """The on-GPU split also starts from a carried-in state and honours skip_frames (what a frame-range rank
+    of a multi-GPU run does); and the public aggregate is split the same way.  All bit-identical to sequential."""
+    N, Ha, Hs, nf, k_cut, skip = 1024, 256, 256, 2600, 900, 3
+    betas = [SEMI7, 1.0]
+    x = torch.from_numpy(multitone(N + nf * Ha, seed=31, noise=1e-3)).cuda()[None, :]
+
+    def run(pv):
+        st = torch.zeros((1, pv.state_bytes()), dtype=torch.uint8, device="cuda")
+        a = pv.process(x, k_cut, state=st, flags=pvb200.CARRY_OUT)
+        b = pv.process(x[:, k_cut * Ha:], nf - k_cut, state=st, flags=pvb200.CARRY_IN | pvb200.CARRY_OUT, skip=skip)
+        sumD, Pf, Pl = pv.aggregate(x, nf)
+        return a.cpu().numpy(), b.cpu().numpy(), st.cpu().numpy(), sumD.cpu().numpy(), Pf.cpu().numpy(), Pl.cpu().numpy()
+
+    got = run(make(N, Ha, Hs, betas))
+    monkeypatch.setenv("PV_NO_SPLIT", "1")
+    want = run(make(N, Ha, Hs, betas))
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    assert got[1].shape[2] == (nf - k_cut - skip) * Hs
