@@ -319,7 +319,7 @@ PV_DEV void middle_compat(int u, const Tables &tb, const ThreadTw &tt, bool nan_
     using S = Shape<LOG2N>;
     constexpr int N = S::N, B3 = S::B3;
     float2 Yp[5], Yq[4];
-    if constexpr (TWREG) {
+    {
         // one path for all threads (see ThreadTw): selects instead of a divergent copy for thread 0
         const bool u0 = (u == 0);
         auto sel = [&](float2 a, float2 b) { return u0 ? a : b; };
@@ -350,38 +350,9 @@ PV_DEV void middle_compat(int u, const Tables &tb, const ThreadTw &tt, bool nan_
         Zq[1] = herm_pack(Yq[1], sel(Yq[2], Yp[2]), cconj(rot16<4>(q1c)));
         Zq[2] = herm_pack(Yq[2], sel(Yq[1], Yp[1]), cconj(rot16<6>(q1c)));
         Zq[3] = herm_pack(Yq[3], sel(Yq[0], Yp[0]), cconj(rot16<8>(q1c)));
-    } else if (u != 0) {
-        {
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int kp = u + B3 * j, kq = (B3 - u) + B3 * j;
-                Yp[j] = compat_map(split(P[j], Q[7 - j], PV_LDG(tb.tw2n + kp)), nan_compat);
-                Yq[j] = compat_map(split(Q[j], P[7 - j], PV_LDG(tb.tw2n + kq)), nan_compat);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int kp = u + B3 * j, kq = (B3 - u) + B3 * j;
-                Zp[j] = herm_pack(Yp[j], Yq[3 - j], cconj(PV_LDG(tb.tw2n + 2 * kp)));
-                Zq[j] = herm_pack(Yq[j], Yp[3 - j], cconj(PV_LDG(tb.tw2n + 2 * kq)));
-            }
-        }
-    } else {
-        // thread 0 owns the self-paired columns t3 = 0 (bins 0, B3, .., 4*B3 = N/2) and t3 = B3/2
-#pragma unroll
-        for (int j = 0; j < 5; j++)
-            Yp[j] = compat_map(split(P[j], P[(8 - j) & 7], PV_LDG(tb.tw2n + B3 * j)), nan_compat);
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            Yq[j] = compat_map(split(Q[j], Q[7 - j], PV_LDG(tb.tw2n + B3 / 2 + B3 * j)), nan_compat);
-        Yp[0].y = 0.f;          // C2R ignores Im of bins 0 and N/2 (cuFFT, kernel.cu:366)
-        Yp[4].y = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float2 wp = (j == 0) ? make_float2(1.f, 0.f) : cconj(PV_LDG(tb.tw2n + 2 * B3 * j));
-            Zp[j] = herm_pack(Yp[j], Yp[4 - j], wp);
-            Zq[j] = herm_pack(Yq[j], Yq[3 - j], cconj(PV_LDG(tb.tw2n + B3 + 2 * B3 * j)));
-        }
     }
+    (void)tb;
+    (void)B3;
     (void)N;
 }
 
@@ -545,15 +516,12 @@ PV_DEV void frame_compat(int tid, const FrameIO &io, const Tables &tb, const Thr
         // Exchange 3 goes to B (other threads may still be reading A in pass 3); exchange 4 goes back to A.
         // The caller puts one barrier at the end of the frame so that the next frame's pass 1 cannot
         // overwrite A while the last inverse pass still reads it.
-        if (TWREG) {
+        {
             // exp(+2 pi i m1 u/(N/2)) = conj(W_N^{2 m1 u}); for t1 = B3-u_q: j^m1 * W_N^{2 m1 u_q}
             const float2 w6 = cmul(tt.w2, tt.w4), q6 = cmul(tt.q2, tt.q4);
             inverse_1_tw<LOG2N>(tid, cconj(tt.w2), cconj(tt.w4), cconj(w6), Zp, bufB);
             inverse_1_tw<LOG2N>(tid == 0 ? S::B3 / 2 : S::B3 - tid, mul_pj(tt.q2), make_float2(-tt.q4.x, -tt.q4.y),
                                 mul_mj(q6), Zq, bufB);
-        } else {
-            inverse_1<LOG2N>(tid, tb, Zp, bufB);
-            inverse_1<LOG2N>(tid == 0 ? S::B3 / 2 : S::B3 - tid, tb, Zq, bufB);
         }
     } else {
         sync();
