@@ -232,8 +232,7 @@ cudaError_t claunch(const PvDev &d, const CTables &tb, const PvProcessArgs &a, c
                         ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
     // 2: 16-byte cp.async.cg pieces (L1 bypass) when rows and hops are 16-byte aligned, 1: 8-byte pieces
     const bool al16 = in_ok && (d.Ha % 4 == 0) && (a.in_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0);
-    static const char *variant = getenv("PV_VARIANT");
-    const int ring = (in_ok && d.Ha <= d.N && !no_ring) ? ((al16 && !(variant && variant[0] == '1')) ? 2 : 1) : 0;
+    const int ring = (in_ok && d.Ha <= d.N && !no_ring) ? (al16 ? 2 : 1) : 0;
     const size_t gb = L::group_bytes(tb.V) - (ring ? 0 : (size_t)d.N * 4);
     const size_t smem = gb * L::G;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -435,11 +434,7 @@ cudaError_t pv_launch_corrected_fused(const PvDev &d, const PvFusedTables &t, co
         case 256: return claunch<8, 4>(d, tb, a, st);
         case 512: return claunch<9, 4>(d, tb, a, st);
         case 1024: return claunch<10, 4>(d, tb, a, st);
-        case 2048: {
-            static const char *variant = getenv("PV_VARIANT");
-            if (variant && variant[0] == 'c') return claunch<11, 5>(d, tb, a, st, true);
-            return claunch<11, 4>(d, tb, a, st);
-        }
+        case 2048: return claunch<11, 4>(d, tb, a, st);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -162,14 +162,11 @@ template <int LOG2N, int MINB>
 cudaError_t launch(const PvDev &d, const Tables &tb, const PvProcessArgs &a, int vec_in_ok, int vec_out_ok,
                    cudaStream_t st)
 {
-    static const char *variant = getenv("PV_VARIANT");      // experiment switch
-    if (variant && variant[0] == '5') return launch2<LOG2N, 5, 0>(d, tb, a, vec_in_ok, vec_out_ok, st);
     // 16-byte cooperative ring needs 16-byte aligned rows and hops
     const bool al16 = vec_in_ok && d.Ha <= d.N && (d.Ha % 4 == 0) && (a.in_stride % 4 == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0);
     // 5 CTAs/SM: with exchange 2 in place a group needs 40.7 KB of shared memory at N = 2048 and 96 registers
-    if (al16 && variant && variant[0] == '4') return launch2<LOG2N, 4, 2>(d, tb, a, vec_in_ok, vec_out_ok, st);
-    if (al16 && !(variant && variant[0] == '1')) return launch2<LOG2N, 5, 2>(d, tb, a, vec_in_ok, vec_out_ok, st);
+    if (al16) return launch2<LOG2N, 5, 2>(d, tb, a, vec_in_ok, vec_out_ok, st);
     if (ring_ok<LOG2N>(d, vec_in_ok != 0)) return launch2<LOG2N, MINB, 1>(d, tb, a, vec_in_ok, vec_out_ok, st);
     return launch2<LOG2N, MINB, 0>(d, tb, a, vec_in_ok, vec_out_ok, st);
 }
