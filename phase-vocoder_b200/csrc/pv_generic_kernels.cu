@@ -24,7 +24,9 @@
 
 namespace {
 
-constexpr int kGenericThreads = 128;
+constexpr int kGenericThreads = 256;      // launch bound; small windows launch 128
+
+inline int generic_threads(int N) { return N >= 2048 ? 256 : 128; }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 {
@@ -523,7 +525,7 @@ cudaError_t pv_launch_aggregate_generic(const PvDev &d, const PvAggArgs &a, cuda
     const size_t smem = sizeof(float2) * 2 * NB + sizeof(uint32_t) * NB;
     cudaError_t e = cudaFuncSetAttribute(aggregate_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    aggregate_generic_kernel<<<(unsigned)a.n_segs, kGenericThreads, smem, st>>>(d, a);
+    aggregate_generic_kernel<<<(unsigned)a.n_segs, generic_threads(d.N), smem, st>>>(d, a);
     return cudaGetLastError();
 }
 
@@ -534,7 +536,7 @@ cudaError_t pv_launch_corrected_generic(const PvDev &d, const PvProcessArgs &a, 
     const size_t smem = std::max(sizeof(float2) * 3 * NB + sizeof(float) * 2 * NB, sizeof(float) * (size_t)d.N);
     cudaError_t e = cudaFuncSetAttribute(corrected_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    corrected_generic_kernel<<<a.n_segs, kGenericThreads, smem, st>>>(d, a);
+    corrected_generic_kernel<<<a.n_segs, generic_threads(d.N), smem, st>>>(d, a);
     return cudaGetLastError();
 }
 
@@ -545,7 +547,7 @@ cudaError_t pv_launch_analysis_batch(const PvDev &d, const float *in, int64_t n_
     const size_t smem = sizeof(float2) * 2 * (size_t)d.N;
     cudaError_t e = cudaFuncSetAttribute(analysis_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    analysis_batch_kernel<<<(unsigned)n_frames, kGenericThreads, smem, st>>>(
+    analysis_batch_kernel<<<(unsigned)n_frames, generic_threads(d.N), smem, st>>>(
         d, in, n_in, reinterpret_cast<float2 *>(out_magphase));
     return cudaGetLastError();
 }
@@ -556,7 +558,7 @@ static cudaError_t launch_resynth(const PvDev &d, const float *spectra, int64_t 
     const size_t smem = sizeof(float2) * (size_t)d.N + sizeof(float) * (size_t)d.N;
     cudaError_t e = cudaFuncSetAttribute(resynthesis_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    resynthesis_batch_kernel<<<1, kGenericThreads, smem, st>>>(d, reinterpret_cast<const float2 *>(spectra), n_frames,
+    resynthesis_batch_kernel<<<1, generic_threads(d.N), smem, st>>>(d, reinterpret_cast<const float2 *>(spectra), n_frames,
                                                              back_in, back_out, out, full);
     return cudaGetLastError();
 }
@@ -587,6 +589,6 @@ cudaError_t pv_launch_compat_generic(const PvDev &d, const PvProcessArgs &a, cud
     const size_t smem = sizeof(float2) * 2 * (size_t)d.N + sizeof(float) * (size_t)d.N;
     cudaError_t e = cudaFuncSetAttribute(compat_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    compat_generic_kernel<<<a.n_segs, kGenericThreads, smem, st>>>(d, a);
+    compat_generic_kernel<<<a.n_segs, generic_threads(d.N), smem, st>>>(d, a);
     return cudaGetLastError();
 }
