@@ -93,9 +93,11 @@ PV_DEV uint32_t phase_turns32(float re, float im)
     r = re < 0.f ? 0.5f - r : r;
     r = im < 0.f ? -r : r;
 #ifdef PV_HOST_EMUL
-    return (uint32_t)(int64_t)llrintf(r * 4294967296.0f);
+    const float v = r * 4294967296.0f;
+    return v >= 2147483648.0f ? 0x7fffffffu : (uint32_t)(int32_t)llrintf(v);
 #else
-    return (uint32_t)__float2ll_rn(r * 4294967296.0f);
+    // 32-bit conversion (saturating): |r| <= 1/2 so only r = +1/2 exactly saturates, one LSB (2^-32 turn) short
+    return (uint32_t)__float2int_rn(r * 4294967296.0f);
 #endif
 }
 
