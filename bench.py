@@ -336,7 +336,27 @@ def run_ours(args):
                "api": "pv_process_host (C ABI, pinned host buffers)"}
         # keep a checksum so that the D2H result is actually consumed
         e2e["checksum"] = float(oh[0, 0, :4096].double().abs().sum())
-        del xh, oh
+        del oh
+        # the same call with 16-bit PCM host buffers (what a WAV file holds): AudioFile's int16<->float rules run
+        # on the device, half the bytes cross PCIe
+        xi = torch.empty((S, n_in), dtype=torch.int16, pin_memory=True)
+        xi.copy_((xh * 32767.0).to(torch.int16))
+        oi = torch.empty((S, V, F * HOP), dtype=torch.int16, pin_memory=True)
+        for _ in range(2):
+            pv.process_host_pcm16(xi, F, out=oi)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            pv.process_host_pcm16(xi, F, out=oi)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e["pcm16"] = {"value": frames_step * n_e2e / float(dt.item()), "unit": "frames/s",
+                        "h2d_bytes_per_step": int(S * n_in * 2 * world), "d2h_bytes_per_step": int(S * V * F * HOP * 2 * world),
+                        "api": "pv_process_host_pcm16 (16-bit PCM host buffers, AudioFile conversions on the device)",
+                        "checksum": float(oi[0, 0, :4096].double().abs().sum())}
+        del xh, xi, oi
 
     # ---- the other mode, device-resident only (reported next to the headline, same workload) ----
     other = None

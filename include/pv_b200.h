@@ -144,7 +144,8 @@ size_t pv_state_bytes(const pv_handle *h);
  *   out         [stream][voice][n_frames*Hs]: out + s*out_stream_stride + v*out_voice_stride
  *   state       NULL, or n_streams * pv_state_bytes(h) bytes: read as the carry-in when
  *               (flags & PV_PROCESS_CARRY_IN), written as the carry-out when
- *               (flags & PV_PROCESS_CARRY_OUT).
+ *               (flags & PV_PROCESS_CARRY_OUT).  An all-zero state is a fresh start, so a block-by-block
+ *               caller may zero it once and pass both flags on every call.
  * Long streams are split into frame-range segments processed concurrently (the (N-Hs) OLA
  * halo is recomputed, so the result does not depend on the split).                            */
 enum { PV_PROCESS_CARRY_IN = 1, PV_PROCESS_CARRY_OUT = 2 };
@@ -188,6 +189,14 @@ int pv_process_host(pv_handle *h, const float *in, int64_t n_streams, int64_t in
                     int64_t n_in, int64_t n_analysed, int64_t n_frames, float *out,
                     int64_t out_stream_stride, int64_t out_voice_stride, void *state,
                     int32_t flags);
+
+/* Same with 16-bit PCM host buffers: the sample conversions of the reference's AudioFile<float> -- s/32768 on
+ * load (src/AudioFile.h:1038-1042) and (int16) trunc(clamp(x,-1,1)*32767) on save (:1045-1049) -- run on the
+ * device, so a WAV file's samples cross PCIe as they are stored (half the bytes of the float call).         */
+int pv_process_host_pcm16(pv_handle *h, const int16_t *in, int64_t n_streams, int64_t in_stride,
+                          int64_t n_in, int64_t n_analysed, int64_t n_frames, int16_t *out,
+                          int64_t out_stream_stride, int64_t out_voice_stride, void *state,
+                          int32_t flags);
 
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t pv_launch_count(const pv_handle *h);

@@ -36,33 +36,39 @@ struct pv_handle {
     PvFusedTables ft;
     float2 *d_ft[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // segment plan cache
-    std::vector<PvSegment> h_segs;
     // split of corrected streams into frame-range parts (intra-GPU phase-carry scan)
-    PvSegment *d_agg_segs = nullptr, *d_api_segs = nullptr;
-    size_t agg_cap = 0, api_cap = 0;
-    int32_t split_parts = 0;
-    int64_t split_streams = -1, split_frames = -1;
-    int split_carry = -1;
-    int64_t split_skip = -1;
+    PvSegment *d_api_segs = nullptr;
+    size_t api_cap = 0;
     uint32_t *d_Pl = nullptr;
     int64_t *d_S = nullptr, *d_H = nullptr;
     uint32_t *d_Pf = nullptr;
     size_t carry_cap = 0;
     unsigned char *d_slots = nullptr;
     size_t slots_cap = 0;
-    PvSegment *d_segs = nullptr;
-    size_t segs_cap = 0;
-    int32_t n_segs = 0;
-    int64_t plan_streams = -1, plan_frames = -1, plan_skip = -1;
-    int32_t plan_flags = -1;
+    // Segment tables, cached by shape.  Every entry owns its device tables, so a plan that queued launches
+    // still read is never overwritten by the next shape (the pipelined host path alternates between plans).
+    struct Plan {
+        int kind = -1;                 // -1 free, 0 plan_segments, 1 corrected split
+        int64_t n_streams = 0, n_frames = 0, skip = 0;
+        int32_t flags = 0, parts = 0;
+        PvSegment *d_segs = nullptr, *d_agg_segs = nullptr;
+        size_t cap = 0, agg_cap = 0;
+        int32_t n_segs = 0;
+        uint64_t stamp = 0;
+    };
+    Plan plans[8];
+    uint64_t plan_clock = 0;
     // staging for the host-pointer entry point
     float *d_in = nullptr, *d_out = nullptr;
     size_t in_cap = 0, out_cap = 0;
+    float *d_in16 = nullptr, *d_out16 = nullptr;      // 16-bit PCM staging (sized in floats)
+    size_t in16_cap = 0, out16_cap = 0;
     void *d_state = nullptr;
     size_t state_cap = 0;
     void *d_scratch_state = nullptr;
     size_t scratch_cap = 0;
-    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};        // host path: H2D, kernels, D2H
+    std::vector<cudaEvent_t> pipe_events;
     // accounting
     int64_t launches = 0;
     bool timing = false;
@@ -154,13 +160,56 @@ void corrected_tables(int N, int Ha, int Hs, double beta, uint64_t *Rq, int32_t 
         nomS[s] = (a_lo[s] > a_hi[s]) ? 0 : ((bq * (uint64_t)a_hi[s] * (uint64_t)Hs) << (32 - lg));
 }
 
+// Looks a plan up by shape; on a miss hands out the least recently used entry (after the device has
+// drained, so that no queued launch still reads the tables about to be rewritten).
+pv_handle::Plan *find_plan(pv_handle *h, int kind, int64_t n_streams, int64_t n_frames, int64_t skip, int32_t flags,
+                           int32_t parts, bool *hit)
+{
+    pv_handle::Plan *lru = &h->plans[0];
+    for (auto &pl : h->plans) {
+        if (pl.kind == kind && pl.n_streams == n_streams && pl.n_frames == n_frames && pl.skip == skip &&
+            pl.flags == flags && pl.parts == parts) {
+            pl.stamp = ++h->plan_clock;
+            *hit = true;
+            return &pl;
+        }
+        if (pl.stamp < lru->stamp) lru = &pl;
+    }
+    if (lru->kind >= 0) cudaDeviceSynchronize();
+    lru->kind = -1;                  // valid only once the caller has filled it
+    lru->n_streams = n_streams;
+    lru->n_frames = n_frames;
+    lru->skip = skip;
+    lru->flags = flags;
+    lru->parts = parts;
+    lru->stamp = ++h->plan_clock;
+    *hit = false;
+    return lru;
+}
+
+int upload_segments(PvSegment **d, size_t *cap, const std::vector<PvSegment> &segs)
+{
+    if (segs.size() > *cap) {
+        cudaFree(*d);
+        *d = nullptr;
+        *cap = 0;
+        PV_CUDA(cudaMalloc((void **)d, sizeof(PvSegment) * segs.size()));
+        *cap = segs.size();
+    }
+    // One blocking upload per new shape; every later launch of the same shape (any stream) reuses it.
+    PV_CUDA(cudaMemcpy(*d, segs.data(), sizeof(PvSegment) * segs.size(), cudaMemcpyHostToDevice));
+    return PV_OK;
+}
+
 // Splits every stream into frame-range segments so that the grid fills the machine.
 // The (R-1)-frame OLA halo in front of each segment is recomputed (compat frames are
 // independent), so the output does not depend on the split.
-int plan_segments(pv_handle *h, int64_t n_streams, int64_t n_frames, int64_t skip, int32_t flags, cudaStream_t st)
+int plan_segments(pv_handle *h, int64_t n_streams, int64_t n_frames, int64_t skip, int32_t flags, pv_handle::Plan **out)
 {
-    if (h->plan_streams == n_streams && h->plan_frames == n_frames && h->plan_flags == flags && h->plan_skip == skip)
-        return PV_OK;
+    bool hit = false;
+    pv_handle::Plan *pl = find_plan(h, 0, n_streams, n_frames, skip, flags, 0, &hit);
+    *out = pl;
+    if (hit) return PV_OK;
     const int N = h->p.window, Hs = h->p.hop_out;
     const int64_t halo = (N - 1) / Hs;                     // frames k' < k that still overlap frame k
     // aim at ~8 waves of resident groups so that the tail wave is small, but keep the halo
@@ -174,8 +223,7 @@ int plan_segments(pv_handle *h, int64_t n_streams, int64_t n_frames, int64_t ski
     int64_t seg_len = (n_frames + per_stream - 1) / per_stream;
     const int64_t min_len = std::max<int64_t>(32 * halo, 32);
     if (seg_len < min_len) seg_len = min_len;
-    std::vector<PvSegment> &segs = h->h_segs;       // kept alive in the handle: the upload is asynchronous
-    segs.clear();
+    std::vector<PvSegment> segs;
     for (int64_t s = 0; s < n_streams; s++) {
         for (int64_t k0 = skip; k0 < n_frames; k0 += seg_len) {
             PvSegment g{};
@@ -190,21 +238,10 @@ int plan_segments(pv_handle *h, int64_t n_streams, int64_t n_frames, int64_t ski
             segs.push_back(g);
         }
     }
-    if (segs.size() > h->segs_cap) {
-        if (h->d_segs) cudaFree(h->d_segs);
-        h->d_segs = nullptr;
-        PV_CUDA(cudaMalloc((void **)&h->d_segs, sizeof(PvSegment) * segs.size()));
-        h->segs_cap = segs.size();
-    }
-    // One blocking upload per new shape; every later launch of the same shape (any stream) reuses it.
-    (void)st;
-    PV_CUDA(cudaMemcpy(h->d_segs, segs.data(), sizeof(PvSegment) * segs.size(), cudaMemcpyHostToDevice));
-    h->n_segs = (int32_t)segs.size();
-    h->split_streams = -1;           // d_segs now holds this plan, not a corrected split
-    h->plan_streams = n_streams;
-    h->plan_frames = n_frames;
-    h->plan_skip = skip;
-    h->plan_flags = flags;
+    int rc = upload_segments(&pl->d_segs, &pl->cap, segs);
+    if (rc != PV_OK) return rc;
+    pl->n_segs = (int32_t)segs.size();
+    pl->kind = 0;
     return PV_OK;
 }
 
@@ -212,11 +249,12 @@ int plan_segments(pv_handle *h, int64_t n_streams, int64_t n_frames, int64_t ski
 // machine.  Two tables (index = stream*parts + part): the analysis ranges for the phase-carry aggregate
 // and the processing ranges (halo + owned frames) that start from the rebuilt state of each part.
 int plan_corrected_split(pv_handle *h, int64_t n_streams, int64_t n_frames, int32_t parts, bool user_carry,
-                         int64_t skip = 0)
+                         int64_t skip, pv_handle::Plan **out)
 {
-    if (h->split_streams == n_streams && h->split_frames == n_frames && h->split_parts == parts &&
-        h->split_carry == (int)user_carry && h->split_skip == skip)
-        return PV_OK;
+    bool hit = false;
+    pv_handle::Plan *pl = find_plan(h, 1, n_streams, n_frames, skip, user_carry ? 1 : 0, parts, &hit);
+    *out = pl;
+    if (hit) return PV_OK;
     const int N = h->p.window, Hs = h->p.hop_out;
     const int64_t halo = (N - 1) / Hs;
     const int64_t L = (n_frames + parts - 1) / parts;
@@ -242,24 +280,12 @@ int plan_corrected_split(pv_handle *h, int64_t n_streams, int64_t n_frames, int3
             proc[i] = q;
         }
     const size_t n = agg.size();
-    if (n > h->agg_cap) {
-        cudaFree(h->d_agg_segs);
-        h->d_agg_segs = nullptr;
-        h->agg_cap = 0;
-        PV_CUDA(cudaMalloc((void **)&h->d_agg_segs, sizeof(PvSegment) * n));
-        h->agg_cap = n;
-    }
-    if (n > h->segs_cap) {
-        cudaFree(h->d_segs);
-        h->d_segs = nullptr;
-        h->segs_cap = 0;
-        PV_CUDA(cudaMalloc((void **)&h->d_segs, sizeof(PvSegment) * n));
-        h->segs_cap = n;
-    }
-    PV_CUDA(cudaMemcpy(h->d_agg_segs, agg.data(), sizeof(PvSegment) * n, cudaMemcpyHostToDevice));
-    PV_CUDA(cudaMemcpy(h->d_segs, proc.data(), sizeof(PvSegment) * n, cudaMemcpyHostToDevice));
+    int rc = upload_segments(&pl->d_agg_segs, &pl->agg_cap, agg);
+    if (rc == PV_OK) rc = upload_segments(&pl->d_segs, &pl->cap, proc);
+    if (rc != PV_OK) return rc;
     const size_t nb = (size_t)N / 2 + 1;
     if (n * nb > h->carry_cap) {
+        cudaDeviceSynchronize();
         cudaFree(h->d_S); cudaFree(h->d_H); cudaFree(h->d_Pf); cudaFree(h->d_Pl);
         h->d_S = h->d_H = nullptr; h->d_Pf = h->d_Pl = nullptr; h->carry_cap = 0;
         PV_CUDA(cudaMalloc((void **)&h->d_S, sizeof(int64_t) * n * nb));
@@ -270,19 +296,15 @@ int plan_corrected_split(pv_handle *h, int64_t n_streams, int64_t n_frames, int3
     }
     const size_t sb = pv_state_bytes(h);
     if (n * sb > h->slots_cap) {
+        cudaDeviceSynchronize();
         cudaFree(h->d_slots);
         h->d_slots = nullptr;
         h->slots_cap = 0;
         PV_CUDA(cudaMalloc((void **)&h->d_slots, n * sb));
         h->slots_cap = n * sb;
     }
-    h->split_streams = n_streams;
-    h->split_frames = n_frames;
-    h->split_parts = parts;
-    h->split_carry = (int)user_carry;
-    h->split_skip = skip;
-    h->n_segs = (int32_t)n;
-    h->plan_streams = -1;            // the shared d_segs table no longer holds a plan_segments() plan
+    pl->n_segs = (int32_t)n;
+    pl->kind = 1;
     return PV_OK;
 }
 
@@ -446,14 +468,19 @@ void pv_destroy(pv_handle *h)
     cudaFree(h->d_nomS);
     cudaFree(h->d_gather);
     for (auto p : h->d_ft) cudaFree(p);
-    cudaFree(h->d_segs);
-    cudaFree(h->d_agg_segs);
+    for (auto &pl : h->plans) {
+        cudaFree(pl.d_segs);
+        cudaFree(pl.d_agg_segs);
+    }
+    for (auto e : h->pipe_events) cudaEventDestroy(e);
     cudaFree(h->d_api_segs);
     cudaFree(h->d_S);
     cudaFree(h->d_H);
     cudaFree(h->d_Pf);
     cudaFree(h->d_Pl);
     cudaFree(h->d_slots);
+    cudaFree(h->d_in16);
+    cudaFree(h->d_out16);
     cudaFree(h->d_in);
     cudaFree(h->d_out);
     cudaFree(h->d_state);
@@ -581,10 +608,11 @@ int pv_corrected_aggregate(pv_handle *h, const float *in, int64_t n_streams, int
     {   // few long streams: aggregate frame-range parts concurrently, then add the per-part sums
         const int64_t parts = corrected_parts(h, n_streams, n_frames);
         if (parts >= 2) {
-            int rc0 = plan_corrected_split(h, n_streams, n_frames, (int32_t)parts, false);
+            pv_handle::Plan *pl = nullptr;
+            int rc0 = plan_corrected_split(h, n_streams, n_frames, (int32_t)parts, false, 0, &pl);
             if (rc0 != PV_OK) return rc0;
             const int nb = h->p.window / 2 + 1;
-            PvAggArgs ag{in, in_stride, n_in, h->d_agg_segs, h->n_segs, P_prev, (int64_t)nb, h->d_S, nullptr, h->d_Pf, h->d_Pl};
+            PvAggArgs ag{in, in_stride, n_in, pl->d_agg_segs, pl->n_segs, P_prev, (int64_t)nb, h->d_S, nullptr, h->d_Pf, h->d_Pl, 0};
             if (h->fused && !getenv("PV_FORCE_GENERIC")) PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, ag, (cudaStream_t)cuda_stream));
             else PV_CUDA(pv_launch_aggregate_generic(h->dev, ag, (cudaStream_t)cuda_stream));
             PV_CUDA(pv_launch_reduce_parts(nb, n_streams, (int32_t)parts, h->d_S, h->d_Pf, h->d_Pl, sumD, P_first, P_last,
@@ -612,7 +640,7 @@ int pv_corrected_aggregate(pv_handle *h, const float *in, int64_t n_streams, int
         h->api_cap = segs.size();
     }
     PV_CUDA(cudaMemcpy(h->d_api_segs, segs.data(), sizeof(PvSegment) * segs.size(), cudaMemcpyHostToDevice));
-    PvAggArgs a{in, in_stride, n_in, h->d_api_segs, (int32_t)n_streams, P_prev, (int64_t)(h->p.window / 2 + 1), sumD, nullptr, P_first, P_last};
+    PvAggArgs a{in, in_stride, n_in, h->d_api_segs, (int32_t)n_streams, P_prev, (int64_t)(h->p.window / 2 + 1), sumD, nullptr, P_first, P_last, 0};
     if (h->fused && !getenv("PV_FORCE_GENERIC")) PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, a, (cudaStream_t)cuda_stream));
     else PV_CUDA(pv_launch_aggregate_generic(h->dev, a, (cudaStream_t)cuda_stream));
     h->launches++;
@@ -673,16 +701,17 @@ static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_
         const bool user_carry = (flags & PV_PROCESS_CARRY_IN) != 0;
         const int64_t parts = corrected_parts(h, n_streams, n_frames);
         if (parts >= 2) {
-            int rc0 = plan_corrected_split(h, n_streams, n_frames, (int32_t)parts, user_carry, skip_frames);
+            pv_handle::Plan *pl = nullptr;
+            int rc0 = plan_corrected_split(h, n_streams, n_frames, (int32_t)parts, user_carry, skip_frames, &pl);
             if (rc0 != PV_OK) return rc0;
             const bool fused_ok = h->fused && !force_generic0;
             const int64_t sb = (int64_t)pv_state_bytes(h);
-            PvAggArgs ag{in, in_stride, n_in, h->d_agg_segs, h->n_segs,
+            PvAggArgs ag{in, in_stride, n_in, pl->d_agg_segs, pl->n_segs,
                          user_carry ? reinterpret_cast<const uint32_t *>((const unsigned char *)state + 8) : nullptr, sb / 4,
-                         h->d_S, h->d_H, h->d_Pf, nullptr};
+                         h->d_S, h->d_H, h->d_Pf, nullptr, 1};
             if (fused_ok) PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, ag, st));
             else PV_CUDA(pv_launch_aggregate_generic(h->dev, ag, st));
-            PV_CUDA(pv_launch_split_states(h->dev, n_streams, (int32_t)parts, h->d_segs, h->d_S, h->d_H, h->d_Pf,
+            PV_CUDA(pv_launch_split_states(h->dev, n_streams, (int32_t)parts, pl->d_segs, h->d_S, h->d_H, h->d_Pf,
                                            h->d_slots, sb, user_carry ? (const unsigned char *)state : nullptr, st));
             PvProcessArgs a{};
             a.in = in;
@@ -695,8 +724,8 @@ static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_
             a.out_voice_stride = out_voice_stride;
             a.state = h->d_slots;
             a.state_stride = sb;
-            a.segs = h->d_segs;
-            a.n_segs = h->n_segs;
+            a.segs = pl->d_segs;
+            a.n_segs = pl->n_segs;
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (h->timing) {
                 PV_CUDA(cudaEventCreate(&e0));
@@ -720,7 +749,8 @@ static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_
             return PV_OK;
         }
     }
-    int rc = plan_segments(h, plan_streams, n_frames, skip_frames, flags, st);
+    pv_handle::Plan *pl = nullptr;
+    int rc = plan_segments(h, plan_streams, n_frames, skip_frames, flags, &pl);
     if (rc != PV_OK) return rc;
     PvProcessArgs a{};
     a.in = in;
@@ -733,8 +763,8 @@ static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_
     a.out_voice_stride = out_voice_stride;
     a.state = (unsigned char *)state;
     a.state_stride = (int64_t)pv_state_bytes(h);
-    a.segs = h->d_segs;
-    a.n_segs = (int32_t)((int64_t)h->n_segs / plan_streams * n_streams);      // stream-major table
+    a.segs = pl->d_segs;
+    a.n_segs = (int32_t)((int64_t)pl->n_segs / plan_streams * n_streams);      // stream-major table
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->timing) {
         PV_CUDA(cudaEventCreate(&e0));
@@ -767,63 +797,138 @@ static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_
     return PV_OK;
 }
 
-int pv_process_host(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride, int64_t n_in,
-                    int64_t n_analysed, int64_t n_frames, float *out, int64_t out_stream_stride,
-                    int64_t out_voice_stride, void *state, int32_t flags)
+}  // extern "C"
+
+// Shared body of the host entry points.  PCM16: the host buffers hold 16-bit PCM and the conversions of the
+// reference's AudioFile (s/32768 in, trunc(clamp(x,-1,1)*32767) out; src/AudioFile.h:1038-1049) run on the
+// device, which halves the bytes crossing PCIe in both directions.
+template <bool PCM16>
+static int process_host_impl(pv_handle *h, const void *in_v, int64_t n_streams, int64_t in_stride, int64_t n_in,
+                             int64_t n_analysed, int64_t n_frames, void *out_v, int64_t out_stream_stride,
+                             int64_t out_voice_stride, void *state, int32_t flags)
 {
-    if (!h || !in || !out) return fail(PV_ERR_PARAM, "pv_process_host: null argument");
+    if (!h || !in_v || !out_v) return fail(PV_ERR_PARAM, "pv_process_host: null argument");
     if (n_streams <= 0 || n_frames <= 0) return PV_OK;
     if ((flags & (PV_PROCESS_CARRY_IN | PV_PROCESS_CARRY_OUT)) && !state)
         return fail(PV_ERR_PARAM, "pv_process_host: carry requested without a state buffer");
     DeviceGuard guard(h->device);
     const int64_t V = h->p.n_voices, n_out = n_frames * h->p.hop_out;
-    int rc = ensure(&h->d_in, &h->in_cap, (size_t)(n_streams * n_in));
+    const size_t esz = PCM16 ? 2 : 4;
+    // device rows are padded to 4 samples so that the kernels keep their 16-byte aligned fast paths
+    const int64_t n_in_p = (n_in + 3) & ~int64_t(3);
+    int rc = ensure(&h->d_in, &h->in_cap, (size_t)(n_streams * n_in_p));
     if (rc == PV_OK) rc = ensure(&h->d_out, &h->out_cap, (size_t)(n_streams * V * n_out));
+    if (rc == PV_OK && PCM16) rc = ensure(&h->d_in16, &h->in16_cap, (size_t)(n_streams * n_in_p) / 2);
+    if (rc == PV_OK && PCM16) rc = ensure(&h->d_out16, &h->out16_cap, (size_t)(n_streams * V * n_out + 1) / 2);
     if (rc != PV_OK) return rc;
+    for (auto &ps : h->pipe)
+        if (!ps) PV_CUDA(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+    cudaStream_t s_in = h->pipe[0], s_k = h->pipe[1], s_out = h->pipe[2];
+    // Software pipeline over chunks of FRAMES (all streams each): the H2D copy of chunk c+1, the kernels of
+    // chunk c and the D2H copy of chunk c-1 overlap (PCIe is full duplex), so a large batch costs about
+    // max(H2D, D2H, kernel) instead of their sum.  Every chunk keeps the whole batch's parallelism, and the
+    // per-stream state (phase accumulators + overlap-add tail) is carried from chunk to chunk on the device,
+    // which is the same carry a caller streaming block by block uses -- the result is bit-identical to one
+    // unchunked call.  Pinned host buffers are needed for real overlap.
+    const int N = h->p.window, Ha = h->p.hop_in, Hs = h->p.hop_out;
+    const int64_t bytes_in = n_streams * n_in * (int64_t)esz;
+    int64_t n_chunks = std::min<int64_t>(32, std::max<int64_t>(1, bytes_in / (32ll << 20)));
+    if (const char *e = getenv("PV_HOST_CHUNKS")) n_chunks = std::max(1, atoi(e));      // test / tuning knob
+    const int64_t min_fc = std::max<int64_t>(8, 4 * ((N + Ha - 1) / Ha));
+    int64_t fc = std::max(min_fc, (n_frames + n_chunks - 1) / n_chunks);
+    n_chunks = (n_frames + fc - 1) / fc;
+    const bool use_state = n_chunks > 1 || state != nullptr;
     const size_t sb = pv_state_bytes(h);
-    // the shape-generic corrected kernel works in a per-stream state buffer: give every chunk its own slice
-    const bool dev_state = state != nullptr || (h->p.mode == PV_MODE_CORRECTED && (!h->fused || getenv("PV_FORCE_GENERIC")));
-    if (dev_state && (size_t)n_streams * sb > h->state_cap) {
+    if (use_state && (size_t)n_streams * sb > h->state_cap) {
         cudaFree(h->d_state);
         h->d_state = nullptr;
         h->state_cap = 0;
         PV_CUDA(cudaMalloc(&h->d_state, (size_t)n_streams * sb));
         h->state_cap = (size_t)n_streams * sb;
     }
-    for (auto &ps : h->pipe)
-        if (!ps) PV_CUDA(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
-    // Software pipeline over chunks of streams on three CUDA streams: the H2D copy of chunk c+1, the kernel
-    // of chunk c and the D2H copy of chunk c-1 overlap (PCIe is full duplex), so a large batch costs about
-    // max(H2D, D2H, kernel) instead of their sum.  Pinned host buffers are needed for real overlap.
-    const int64_t bytes_in = n_streams * n_in * 4;
-    int64_t n_chunks = std::min<int64_t>(16, std::max<int64_t>(1, bytes_in / (64ll << 20)));
-    n_chunks = std::min(n_chunks, n_streams);
-    const int64_t cs = (n_streams + n_chunks - 1) / n_chunks;
-    int c = 0;
-    for (int64_t s0 = 0; s0 < n_streams; s0 += cs, ++c) {
-        const int64_t ns = std::min(cs, n_streams - s0);
-        cudaStream_t st = h->pipe[c % 3];
-        float *di = h->d_in + s0 * n_in, *dout = h->d_out + s0 * V * n_out;
-        unsigned char *dst = dev_state ? (unsigned char *)h->d_state + s0 * sb : nullptr;
-        unsigned char *hst = state ? (unsigned char *)state + s0 * sb : nullptr;
-        if (state && (flags & PV_PROCESS_CARRY_IN))
-            PV_CUDA(cudaMemcpyAsync(dst, hst, (size_t)ns * sb, cudaMemcpyHostToDevice, st));
-        PV_CUDA(cudaMemcpy2DAsync(di, sizeof(float) * n_in, in + s0 * in_stride, sizeof(float) * in_stride,
-                                  sizeof(float) * n_in, (size_t)ns, cudaMemcpyHostToDevice, st));
-        rc = process_impl(h, di, ns, cs, n_in, n_in, n_analysed, n_frames, 0, dout, V * n_out, n_out, dst, flags, st);
-        if (rc != PV_OK) break;
-        for (int64_t v = 0; v < V; v++)
-            PV_CUDA(cudaMemcpy2DAsync(out + s0 * out_stream_stride + v * out_voice_stride, sizeof(float) * out_stream_stride,
-                                      dout + v * n_out, sizeof(float) * V * n_out, sizeof(float) * n_out, (size_t)ns,
-                                      cudaMemcpyDeviceToHost, st));
-        if (state && (flags & PV_PROCESS_CARRY_OUT))
-            PV_CUDA(cudaMemcpyAsync(hst, dst, (size_t)ns * sb, cudaMemcpyDeviceToHost, st));
+    while ((int64_t)h->pipe_events.size() < 2 * n_chunks) {
+        cudaEvent_t e = nullptr;
+        PV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->pipe_events.push_back(e);
     }
+    int32_t cflags = 0;
+    if (use_state) {
+        if (flags & PV_PROCESS_CARRY_IN)
+            PV_CUDA(cudaMemcpyAsync(h->d_state, state, (size_t)n_streams * sb, cudaMemcpyHostToDevice, s_k));
+        else if (n_chunks > 1)          // an all-zero state is a fresh start
+            PV_CUDA(cudaMemsetAsync(h->d_state, 0, (size_t)n_streams * sb, s_k));
+        cflags = n_chunks > 1 ? (PV_PROCESS_CARRY_IN | PV_PROCESS_CARRY_OUT) : flags;
+    }
+    const unsigned char *in = (const unsigned char *)in_v;
+    unsigned char *out = (unsigned char *)out_v;
+    int16_t *d16 = reinterpret_cast<int16_t *>(h->d_in16), *o16 = reinterpret_cast<int16_t *>(h->d_out16);
+    int64_t e0 = 0;                                       // input samples already on the device
+    for (int64_t c = 0; c < n_chunks && rc == PV_OK; ++c) {
+        const int64_t k0 = c * fc, k1 = std::min(n_frames, k0 + fc);
+        const int64_t e1 = std::max(e0, std::min(n_in, (k1 - 1) * Ha + N));
+        cudaEvent_t ev_in = h->pipe_events[(size_t)(2 * c)], ev_k = h->pipe_events[(size_t)(2 * c + 1)];
+        if (e1 > e0) {
+            if (PCM16)
+                PV_CUDA(cudaMemcpy2DAsync(d16 + e0, 2 * n_in_p, in + (size_t)e0 * 2, 2 * in_stride, 2 * (size_t)(e1 - e0),
+                                          (size_t)n_streams, cudaMemcpyHostToDevice, s_in));
+            else
+                PV_CUDA(cudaMemcpy2DAsync(h->d_in + e0, 4 * n_in_p, in + (size_t)e0 * 4, 4 * in_stride, 4 * (size_t)(e1 - e0),
+                                          (size_t)n_streams, cudaMemcpyHostToDevice, s_in));
+        }
+        PV_CUDA(cudaEventRecord(ev_in, s_in));
+        PV_CUDA(cudaStreamWaitEvent(s_k, ev_in, 0));
+        if (PCM16 && e1 > e0) {
+            PV_CUDA(pv_launch_pcm16_to_float(d16, h->d_in, n_streams, n_in_p, e0 & ~int64_t(3), e1, n_in, s_k));
+            h->launches++;
+        }
+        e0 = e1;
+        const int64_t an = std::min(k1 - k0, std::max<int64_t>(0, n_analysed - k0));
+        rc = process_impl(h, h->d_in + k0 * Ha, n_streams, n_streams, n_in_p, std::max<int64_t>(0, n_in - k0 * Ha), an, k1 - k0, 0,
+                          h->d_out + k0 * Hs, V * n_out, n_out, use_state ? h->d_state : nullptr, cflags, s_k);
+        if (rc != PV_OK) break;
+        if (PCM16) {
+            PV_CUDA(pv_launch_float_to_pcm16(h->d_out, o16, n_streams * V, n_out, k0 * Hs, k1 * Hs, s_k));
+            h->launches++;
+        }
+        PV_CUDA(cudaEventRecord(ev_k, s_k));
+        PV_CUDA(cudaStreamWaitEvent(s_out, ev_k, 0));
+        const size_t w = (size_t)(k1 - k0) * Hs;
+        for (int64_t v = 0; v < V; v++) {
+            if (PCM16)
+                PV_CUDA(cudaMemcpy2DAsync(out + ((size_t)v * out_voice_stride + (size_t)k0 * Hs) * 2, 2 * out_stream_stride,
+                                          o16 + v * n_out + k0 * Hs, 2 * V * n_out, 2 * w, (size_t)n_streams,
+                                          cudaMemcpyDeviceToHost, s_out));
+            else
+                PV_CUDA(cudaMemcpy2DAsync(out + ((size_t)v * out_voice_stride + (size_t)k0 * Hs) * 4, 4 * out_stream_stride,
+                                          h->d_out + v * n_out + k0 * Hs, 4 * V * n_out, 4 * w, (size_t)n_streams,
+                                          cudaMemcpyDeviceToHost, s_out));
+        }
+    }
+    if (rc == PV_OK && use_state && (flags & PV_PROCESS_CARRY_OUT))
+        PV_CUDA(cudaMemcpyAsync(state, h->d_state, (size_t)n_streams * sb, cudaMemcpyDeviceToHost, s_k));
     for (auto &ps : h->pipe) {
         cudaError_t e = cudaStreamSynchronize(ps);
         if (e != cudaSuccess && rc == PV_OK) rc = fail(PV_ERR_CUDA, "pipeline stream: %s", cudaGetErrorString(e));
     }
     return rc;
+}
+
+extern "C" {
+
+int pv_process_host(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride, int64_t n_in,
+                    int64_t n_analysed, int64_t n_frames, float *out, int64_t out_stream_stride,
+                    int64_t out_voice_stride, void *state, int32_t flags)
+{
+    return process_host_impl<false>(h, in, n_streams, in_stride, n_in, n_analysed, n_frames, out, out_stream_stride,
+                                    out_voice_stride, state, flags);
+}
+
+int pv_process_host_pcm16(pv_handle *h, const int16_t *in, int64_t n_streams, int64_t in_stride, int64_t n_in,
+                          int64_t n_analysed, int64_t n_frames, int16_t *out, int64_t out_stream_stride,
+                          int64_t out_voice_stride, void *state, int32_t flags)
+{
+    return process_host_impl<true>(h, in, n_streams, in_stride, n_in, n_analysed, n_frames, out, out_stream_stride,
+                                   out_voice_stride, state, flags);
 }
 
 int64_t pv_launch_count(const pv_handle *h) { return h ? h->launches : 0; }

@@ -93,11 +93,10 @@ PV_DEV uint32_t phase_turns32(float re, float im)
     r = re < 0.f ? 0.5f - r : r;
     r = im < 0.f ? -r : r;
 #ifdef PV_HOST_EMUL
-    const float v = r * 4294967296.0f;
-    return v >= 2147483648.0f ? 0x7fffffffu : (uint32_t)(int32_t)llrintf(v);
+    return (uint32_t)(int64_t)llrintf(r * 4294967296.0f);
 #else
-    // 32-bit conversion (saturating): |r| <= 1/2 so only r = +1/2 exactly saturates, one LSB (2^-32 turn) short
-    return (uint32_t)__float2int_rn(r * 4294967296.0f);
+    // 64-bit conversion on purpose: r*2^32 reaches +-2^31 (r = +-1/2 turn), outside the int32 range
+    return (uint32_t)__float2ll_rn(r * 4294967296.0f);
 #endif
 }
 

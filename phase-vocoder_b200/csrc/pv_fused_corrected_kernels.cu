@@ -106,7 +106,8 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
             if (sl < 8 || tid == 0) st.Pprev[sl] = st_P[slot_bin<B3>(tid, sl)];
     }
     if (agg_mode) {
-        const bool carried = seg.carry_in && ag.P_prev != nullptr;
+        const bool carried = seg.carry_in && ag.P_prev != nullptr &&
+                             (!ag.P_prev_in_state || ag.P_prev[(long long)seg.stream * ag.P_prev_stride - 2] != 0u);
         st.have_prev = carried;
 #pragma unroll
         for (int sl = 0; sl < 9; sl++) {

@@ -464,7 +464,8 @@ aggregate_generic_kernel(PvDev d, PvAggArgs a)
     const long long sg = blockIdx.x;
     const PvSegment seg = a.segs[sg];
     const float *in = a.in + seg.stream * a.in_stride;
-    const bool carried = seg.carry_in && a.P_prev != nullptr;
+    const bool carried = seg.carry_in && a.P_prev != nullptr &&
+                         (!a.P_prev_in_state || a.P_prev[(long long)seg.stream * a.P_prev_stride - 2] != 0u);
     bool have_prev = carried;
     for (int b = threadIdx.x; b < NB; b += blockDim.x) {
         Pp[b] = carried ? a.P_prev[(long long)seg.stream * a.P_prev_stride + b] : 0u;
@@ -526,6 +527,75 @@ cudaError_t pv_launch_aggregate_generic(const PvDev &d, const PvAggArgs &a, cuda
     cudaError_t e = cudaFuncSetAttribute(aggregate_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     aggregate_generic_kernel<<<(unsigned)a.n_segs, generic_threads(d.N), smem, st>>>(d, a);
+    return cudaGetLastError();
+}
+
+// ---- 16-bit PCM conversions (AudioFile rules) on a column range of a row-major batch, 4 samples per thread ----
+__global__ void pcm16_to_float_kernel(const int16_t *__restrict__ in, float *__restrict__ out, long long pitch,
+                                      long long c0, long long c1, long long n_valid)
+{
+    const long long r = blockIdx.y;
+    const long long c = c0 + 4 * (blockIdx.x * (long long)blockDim.x + threadIdx.x);   // c0 and pitch: multiples of 4
+    if (c >= c1) return;
+    const int16_t *src = in + r * pitch + c;
+    float4 v;                                                    // sixteenBitIntToSample, AudioFile.h:1038-1042
+    v.x = c + 0 < n_valid ? (float)src[0] / 32768.0f : 0.f;
+    v.y = c + 1 < n_valid ? (float)src[1] / 32768.0f : 0.f;
+    v.z = c + 2 < n_valid ? (float)src[2] / 32768.0f : 0.f;
+    v.w = c + 3 < n_valid ? (float)src[3] / 32768.0f : 0.f;
+    *reinterpret_cast<float4 *>(out + r * pitch + c) = v;
+}
+
+__device__ __forceinline__ int16_t to_pcm16(float x)
+{
+    x = fminf(x, 1.0f);                                          // clamp: NaN -> 1 like std::min(value, max)
+    x = fmaxf(x, -1.0f);
+    // sampleToSixteenBitInt, AudioFile.h:1045-1049: trunc((double)x * 32767.0).  |x*32767| < 2^15 and a float
+    // holds 24 bits, so rounding the product toward zero keeps its integer part: same result without FP64.
+    return (int16_t)(int)__fmul_rz(x, 32767.0f);
+}
+
+__global__ void float_to_pcm16_kernel(const float *__restrict__ in, int16_t *__restrict__ out, long long pitch,
+                                      long long c0, long long c1, int vec)
+{
+    const long long r = blockIdx.y;
+    const long long c = c0 + 4 * (blockIdx.x * (long long)blockDim.x + threadIdx.x);
+    if (c >= c1) return;
+    const float *src = in + r * pitch + c;
+    int16_t *dst = out + r * pitch + c;
+    if (vec && c + 3 < c1) {
+        const float4 v = *reinterpret_cast<const float4 *>(src);
+        short4 o;
+        o.x = to_pcm16(v.x); o.y = to_pcm16(v.y); o.z = to_pcm16(v.z); o.w = to_pcm16(v.w);
+        *reinterpret_cast<short4 *>(dst) = o;
+    } else {
+        for (int j = 0; j < 4 && c + j < c1; j++) dst[j] = to_pcm16(src[j]);
+    }
+}
+
+// in/out: `rows` rows of `pitch` samples (pitch and c0 multiples of 4); converts columns [c0, c1), zero-filling
+// columns >= n_valid up to the next multiple of 4
+cudaError_t pv_launch_pcm16_to_float(const int16_t *in, float *out, int64_t rows, int64_t pitch, int64_t c0, int64_t c1,
+                                     int64_t n_valid, cudaStream_t st)
+{
+    if (rows <= 0 || c1 <= c0) return cudaSuccess;
+    if (rows > 65535 || (pitch & 3) || (c0 & 3)) return cudaErrorInvalidValue;
+    const dim3 grid((unsigned)(((c1 - c0 + 3) / 4 + 255) / 256), (unsigned)rows);
+    pcm16_to_float_kernel<<<grid, 256, 0, st>>>(in, out, pitch, c0, c1, n_valid);
+    return cudaGetLastError();
+}
+
+// in/out: `rows` rows of `pitch` samples; converts columns [c0, c1)
+cudaError_t pv_launch_float_to_pcm16(const float *in, int16_t *out, int64_t rows, int64_t pitch, int64_t c0, int64_t c1,
+                                     cudaStream_t st)
+{
+    if (rows <= 0 || c1 <= c0) return cudaSuccess;
+    const int vec = !((pitch | c0) & 3);
+    for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+        const int64_t nr = std::min<int64_t>(65535, rows - r0);
+        const dim3 grid((unsigned)(((c1 - c0 + 3) / 4 + 255) / 256), (unsigned)nr);
+        float_to_pcm16_kernel<<<grid, 256, 0, st>>>(in + r0 * pitch, out + r0 * pitch, pitch, c0, c1, vec);
+    }
     return cudaGetLastError();
 }
 

@@ -76,6 +76,7 @@ struct PvAggArgs {
     int64_t P_prev_stride;    // in uint32 units (nb for a dense array, state_bytes/4 inside state blobs)
     int64_t *S, *H;
     uint32_t *P_first, *P_last;
+    int32_t P_prev_in_state;  // P_prev rows sit inside state records: the have_prev word (P_prev[-2]) gates the carry
 };
 cudaError_t pv_launch_corrected_aggregate(const PvDev &d, const PvFusedTables &t, const PvAggArgs &a, cudaStream_t st);
 cudaError_t pv_launch_state_from_carry(const PvDev &d, const PvFusedTables &t, int64_t n_streams, const uint32_t *P_first,
@@ -104,3 +105,9 @@ cudaError_t pv_launch_reduce_parts(int nb, int64_t n_streams, int32_t parts, con
                                    const uint32_t *Pl, int64_t *sumD, uint32_t *P_first, uint32_t *P_last, cudaStream_t st);
 // generic (any window) fused corrected path; a.state must be non-null (caller's or library scratch)
 cudaError_t pv_launch_corrected_generic(const PvDev &d, const PvProcessArgs &a, cudaStream_t st);
+
+// 16-bit PCM <-> float with the reference's AudioFile rules (src/AudioFile.h:1038-1049)
+cudaError_t pv_launch_pcm16_to_float(const int16_t *in, float *out, int64_t rows, int64_t pitch, int64_t c0, int64_t c1,
+                                     int64_t n_valid, cudaStream_t st);
+cudaError_t pv_launch_float_to_pcm16(const float *in, int16_t *out, int64_t rows, int64_t pitch, int64_t c0, int64_t c1,
+                                     cudaStream_t st);

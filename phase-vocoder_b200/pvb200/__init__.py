@@ -25,6 +25,7 @@ EXPORTS = [
     "pv_last_error", "pv_version", "pv_create", "pv_destroy", "pv_get_params", "pv_window_table",
     "pv_reference_schedule", "pv_analysis", "pv_resynthesis", "pv_test_overlap_add", "pv_analysis_batch",
     "pv_resynthesis_batch", "pv_state_bytes", "pv_process_device", "pv_process_device_ex", "pv_process_host",
+    "pv_process_host_pcm16",
     "pv_corrected_aggregate", "pv_corrected_state_from_carry", "pv_launch_count", "pv_timing_enable", "pv_timing_read",
 ]
 
@@ -69,6 +70,7 @@ def load():
     L.pv_state_bytes.restype = C.c_size_t
     L.pv_process_device.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, i64, i64, vp, i32, vp]
     L.pv_process_host.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, i64, i64, vp, i32]
+    L.pv_process_host_pcm16.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, i64, i64, vp, i32]
     L.pv_process_device_ex.argtypes = [vp, vp, i64, i64, i64, i64, i64, i64, vp, i64, i64, vp, i32, vp]
     L.pv_corrected_aggregate.argtypes = [vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp]
     L.pv_corrected_state_from_carry.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp]
@@ -223,6 +225,22 @@ class PhaseVocoder:
             in_stride, os_, ov = x.stride(0), out.stride(0), out.stride(1)
         _check(load().pv_process_host(self._h, _ptr(x), S, in_stride, n_in, na, n_frames, _ptr(out), os_, ov,
                                       _ptr(state), flags))
+        return out
+
+    def process_host_pcm16(self, x, n_frames, n_analysed=None, out=None, state=None, flags=0):
+        """16-bit PCM in and out (numpy int16 arrays or pinned CPU int16 tensors); AudioFile's conversions run on
+        the device.  x: [streams, n_in] int16 -> out [streams, V, n_frames*Hs] int16."""
+        S, n_in = x.shape
+        n_out = n_frames * self.outHopSize
+        if out is None:
+            out = np.empty((S, self.n_voices, n_out), np.int16)
+        na = n_frames if n_analysed is None else n_analysed
+        if isinstance(x, np.ndarray):
+            in_stride, os_, ov = x.strides[0] // 2, out.strides[0] // 2, out.strides[1] // 2
+        else:
+            in_stride, os_, ov = x.stride(0), out.stride(0), out.stride(1)
+        _check(load().pv_process_host_pcm16(self._h, _ptr(x), S, in_stride, n_in, na, n_frames, _ptr(out), os_, ov,
+                                            _ptr(state), flags))
         return out
 
     def launch_count(self):

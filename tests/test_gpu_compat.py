@@ -240,3 +240,51 @@ def test_many_streams_and_odd_strides():
     for s in (0, 1, 333, 699):
         want, _ = po.process_compat(x[s], N, H, H, pv.imp, nf, nf)
         assert snr_db(want, got[s, 0]) > 100
+
+
+def test_process_host_pcm16_applies_audiofile_rules(golden):
+    """16-bit PCM in/out with the conversions on the device == float path + AudioFile's rules on the host, and it
+    reproduces the golden WAV head directly from the raw int16 samples (+-1 LSB)."""
+    N, H = 256, 128
+    xi = golden["testout_head_in"].astype(np.int16)
+    want = golden["testout_head_out"].astype(np.int32)
+    nf = len(want) // H
+    pv = make(N, H, H)
+    x2 = np.stack([xi, np.roll(xi, 7)])
+    got = pv.process_host_pcm16(x2, nf)
+    assert got.dtype == np.int16 and got.shape == (2, 1, nf * H)
+    assert np.abs(got[0, 0].astype(np.int32) - want).max() <= 1
+    ref = pv.process_host(x2.astype(np.float32) / np.float32(32768), nf)
+    assert np.array_equal(got, wo.float_to_s16(ref))
+    # odd row length (device rows are padded) and many streams (chunked pipeline)
+    rng = np.random.default_rng(5)
+    x3 = rng.integers(-20000, 20000, size=(37, N + 19 * H + 3)).astype(np.int16)
+    g3 = pv.process_host_pcm16(x3, 20)
+    r3 = pv.process_host(x3.astype(np.float32) / np.float32(32768), 20)
+    assert np.array_equal(g3, wo.float_to_s16(r3))
+
+
+@pytest.mark.parametrize("N,Ha,Hs,nf,na", [(1024, 256, 256, 101, 101), (256, 64, 128, 90, 70), (512, 100, 128, 77, 77)])
+def test_host_pipeline_chunks_over_frames_bit_exact(monkeypatch, N, Ha, Hs, nf, na):
+    """The host path pipelines chunks of frames, carrying the overlap-add tail on the device from chunk to chunk:
+    same bits as one device call, for float and 16-bit PCM buffers, with the caller's carry state as well."""
+    S = 6
+    x = np.stack([multitone(N + nf * Ha + 5, seed=40 + s) for s in range(S)])
+    pv = make(N, Ha, Hs)
+    # the host path pads device rows to 4 samples (aligned loads): give the device call the same row pitch
+    xp = np.pad(x, ((0, 0), (0, -x.shape[1] % 4)))
+    d = pv.process(dev(xp), nf, n_analysed=na, n_in=x.shape[1]).cpu().numpy()
+    monkeypatch.setenv("PV_HOST_CHUNKS", "6")
+    assert np.array_equal(d, pv.process_host(x, nf, n_analysed=na))
+    xi = (x * 20000).astype(np.int16)
+    monkeypatch.setenv("PV_HOST_CHUNKS", "1")
+    one = pv.process_host_pcm16(xi, nf, n_analysed=na)
+    monkeypatch.setenv("PV_HOST_CHUNKS", "5")
+    assert np.array_equal(one, pv.process_host_pcm16(xi, nf, n_analysed=na))
+    # two host calls joined by the caller's state == one call
+    k = 40
+    st = np.zeros((S, pv.state_bytes()), np.uint8)
+    a = pv.process_host(x, k, n_analysed=min(na, k), state=st, flags=pvb200.CARRY_OUT)
+    b = pv.process_host(np.ascontiguousarray(x[:, k * Ha:]), nf - k, n_analysed=max(0, na - k), state=st,
+                        flags=pvb200.CARRY_IN | pvb200.CARRY_OUT)
+    assert np.array_equal(np.concatenate([a, b], axis=2), d)

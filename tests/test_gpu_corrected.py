@@ -220,3 +220,31 @@ def test_corrected_split_with_carry_in_and_skip_is_bit_exact(monkeypatch):
     for g, w in zip(got, want):
         assert np.array_equal(g, w)
     assert got[1].shape[2] == (nf - k_cut - skip) * Hs
+
+
+@pytest.mark.parametrize("S,nf", [(5, 120), (1, 900)])
+def test_host_pipeline_chunks_over_frames_bit_exact(monkeypatch, S, nf):
+    """Chunks of frames with the phase accumulators and the OLA tail carried on the device: same bits as one
+    device call (few long streams take the frame-range split inside every chunk)."""
+    N, Ha, Hs = 512, 128, 128
+    betas = [1.0, f32(1.26)]
+    rng = np.random.default_rng(9)
+    x = (rng.normal(size=(S, N + nf * Ha)) * 0.1).astype(np.float32)
+    pv = make(N, Ha, Hs, betas)
+    d = pv.process(dev(x), nf).cpu().numpy()
+    # an all-zero state carried in is a fresh start (also through the frame-range split of few long streams)
+    z = torch.zeros((S, pv.state_bytes() // 4), device="cuda")
+    assert np.array_equal(d, pv.process(dev(x), nf, state=z, flags=pvb200.CARRY_IN | pvb200.CARRY_OUT).cpu().numpy())
+    for chunks in ("4", "7"):
+        monkeypatch.setenv("PV_HOST_CHUNKS", chunks)
+        assert np.array_equal(d, pv.process_host(x, nf))
+    xi = (x * 20000).astype(np.int16)
+    monkeypatch.setenv("PV_HOST_CHUNKS", "1")
+    one = pv.process_host_pcm16(xi, nf)
+    monkeypatch.setenv("PV_HOST_CHUNKS", "6")
+    assert np.array_equal(one, pv.process_host_pcm16(xi, nf))
+    k = 50
+    st = np.zeros((S, pv.state_bytes()), np.uint8)
+    a = pv.process_host(x, k, state=st, flags=pvb200.CARRY_OUT)
+    b = pv.process_host(np.ascontiguousarray(x[:, k * Ha:]), nf - k, state=st, flags=pvb200.CARRY_IN | pvb200.CARRY_OUT)
+    assert np.array_equal(np.concatenate([a, b], axis=2), d)
