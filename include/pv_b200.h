@@ -198,6 +198,39 @@ int pv_process_host_pcm16(pv_handle *h, const int16_t *in, int64_t n_streams, in
                           int64_t out_stream_stride, int64_t out_voice_stride, void *state,
                           int32_t flags);
 
+/* ------------------------------------------------------------------------------------------
+ * Real-time block server: the reference's unfinished RtAudio path (src/main.cpp:45-59 `callback`,
+ * README.md:44-50, img/Realtime.png).  Its contract: every time the audio buffer is full the
+ * callback receives nBufferFrames new samples and must return nBufferFrames processed ones,
+ * "looking backwards at the previous input through a ring buffer to maintain continuity".
+ * Here one server handles n_streams such callbacks at once.  A block is block_frames hops:
+ * block_frames*Ha new samples per stream in, block_frames*Hs samples per stream and voice out.
+ * The last N-Ha input samples stay on the device (the ring), the phase accumulators and the
+ * overlap-add tail are carried from block to block, and one block is ONE CUDA-graph launch
+ * (H2D of the block, the fused kernel, the ring advance, D2H of the result).
+ *
+ * The output equals the offline result of pv_process_* on the input delayed by the latency
+ * N-Ha (the ring starts out silent), bit for bit.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct pv_rt pv_rt;
+
+int pv_rt_open(pv_handle *h, int64_t n_streams, int32_t block_frames, pv_rt **out);
+void pv_rt_close(pv_rt *rt);
+/* Silence the ring and the carried state (a new take). */
+int pv_rt_reset(pv_rt *rt);
+/* Input-to-output delay in samples at the input rate: N - Ha. */
+int64_t pv_rt_latency_samples(const pv_rt *rt);
+/* Page-locked staging owned by the server: input [n_streams][block_frames*Ha], output
+ * [n_streams][voices][block_frames*Hs].  Fill the input, call pv_rt_step, read the output:
+ * the zero-copy variant of the callback for callers that can record straight into it.       */
+float *pv_rt_input(pv_rt *rt);
+float *pv_rt_output(pv_rt *rt);
+int pv_rt_step(pv_rt *rt);
+/* The reference's callback signature for n_streams planar channels (RTAUDIO_NONINTERLEAVED
+ * layout): in [n_streams][nBufferFrames], out [n_streams][voices][nBufferFrames*Hs/Ha];
+ * nBufferFrames must be block_frames*Ha.  Returns 0 like the reference's callback.          */
+int pv_rt_callback(pv_rt *rt, float *outputBuffer, const float *inputBuffer, uint32_t nBufferFrames);
+
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t pv_launch_count(const pv_handle *h);
 

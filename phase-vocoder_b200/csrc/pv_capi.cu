@@ -931,6 +931,165 @@ int pv_process_host_pcm16(pv_handle *h, const int16_t *in, int64_t n_streams, in
                                    out_voice_stride, state, flags);
 }
 
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// Real-time block server (include/pv_b200.h, "Real-time block server")
+// ---------------------------------------------------------------------------------------------------
+struct pv_rt {
+    pv_handle *h = nullptr;
+    int64_t S = 0, hist = 0, in_w = 0, out_w = 0, row = 0;
+    int32_t B = 0;
+    float *d_buf[2] = {nullptr, nullptr};     // [S][row]: ring history (N-Ha) followed by the new block
+    float *d_out = nullptr;
+    void *d_state = nullptr;
+    float *h_in = nullptr, *h_out = nullptr;  // page-locked staging
+    cudaStream_t st = nullptr;
+    cudaGraphExec_t exec[2] = {nullptr, nullptr};
+    int cur = 0;
+    int kernels_per_step = 0;
+};
+
+namespace {
+
+// One block on the server's stream: the four operations that the graph records.
+int rt_enqueue(pv_rt *rt, int p)
+{
+    pv_handle *h = rt->h;
+    const int64_t V = h->p.n_voices;
+    PV_CUDA(cudaMemcpy2DAsync(rt->d_buf[p] + rt->hist, sizeof(float) * rt->row, rt->h_in, sizeof(float) * rt->in_w,
+                              sizeof(float) * rt->in_w, (size_t)rt->S, cudaMemcpyHostToDevice, rt->st));
+    int rc = pv_process_device_ex(h, rt->d_buf[p], rt->S, rt->row, rt->hist + rt->in_w, rt->B, rt->B, 0, rt->d_out, V * rt->out_w,
+                                  rt->out_w, rt->d_state, PV_PROCESS_CARRY_IN | PV_PROCESS_CARRY_OUT, rt->st);
+    if (rc != PV_OK) return rc;
+    if (rt->hist > 0)       // ring advance: the last N-Ha samples become the next block's history
+        PV_CUDA(cudaMemcpy2DAsync(rt->d_buf[1 - p], sizeof(float) * rt->row, rt->d_buf[p] + rt->in_w, sizeof(float) * rt->row,
+                                  sizeof(float) * rt->hist, (size_t)rt->S, cudaMemcpyDeviceToDevice, rt->st));
+    PV_CUDA(cudaMemcpyAsync(rt->h_out, rt->d_out, sizeof(float) * (size_t)(rt->S * V * rt->out_w), cudaMemcpyDeviceToHost, rt->st));
+    return PV_OK;
+}
+
+int rt_clear(pv_rt *rt)
+{
+    PV_CUDA(cudaMemsetAsync(rt->d_buf[0], 0, sizeof(float) * (size_t)(rt->S * rt->row), rt->st));
+    PV_CUDA(cudaMemsetAsync(rt->d_buf[1], 0, sizeof(float) * (size_t)(rt->S * rt->row), rt->st));
+    PV_CUDA(cudaMemsetAsync(rt->d_state, 0, (size_t)rt->S * pv_state_bytes(rt->h), rt->st));   // all-zero state = fresh start
+    PV_CUDA(cudaStreamSynchronize(rt->st));
+    rt->cur = 0;
+    return PV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void pv_rt_close(pv_rt *rt)
+{
+    if (!rt) return;
+    DeviceGuard guard(rt->h->device);
+    if (rt->st) cudaStreamSynchronize(rt->st);
+    for (auto &e : rt->exec)
+        if (e) cudaGraphExecDestroy(e);
+    cudaFree(rt->d_buf[0]);
+    cudaFree(rt->d_buf[1]);
+    cudaFree(rt->d_out);
+    cudaFree(rt->d_state);
+    cudaFreeHost(rt->h_in);
+    cudaFreeHost(rt->h_out);
+    if (rt->st) cudaStreamDestroy(rt->st);
+    delete rt;
+}
+
+int pv_rt_open(pv_handle *h, int64_t n_streams, int32_t block_frames, pv_rt **out)
+{
+    if (!h || !out || n_streams <= 0 || block_frames <= 0) return fail(PV_ERR_PARAM, "pv_rt_open: bad argument");
+    *out = nullptr;
+    DeviceGuard guard(h->device);
+    pv_rt *rt = new pv_rt;
+    rt->h = h;
+    rt->S = n_streams;
+    rt->B = block_frames;
+    const int64_t V = h->p.n_voices;
+    rt->hist = h->p.window - h->p.hop_in;
+    rt->in_w = (int64_t)block_frames * h->p.hop_in;
+    rt->out_w = (int64_t)block_frames * h->p.hop_out;
+    rt->row = (rt->hist + rt->in_w + 3) & ~int64_t(3);
+    int rc = PV_OK;
+    auto ck = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && rc == PV_OK) rc = fail(PV_ERR_CUDA, "pv_rt_open: %s: %s", what, cudaGetErrorString(e));
+    };
+    ck(cudaStreamCreateWithFlags(&rt->st, cudaStreamNonBlocking), "stream");
+    ck(cudaMalloc((void **)&rt->d_buf[0], sizeof(float) * (size_t)(rt->S * rt->row)), "ring");
+    ck(cudaMalloc((void **)&rt->d_buf[1], sizeof(float) * (size_t)(rt->S * rt->row)), "ring");
+    ck(cudaMalloc((void **)&rt->d_out, sizeof(float) * (size_t)(rt->S * V * rt->out_w)), "output");
+    ck(cudaMalloc(&rt->d_state, (size_t)rt->S * pv_state_bytes(h)), "state");
+    ck(cudaHostAlloc((void **)&rt->h_in, sizeof(float) * (size_t)(rt->S * rt->in_w), cudaHostAllocDefault), "pinned input");
+    ck(cudaHostAlloc((void **)&rt->h_out, sizeof(float) * (size_t)(rt->S * V * rt->out_w), cudaHostAllocDefault), "pinned output");
+    if (rc == PV_OK) {
+        memset(rt->h_in, 0, sizeof(float) * (size_t)(rt->S * rt->in_w));
+        rc = rt_clear(rt);
+    }
+    // one eager block: builds the segment plan and sets the kernel attributes, neither of which can be recorded
+    const int64_t l0 = h->launches;
+    if (rc == PV_OK) rc = rt_enqueue(rt, 0);
+    if (rc == PV_OK) ck(cudaStreamSynchronize(rt->st), "first block");
+    rt->kernels_per_step = (int)(h->launches - l0);
+    for (int p = 0; p < 2 && rc == PV_OK; p++) {
+        cudaGraph_t g = nullptr;
+        ck(cudaStreamBeginCapture(rt->st, cudaStreamCaptureModeThreadLocal), "begin capture");
+        if (rc != PV_OK) break;
+        int rc2 = rt_enqueue(rt, p);
+        cudaError_t e = cudaStreamEndCapture(rt->st, &g);
+        if (rc2 != PV_OK) rc = rc2;
+        else ck(e, "end capture");
+        if (rc == PV_OK) ck(cudaGraphInstantiate(&rt->exec[p], g, 0), "instantiate");
+        if (g) cudaGraphDestroy(g);
+    }
+    h->launches = l0;            // the recording issued nothing; pv_rt_step counts the replays
+    if (rc == PV_OK) rc = rt_clear(rt);
+    if (rc != PV_OK) {
+        pv_rt_close(rt);
+        return rc;
+    }
+    *out = rt;
+    return PV_OK;
+}
+
+int pv_rt_reset(pv_rt *rt)
+{
+    if (!rt) return fail(PV_ERR_PARAM, "pv_rt_reset: null server");
+    DeviceGuard guard(rt->h->device);
+    return rt_clear(rt);
+}
+
+int64_t pv_rt_latency_samples(const pv_rt *rt) { return rt ? rt->hist : 0; }
+float *pv_rt_input(pv_rt *rt) { return rt ? rt->h_in : nullptr; }
+float *pv_rt_output(pv_rt *rt) { return rt ? rt->h_out : nullptr; }
+
+int pv_rt_step(pv_rt *rt)
+{
+    if (!rt) return fail(PV_ERR_PARAM, "pv_rt_step: null server");
+    DeviceGuard guard(rt->h->device);
+    PV_CUDA(cudaGraphLaunch(rt->exec[rt->cur], rt->st));
+    PV_CUDA(cudaStreamSynchronize(rt->st));
+    rt->cur ^= (rt->hist > 0);
+    rt->h->launches += rt->kernels_per_step;
+    return PV_OK;
+}
+
+int pv_rt_callback(pv_rt *rt, float *outputBuffer, const float *inputBuffer, uint32_t nBufferFrames)
+{
+    if (!rt || !outputBuffer || !inputBuffer) return fail(PV_ERR_PARAM, "pv_rt_callback: null argument");
+    if ((int64_t)nBufferFrames != rt->in_w)
+        return fail(PV_ERR_PARAM, "pv_rt_callback: nBufferFrames=%u, the server was opened for blocks of %lld samples",
+                    nBufferFrames, (long long)rt->in_w);
+    memcpy(rt->h_in, inputBuffer, sizeof(float) * (size_t)(rt->S * rt->in_w));
+    int rc = pv_rt_step(rt);
+    if (rc != PV_OK) return rc;
+    memcpy(outputBuffer, rt->h_out, sizeof(float) * (size_t)(rt->S * rt->h->p.n_voices * rt->out_w));
+    return 0;
+}
+
 int64_t pv_launch_count(const pv_handle *h) { return h ? h->launches : 0; }
 
 int pv_timing_enable(pv_handle *h, int32_t on)

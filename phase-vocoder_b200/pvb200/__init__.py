@@ -27,6 +27,8 @@ EXPORTS = [
     "pv_resynthesis_batch", "pv_state_bytes", "pv_process_device", "pv_process_device_ex", "pv_process_host",
     "pv_process_host_pcm16",
     "pv_corrected_aggregate", "pv_corrected_state_from_carry", "pv_launch_count", "pv_timing_enable", "pv_timing_read",
+    "pv_rt_open", "pv_rt_close", "pv_rt_reset", "pv_rt_latency_samples", "pv_rt_input", "pv_rt_output", "pv_rt_step",
+    "pv_rt_callback",
 ]
 
 
@@ -78,6 +80,18 @@ def load():
     L.pv_launch_count.restype = i64
     L.pv_timing_enable.argtypes = [vp, i32]
     L.pv_timing_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
+    L.pv_rt_open.argtypes = [vp, i64, i32, C.POINTER(vp)]
+    L.pv_rt_close.argtypes = [vp]
+    L.pv_rt_close.restype = None
+    L.pv_rt_reset.argtypes = [vp]
+    L.pv_rt_latency_samples.argtypes = [vp]
+    L.pv_rt_latency_samples.restype = i64
+    L.pv_rt_input.argtypes = [vp]
+    L.pv_rt_input.restype = C.POINTER(C.c_float)
+    L.pv_rt_output.argtypes = [vp]
+    L.pv_rt_output.restype = C.POINTER(C.c_float)
+    L.pv_rt_step.argtypes = [vp]
+    L.pv_rt_callback.argtypes = [vp, vp, vp, C.c_uint32]
     _lib = L
     return L
 
@@ -253,3 +267,43 @@ class PhaseVocoder:
         ms, n = C.c_double(), C.c_int64()
         _check(load().pv_timing_read(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+
+class RealtimeServer:
+    """Block server for live streams: the reference's RtAudio callback contract (src/main.cpp:45-59) for
+    n_streams channels at once.  `input` / `output` are numpy views of the server's page-locked staging."""
+
+    def __init__(self, pv, n_streams, block_frames=1):
+        self.pv = pv                      # keeps the handle alive
+        self._rt = C.c_void_p()
+        _check(load().pv_rt_open(pv._h, n_streams, block_frames, C.byref(self._rt)))
+        self.n_streams, self.block_frames = n_streams, block_frames
+        self.block_in = block_frames * pv.hopSize
+        self.block_out = block_frames * pv.outHopSize
+        self.latency = load().pv_rt_latency_samples(self._rt)
+        self.input = np.ctypeslib.as_array(load().pv_rt_input(self._rt), shape=(n_streams, self.block_in))
+        self.output = np.ctypeslib.as_array(load().pv_rt_output(self._rt), shape=(n_streams, pv.n_voices, self.block_out))
+
+    def step(self):
+        _check(load().pv_rt_step(self._rt))
+        return self.output
+
+    def callback(self, output_buffer, input_buffer):
+        """out, in, nBufferFrames as the reference's callback; planar float32 numpy arrays."""
+        _check(load().pv_rt_callback(self._rt, output_buffer.ctypes.data, input_buffer.ctypes.data, input_buffer.shape[-1]))
+        return 0
+
+    def reset(self):
+        _check(load().pv_rt_reset(self._rt))
+
+    def close(self):
+        if self._rt:
+            load().pv_rt_close(self._rt)
+            self._rt = C.c_void_p()
+            self.input = self.output = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

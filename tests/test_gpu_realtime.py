@@ -1,0 +1,58 @@
+"""Real-time block server (pv_rt_*): the reference's callback contract (src/main.cpp:45-59) for many channels.
+Block-by-block output == offline output of the input delayed by the latency N-Ha, bit for bit."""
+import numpy as np
+import pytest
+import torch
+
+import pvb200
+from signals import multitone
+
+pytestmark = pytest.mark.gpu
+
+
+def f32(x):
+    return float(np.float32(x))
+
+
+def offline(pv, x, latency, n_frames):
+    xd = np.concatenate([np.zeros((x.shape[0], latency), np.float32), x], axis=1)
+    xd = np.pad(xd, ((0, 0), (0, -xd.shape[1] % 4)))
+    return pv.process(torch.from_numpy(xd).cuda(), n_frames, n_in=latency + x.shape[1]).cpu().numpy()
+
+
+@pytest.mark.parametrize("mode,N,Ha,Hs,B,S", [
+    ("compat", 256, 128, 128, 2, 3),          # the reference's head config: nBufferFrames = nSamps = 256
+    ("compat", 1024, 256, 512, 1, 5),
+    ("corrected", 256, 64, 64, 1, 7),         # C4's shape, one hop per block
+    ("corrected", 2048, 512, 512, 3, 2),
+    ("corrected", 512, 100, 100, 4, 2),       # hop not a multiple of 4: unaligned ring rows
+])
+def test_blocks_equal_offline_delayed_input(mode, N, Ha, Hs, B, S):
+    blocks = 9
+    if mode == "compat":
+        pv = pvb200.PhaseVocoder(N, hop_in=Ha, hop_out=Hs, mode=pvb200.MODE_COMPAT)
+    else:
+        pv = pvb200.PhaseVocoder(N, hop_in=Ha, hop_out=Hs, mode=pvb200.MODE_CORRECTED,
+                                 window_type=pvb200.WIN_HANN_PERIODIC, pitch=(1.0, f32(1.5)))
+    x = np.stack([multitone(blocks * B * Ha, seed=70 + s) for s in range(S)])
+    rt = pvb200.RealtimeServer(pv, S, B)
+    assert rt.latency == N - Ha and rt.block_in == B * Ha and rt.block_out == B * Hs
+    want = offline(pv, x, rt.latency, blocks * B)
+    got = []
+    for b in range(blocks):
+        rt.input[:] = x[:, b * B * Ha:(b + 1) * B * Ha]
+        got.append(rt.step().copy())
+    got = np.concatenate(got, axis=2)
+    assert np.array_equal(got, want)
+    # a reset starts a new take; the callback form gives the same samples
+    rt.reset()
+    out = np.empty((S, pv.n_voices, B * Hs), np.float32)
+    for b in range(2):
+        assert rt.callback(out, np.ascontiguousarray(x[:, b * B * Ha:(b + 1) * B * Ha])) == 0
+        assert np.array_equal(out, want[:, :, b * B * Hs:(b + 1) * B * Hs])
+    with pytest.raises(pvb200.PvError):
+        rt.callback(out, np.zeros((S, B * Ha + 1), np.float32))
+    n0 = pv.launch_count()
+    rt.step()
+    assert pv.launch_count() == n0 + 1           # one fused kernel per block
+    rt.close()

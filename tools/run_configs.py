@@ -81,6 +81,21 @@ def realtime_step(streams=4096, N=256, H=64, betas=(1.0, 2 ** (4 / 12), 2 ** (7 
     print(f"\nC4 real-time step: {streams} streams x 1 hop ({H} samples) x {len(betas)} voices per call: "
           f"{ms*1e3:.0f} us device time per call, {wall*1e3:.0f} us wall per call (hop period {H/44100*1e3:.2f} ms, "
           f"window budget {N/44100*1e3:.1f} ms) -> {streams/(ms*1e-3)/1e6:.1f} M frames/s")
+    # the same through the block server (pv_rt_*): host buffers in, host buffers out, one graph launch per block
+    for S, B in ((streams, 1), (streams, 4), (64, 1)):
+        rt = pvb200.RealtimeServer(pv, S, B)
+        rt.input[:] = np.random.default_rng(0).normal(size=rt.input.shape).astype(np.float32) * 0.1
+        for _ in range(50):
+            rt.step()
+        ts = []
+        for _ in range(2000):
+            t0 = time.perf_counter()
+            rt.step()
+            ts.append(time.perf_counter() - t0)
+        ts = np.sort(np.array(ts)) * 1e6
+        print(f"C4 block server: {S} streams x {B} hop(s) per block, host buffer to host buffer: median {ts[1000]:.0f} us, "
+              f"p99 {ts[1980]:.0f} us, max {ts[-1]:.0f} us per block (block period {B*H/44100*1e3:.2f} ms)")
+        rt.close()
 
 
 def main():
