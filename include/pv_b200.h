@@ -231,6 +231,15 @@ int pv_rt_step(pv_rt *rt);
  * nBufferFrames must be block_frames*Ha.  Returns 0 like the reference's callback.          */
 int pv_rt_callback(pv_rt *rt, float *outputBuffer, const float *inputBuffer, uint32_t nBufferFrames);
 
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone batched complex FFT: the counterpart of the reference's FFT back-ends and of the
+ * micro-benchmark that times them (karnel/hpfft.cu:145-203 `GPU_FFT`, :104-143 `FFTShMem`,
+ * karnel/cufft_.cu:19-26 `computeCuFFT`).  in/out: batch x n interleaved complex floats on the
+ * device (in == out allowed), n a power of two <= 8192, direction -1 forward / +1 inverse,
+ * unnormalised both ways (cuFFT's convention).  One launch per call.                          */
+int pv_fft_batch(pv_handle *h, const float *in, float *out, int32_t n, int64_t batch,
+                 int32_t direction, void *cuda_stream);
+
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t pv_launch_count(const pv_handle *h);
 

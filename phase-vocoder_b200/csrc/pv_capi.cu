@@ -58,6 +58,7 @@ struct pv_handle {
     };
     Plan plans[8];
     uint64_t plan_clock = 0;
+    float2 *d_fft_tw[14] = {};      // stand-alone FFT: n-th roots of unity per log2 n, built on first use
     // staging for the host-pointer entry point
     float *d_in = nullptr, *d_out = nullptr;
     size_t in_cap = 0, out_cap = 0;
@@ -473,6 +474,7 @@ void pv_destroy(pv_handle *h)
         cudaFree(pl.d_agg_segs);
     }
     for (auto e : h->pipe_events) cudaEventDestroy(e);
+    for (auto p : h->d_fft_tw) cudaFree(p);
     cudaFree(h->d_api_segs);
     cudaFree(h->d_S);
     cudaFree(h->d_H);
@@ -1088,6 +1090,29 @@ int pv_rt_callback(pv_rt *rt, float *outputBuffer, const float *inputBuffer, uin
     if (rc != PV_OK) return rc;
     memcpy(outputBuffer, rt->h_out, sizeof(float) * (size_t)(rt->S * rt->h->p.n_voices * rt->out_w));
     return 0;
+}
+
+int pv_fft_batch(pv_handle *h, const float *in, float *out, int32_t n, int64_t batch, int32_t direction, void *cuda_stream)
+{
+    if (!h || !in || !out || batch < 0 || (direction != 1 && direction != -1))
+        return fail(PV_ERR_PARAM, "pv_fft_batch: bad argument");
+    if (n < 1 || n > 8192 || (n & (n - 1))) return fail(PV_ERR_PARAM, "pv_fft_batch: n=%d is not a power of two in 1..8192", n);
+    if (batch == 0) return PV_OK;
+    DeviceGuard guard(h->device);
+    const int lg = ilog2(n);
+    if (!h->d_fft_tw[lg]) {
+        std::vector<float2> tw((size_t)n);
+        for (int k = 0; k < n; k++) {
+            const double a = -2.0 * M_PI * (double)k / (double)n;
+            tw[(size_t)k] = make_float2((float)cos(a), (float)sin(a));
+        }
+        int rc = upload(&h->d_fft_tw[lg], tw);
+        if (rc != PV_OK) return rc;
+    }
+    PV_CUDA(pv_launch_fft_batch(reinterpret_cast<const float2 *>(in), reinterpret_cast<float2 *>(out), lg, batch, direction,
+                                h->d_fft_tw[lg], (cudaStream_t)cuda_stream));
+    h->launches++;
+    return PV_OK;
 }
 
 int64_t pv_launch_count(const pv_handle *h) { return h ? h->launches : 0; }

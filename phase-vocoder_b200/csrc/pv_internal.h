@@ -107,6 +107,8 @@ cudaError_t pv_launch_reduce_parts(int nb, int64_t n_streams, int32_t parts, con
 cudaError_t pv_launch_corrected_generic(const PvDev &d, const PvProcessArgs &a, cudaStream_t st);
 
 // 16-bit PCM <-> float with the reference's AudioFile rules (src/AudioFile.h:1038-1049)
+cudaError_t pv_launch_fft_batch(const float2 *in, float2 *out, int lg_n, int64_t batch, int dir, const float2 *tw,
+                                cudaStream_t st);
 cudaError_t pv_launch_pcm16_to_float(const int16_t *in, float *out, int64_t rows, int64_t pitch, int64_t c0, int64_t c1,
                                      int64_t n_valid, cudaStream_t st);
 cudaError_t pv_launch_float_to_pcm16(const float *in, int16_t *out, int64_t rows, int64_t pitch, int64_t c0, int64_t c1,

@@ -28,7 +28,7 @@ EXPORTS = [
     "pv_process_host_pcm16",
     "pv_corrected_aggregate", "pv_corrected_state_from_carry", "pv_launch_count", "pv_timing_enable", "pv_timing_read",
     "pv_rt_open", "pv_rt_close", "pv_rt_reset", "pv_rt_latency_samples", "pv_rt_input", "pv_rt_output", "pv_rt_step",
-    "pv_rt_callback",
+    "pv_rt_callback", "pv_fft_batch",
 ]
 
 
@@ -92,6 +92,7 @@ def load():
     L.pv_rt_output.restype = C.POINTER(C.c_float)
     L.pv_rt_step.argtypes = [vp]
     L.pv_rt_callback.argtypes = [vp, vp, vp, C.c_uint32]
+    L.pv_fft_batch.argtypes = [vp, vp, vp, i32, i64, i32, vp]
     _lib = L
     return L
 
@@ -255,6 +256,16 @@ class PhaseVocoder:
             in_stride, os_, ov = x.stride(0), out.stride(0), out.stride(1)
         _check(load().pv_process_host_pcm16(self._h, _ptr(x), S, in_stride, n_in, na, n_frames, _ptr(out), os_, ov,
                                             _ptr(state), flags))
+        return out
+
+    def fft_batch(self, x, inverse=False, out=None):
+        """Stand-alone batched complex FFT of a [batch, n] complex64 CUDA tensor (unnormalised both ways)."""
+        import torch
+        assert x.is_cuda and x.dtype == torch.complex64 and x.dim() == 2 and x.is_contiguous()
+        if out is None:
+            out = torch.empty_like(x)
+        _check(load().pv_fft_batch(self._h, _ptr(x), _ptr(out), x.shape[1], x.shape[0], 1 if inverse else -1,
+                                   _cuda_stream()))
         return out
 
     def launch_count(self):
