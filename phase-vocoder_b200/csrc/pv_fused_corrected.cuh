@@ -237,24 +237,41 @@ PV_DEV void cforward(int tid, const FrameIO &io, const CTables &tb, const CThrea
     using S = Shape<LOG2N>;
     constexpr int N = C::N, T = C::T, B3 = C::B3, R1 = C::R1, R2 = C::R2, M = C::M, S1 = C::S1, NB = C::NB;
     const int rbase = (int)(io.base & (N - 1));
-    auto ld = [&](int i) -> float2 {
-        float2 x;
-        if (ring != nullptr) x = *reinterpret_cast<const float2 *>(ring + ((rbase + i) & (N - 1)));
-        else {
-            const long long g = io.base + i;
-            if (io.vec_ok && g + 1 < io.n_in) x = PV_LDG(reinterpret_cast<const float2 *>(io.in + g));
-            else x = make_float2(g < io.n_in ? PV_LDG(io.in + g) : 0.f, g + 1 < io.n_in ? PV_LDG(io.in + g + 1) : 0.f);
+    // Loads the R windowed sample pairs of one pass-1 butterfly.  The ring / global choice is made ONCE per
+    // butterfly, not per pair: the hot (ring) path stays one straight run of instructions instead of sixteen
+    // short ones separated by the bounds-checked global fallback, which the instruction cache pays for.
+    auto ld_block = [&](auto &v, int t1) {
+        constexpr int R = (int)(sizeof(v) / sizeof(v[0]));
+        if (ring != nullptr) {
+#pragma unroll
+            for (int n1 = 0; n1 < R; n1++) {
+                const int i = (N / 2 + 2 * (n1 * S1 + t1)) & (N - 1);
+                v[n1] = *reinterpret_cast<const float2 *>(ring + ((rbase + i) & (N - 1)));
+            }
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < R; n1++) {
+                const int i = (N / 2 + 2 * (n1 * S1 + t1)) & (N - 1);
+                const long long g = io.base + i;
+                float2 x;
+                if (io.vec_ok && g + 1 < io.n_in) x = PV_LDG(reinterpret_cast<const float2 *>(io.in + g));
+                else x = make_float2(g < io.n_in ? PV_LDG(io.in + g) : 0.f, g + 1 < io.n_in ? PV_LDG(io.in + g + 1) : 0.f);
+                v[n1] = x;
+            }
         }
-        const float2 w = PV_LDG(reinterpret_cast<const float2 *>(tb.win + i));
-        return make_float2(x.x * w.x, x.y * w.y);
+#pragma unroll
+        for (int n1 = 0; n1 < R; n1++) {
+            const int i = (N / 2 + 2 * (n1 * S1 + t1)) & (N - 1);
+            const float2 w = PV_LDG(reinterpret_cast<const float2 *>(tb.win + i));
+            v[n1] = make_float2(v[n1].x * w.x, v[n1].y * w.y);
+        }
     };
 
     // ---- forward pass 1: c[m] = (f[(N/2 + 2m) mod N], f[.. + 1]), m = n1*S1 + t1 ----
     if constexpr (2 * C::C1 == T) {
         const int t1 = tid % C::C1, half = tid / C::C1;
         float2 v[16], o[8];
-#pragma unroll
-        for (int n1 = 0; n1 < 16; n1++) v[n1] = ld((N / 2 + 2 * (n1 * S1 + t1)) & (N - 1));
+        ld_block(v, t1);
         if (half == 0) dft16_half<-1, false>(v, o);
         else dft16_half<-1, true>(v, o);
         float2 e[8];
@@ -270,8 +287,7 @@ PV_DEV void cforward(int tid, const FrameIO &io, const CTables &tb, const CThrea
 #pragma unroll
         for (int t1 = tid; t1 < C::C1; t1 += T) {
             float2 v[R1];
-#pragma unroll
-            for (int n1 = 0; n1 < R1; n1++) v[n1] = ld((N / 2 + 2 * (n1 * S1 + t1)) & (N - 1));
+            ld_block(v, t1);
             dft<R1, -1>(v);
             bufA[t1] = v[0];
 #pragma unroll
@@ -422,7 +438,9 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
             const bool has = lo <= hi;
             const int l0 = has ? lo : 0, h0 = has ? hi : 0;
             float m = magS[l0];
-            for (int a = l0 + 1; a <= h0; a++) m += magS[a];        // ascending, as the specification sums
+#pragma unroll 1
+            for (int a = l0 + 1; a <= h0; a++) m += magS[a];        // ascending, as the specification sums (rarely taken:
+                                                                    // kept rolled so that it stays out of the hot path)
             const int32_t d = dS[h0];
             unsigned long long p;
             if (first) p = (unsigned long long)(uint32_t)d << 32;
