@@ -201,22 +201,32 @@ PV_DEV void forward_12(int tid, const FrameIO &io, const Tables &tb, const Threa
     using S = Shape<LOG2N>;
     constexpr int N = S::N, T = S::T, R1 = S::R1, R2 = S::R2, S1 = S::S1;
     const int rbase = (int)(io.base & (N - 1));
-    auto ld = [&](int i) -> float2 {
-        if (ring == nullptr) return load_pair(io, tb.win, i);
-        const float2 x = *reinterpret_cast<const float2 *>(ring + ((rbase + i) & (N - 1)));
-        const float2 w = PV_LDG(reinterpret_cast<const float2 *>(tb.win + i));
-        return make_float2(x.x * w.x, x.y * w.y);
+    // c[n], n = n1*S1 + t1: n < N/4 -> f[N/2 + 2n]; n >= 3N/4 -> f[2(n - 3N/4)]; else 0
+    auto src_index = [&](int n1, int t1) -> int {
+        return n1 < R1 / 4 ? N / 2 + 2 * (n1 * S1 + t1) : 2 * ((n1 - 3 * R1 / 4) * S1 + t1);
     };
     // pass 1: butterflies t1 in [0, S1)
 #pragma unroll
     for (int t1 = tid; t1 < S1; t1 += T) {
         float2 v[R1];
+        // The ring / global choice is made once per butterfly, not per sample pair: the hot (ring) path stays one
+        // straight run of instructions instead of short runs separated by the bounds-checked global fallback,
+        // which the instruction cache pays for.
+        if (ring != nullptr) {
 #pragma unroll
-        for (int n1 = 0; n1 < R1; n1++) {
-            // c[n], n = n1*S1 + t1: n < N/4 -> f[N/2 + 2n]; n >= 3N/4 -> f[2(n - 3N/4)]; else 0
-            if (n1 < R1 / 4) v[n1] = ld(N / 2 + 2 * (n1 * S1 + t1));
-            else if (n1 >= 3 * R1 / 4) v[n1] = ld(2 * ((n1 - 3 * R1 / 4) * S1 + t1));
-            else v[n1] = make_float2(0.f, 0.f);
+            for (int n1 = 0; n1 < R1; n1++) {
+                if (n1 >= R1 / 4 && n1 < 3 * R1 / 4) { v[n1] = make_float2(0.f, 0.f); continue; }
+                const int i = src_index(n1, t1);
+                const float2 x = *reinterpret_cast<const float2 *>(ring + ((rbase + i) & (N - 1)));
+                const float2 w = PV_LDG(reinterpret_cast<const float2 *>(tb.win + i));
+                v[n1] = make_float2(x.x * w.x, x.y * w.y);
+            }
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < R1; n1++) {
+                if (n1 >= R1 / 4 && n1 < 3 * R1 / 4) { v[n1] = make_float2(0.f, 0.f); continue; }
+                v[n1] = load_pair(io, tb.win, src_index(n1, t1));
+            }
         }
         dft_pruned_fwd<R1>(v);
         bufA[t1] = v[0];
