@@ -251,6 +251,22 @@ def device_streams(torch, n_streams, n_in, seed):
     return x
 
 
+def bind_to_gpu_numa_node(index):
+    """Runs this rank on the CPUs next to its GPU, so that the page-locked host buffers of the end-to-end
+    leg (first touch) sit on the NUMA node the GPU's PCIe root hangs off.  Plain NVML; harmless if it fails."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))
+    except Exception as e:          # noqa: BLE001 -- a placement hint, never a reason to fail the run
+        print(f"[bench] no NUMA binding: {e}", file=sys.stderr)
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -263,6 +279,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -333,7 +350,8 @@ def run_ours(args):
         e2e = {"value": frames_step * n_e2e / float(dt.item()), "unit": "frames/s",
                "h2d_bytes_per_step": int(S * n_in * 4 * world), "d2h_bytes_per_step": int(S * V * F * HOP * 4 * world),
                "steps": n_e2e, "audio_s_per_s": frames_step * n_e2e / float(dt.item()) * HOP / FS,
-               "api": "pv_process_host (C ABI, pinned host buffers)"}
+               "api": "pv_process_host (C ABI, pinned host buffers)",
+               "host_cpus_bound": (len(numa) if numa else None)}
         # keep a checksum so that the D2H result is actually consumed
         e2e["checksum"] = float(oh[0, 0, :4096].double().abs().sum())
         del oh
