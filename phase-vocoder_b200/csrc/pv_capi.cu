@@ -418,7 +418,7 @@ int pv_create(const pv_params *params, pv_handle **out)
         if (rc == PV_OK) rc = upload(&h->d_nomS, nomS);
         if (rc == PV_OK && N >= 256 && N <= 2048) {
             std::vector<uint32_t> gath;
-            build_gather_table(N, V, alo.data(), ahi.data(), gath);
+            build_gather_table(N, V, alo.data(), ahi.data(), gath, d.multi);
             rc = upload(&h->d_gather, gath);
         }
     }

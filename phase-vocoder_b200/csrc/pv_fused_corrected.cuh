@@ -52,7 +52,9 @@ struct CTables {
     const uint32_t *gather; // [V][T][9] per-thread packed a_lo | a_hi << 16 in slot order (4.6 KB per voice at N = 2048:
                             // small on purpose -- only ~24 KB of L1 remain next to the shared-memory carve-out)
     unsigned long long Rq[8];
-    unsigned long long beta_q[8];   // pitch ratio, Q32.32: nomS[s] = (beta_q * a_hi * Hs) << (32 - lgN) is recomputed
+    unsigned long long beta_q[8];   // pitch ratio, Q32.32
+    unsigned long long bqs[8];      // (beta_q * Hs) << (32 - lgN): nomS[s] = a_hi * bqs mod 2^64 is recomputed per slot
+    int multi[8];                   // voice has synthesis bins that sum several analysis bins
     float scale;            // gain / N
     int V;
     int Ha;
@@ -110,6 +112,22 @@ PV_DEV float fast_sqrt(float v)
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
 #endif
+}
+
+// a * b + c and (signed) d * b + c modulo 2^64 with a 32-bit multiplier: one wide multiply-add for the low word of
+// b and 32-bit multiply-adds into the high word (the compiler's generic 64 x 64 product costs twice as much)
+PV_DEV unsigned long long mad_u32_u64(uint32_t a, unsigned long long b, unsigned long long c)
+{
+    const unsigned long long r = (unsigned long long)a * (uint32_t)b + c;
+    const uint32_t hi = (uint32_t)(r >> 32) + a * (uint32_t)(b >> 32);
+    return ((unsigned long long)hi << 32) | (uint32_t)r;
+}
+PV_DEV unsigned long long mad_s32_u64(int32_t d, unsigned long long b, unsigned long long c)
+{
+    const unsigned long long r = mad_u32_u64((uint32_t)d, b, c);
+    // (uint32)d = d + 2^32 for negative d: take b << 32 back out
+    const uint32_t hi = (uint32_t)(r >> 32) + (uint32_t)(d >> 31) * (uint32_t)b;
+    return ((unsigned long long)hi << 32) | (uint32_t)r;
 }
 
 PV_DEV float2 cis_turns64(unsigned long long psi)
@@ -422,33 +440,31 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
     // ---- synthesis, one voice at a time ----
     for (int v = 0; v < tb.V; v++) {
         const uint32_t *gt = tb.gather + ((size_t)v * C::T + u) * 9;
-        const unsigned long long bq = tb.beta_q[v];
+        const unsigned long long bqs = tb.bqs[v];
         unsigned long long *ps = psi + (size_t)v * NB;
         const unsigned long long Rq = tb.Rq[v];
+        const bool multi = tb.multi[v] != 0;
         float2 Y[9];
 #pragma unroll
         for (int sl = 0; sl < 9; sl++) {
             Y[sl] = make_float2(0.f, 0.f);
             if (sl == 8 && u != 0) break;
             const int s = slot_bin<B3>(u, sl);
-            const uint32_t ge = PV_LDG(gt + sl);         // a_lo | a_hi << 16
-            const int lo = (int)(ge & 0xffffu), hi = (int)(ge >> 16);
-            // straight-line for the common case (one source bin); an empty range (lo > hi: no analysis bin
-            // maps here) keeps the slot at zero and leaves the accumulator untouched
-            const bool has = lo <= hi;
-            const int l0 = has ? lo : 0, h0 = has ? hi : 0;
-            float m = magS[l0];
+            const uint32_t ge = PV_LDG(gt + sl);         // a_lo | a_hi << 16; no source bin: both = NB, the dummy bin
+            const uint32_t lo = ge & 0xffffu, hi = ge >> 16;
+            float m = magS[lo];                          // 0 at the dummy bin: the slot stays zero
+            if (multi) {                                 // pitch ratio < 1 only (uniform per voice)
 #pragma unroll 1
-            for (int a = l0 + 1; a <= h0; a++) m += magS[a];        // ascending, as the specification sums (rarely taken:
-                                                                    // kept rolled so that it stays out of the hot path)
-            const int32_t d = dS[h0];
+                for (uint32_t a = lo + 1; a <= hi; a++) m += magS[a];   // ascending, as the specification sums
+            }
+            const int32_t d = dS[hi];
+            // psi[s] += nomS[s] + D * Rq (mod 2^64), nomS[s] = a_hi * bqs: 32 x 64-bit multiply-adds
             unsigned long long p;
             if (first) p = (unsigned long long)(uint32_t)d << 32;
-            else p = ps[s] + ((bq * (unsigned long long)(uint32_t)(h0 * Hs)) << (32 - LOG2N)) +
-                     (unsigned long long)((long long)d * (long long)Rq);
-            if (has) ps[s] = p;
+            else p = mad_s32_u64(d, Rq, mad_u32_u64(hi, bqs, ps[s]));
+            if (lo != (uint32_t)NB) ps[s] = p;           // an empty range leaves the accumulator untouched
             const float2 cs = cis_turns64(p);
-            Y[sl] = has ? make_float2(m * cs.x, m * cs.y) : make_float2(0.f, 0.f);
+            Y[sl] = make_float2(m * cs.x, m * cs.y);
         }
         // Hermitian pack (same register pattern as the compat kernel); exp(+2 pi i k/N) = conj(W_N^k)
         float2 Zp[4], Zq[4];

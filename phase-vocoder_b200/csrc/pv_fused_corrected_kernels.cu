@@ -119,6 +119,7 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
             if (agg_pf) agg_pf[bin] = 0u;
         }
     } else {
+        if (tid == 0) { magS[NB] = 0.f; dS[NB] = 0; }      // the dummy bin behind empty gather entries (pv_fused_tables.h)
         for (int i = tid; i < V * NB; i += T) psi[i] = cin ? st_psi[i] : 0ull;
         for (int i = tid; i < V * N; i += T) {
             const int ii = i & (N - 1);
@@ -288,7 +289,11 @@ static CTables make_ctables(const PvDev &d, const PvFusedTables &t)
     tb.V = d.V;
     tb.Ha = d.Ha;
     tb.gather = d.gather;
-    for (int v = 0; v < d.V; v++) tb.beta_q[v] = d.beta_q[v];
+    for (int v = 0; v < d.V; v++) {
+        tb.beta_q[v] = d.beta_q[v];
+        tb.bqs[v] = (d.beta_q[v] * (unsigned long long)d.Hs) << (32 - d.lgN);
+        tb.multi[v] = d.multi[v];
+    }
     return tb;
 }
 

@@ -25,6 +25,7 @@ struct PvDev {
     const uint32_t *gather; // V*T*9: per-thread packed a_lo | a_hi << 16 (pv_fused_tables.h)
     uint64_t beta_q[PV_MAX_VOICES];
     uint64_t Rq[PV_MAX_VOICES];
+    int32_t multi[PV_MAX_VOICES];   // voice sums several analysis bins into some synthesis bin (pitch ratio < 1)
 };
 
 // A frame-range segment of one stream: frames [k_begin, k_end) are computed, frames

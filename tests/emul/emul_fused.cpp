@@ -101,12 +101,17 @@ static int run_corrected(const float *x, long n_in, int Ha, int Hs, const float 
     tb.V = V;
     tb.Ha = Ha;
     std::vector<uint32_t> gath;
-    build_gather_table(N, V, a_lo, a_hi, gath);
+    int32_t multi[8] = {};
+    build_gather_table(N, V, a_lo, a_hi, gath, multi);
     tb.gather = gath.data();
-    for (int v = 0; v < V; v++) tb.beta_q[v] = beta_q[v];
+    for (int v = 0; v < V; v++) {
+        tb.beta_q[v] = beta_q[v];
+        tb.bqs[v] = (beta_q[v] * (unsigned long long)Hs) << (32 - LOG2N);
+        tb.multi[v] = multi[v];
+    }
     std::vector<float2> bufA(C::BUF_A), bufB(C::BUF_B);
-    std::vector<float> acc((size_t)V * N, 0.f), ringbuf(N, 0.f), magS(NB);
-    std::vector<int32_t> dS(NB);
+    std::vector<float> acc((size_t)V * N, 0.f), ringbuf(N, 0.f), magS(NB + 3, 0.f);
+    std::vector<int32_t> dS(NB + 3, 0);
     std::vector<unsigned long long> psi((size_t)V * NB, 0ull);
     std::barrier bar(T);
     const bool use_ring = (Ha % 2) == 0 && Ha <= N;
