@@ -401,16 +401,26 @@ def run_ours(args):
         kern_s = (kern_ms * 1e-3 / kern_n) if kern_n else (ms_total * 1e-3 / args.steps)
         achieved = S * F * bytes_per_frame / kern_s / 1e9
         traffic = None          # dram__bytes_read + dram__bytes_write of one ncu --set full capture of this launch shape
+        issue = None            # the limit that actually binds: warp-instruction issue slots (4 per SM and cycle)
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[args.mode]
             if tr["frames_per_launch"] == S * F:
                 traffic = tr["bytes_per_launch"]
+                wpf = tr.get("warp_instructions_per_frame")
+                if wpf:
+                    sms = torch.cuda.get_device_properties(local).multi_processor_count
+                    peak_issue = sms * 4 * (sm_max or 1965.0) * 1e6
+                    issue = {"warp_instructions_per_frame": wpf, "achieved": S * F * wpf / kern_s / 1e9,
+                             "peak": peak_issue / 1e9, "unit": "G warp-instructions/s",
+                             "frac": S * F * wpf / kern_s / peak_issue,
+                             "note": "instruction count from the ncu capture in profiles/, time measured live"}
         except Exception:
             pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "algorithmic_bytes_per_launch": S * F * bytes_per_frame, "peak_source": peak_src, "kernel": "fused stream kernel",
                     "kernel_ms": kern_s * 1e3, "algorithmic_bytes_per_frame": bytes_per_frame,
-                    "note": "fully fused, the path is shared-memory/fp32 bound, not HBM bound (SURVEY fact 5)"}
+                    "note": "fully fused, the path is instruction-issue bound, not HBM bound (SURVEY fact 5): see `issue`",
+                    "issue": issue}
         line = {
             "metric": "STFT frames/s (N=2048,hop=512)", "value": value, "unit": "frames/s",
             "audio_s_per_s": value * HOP / FS, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),

@@ -26,6 +26,7 @@ def offline(pv, x, latency, n_frames):
     ("corrected", 256, 64, 64, 1, 7),         # C4's shape, one hop per block
     ("corrected", 2048, 512, 512, 3, 2),
     ("corrected", 512, 100, 100, 4, 2),       # hop not a multiple of 4: unaligned ring rows
+    ("corrected", 256, 64, 64, 96, 1),        # one long block of one stream: the frame-range split inside the graph
 ])
 def test_blocks_equal_offline_delayed_input(mode, N, Ha, Hs, B, S):
     blocks = 9
