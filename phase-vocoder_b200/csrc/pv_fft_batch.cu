@@ -13,146 +13,24 @@
 #include <cstdint>
 #include <cstdlib>
 
-#include "pv_fft_regs.cuh"
+#include "pv_fft_smem.cuh"
 #include "pv_internal.h"
 
 namespace {
 
-using namespace pvfft;
-
-// one float2 of padding every 16 keeps the stride-16 writes of the first pass conflict free
-__device__ __forceinline__ int pad(int i) { return i + (i >> 4); }
-
-template <int R>
-struct Log2 { static constexpr int v = R == 2 ? 1 : R == 4 ? 2 : R == 8 ? 3 : 4; };
-
-// Twiddles of the pass with Ns = 16 (always the second one): k = idx mod 16 = threadIdx mod 16 for every butterfly
-// of a thread (blockDim is a multiple of 16), so w^r is loop invariant and lives in registers.
-template <int R>
-struct RegTw { float2 w[R]; };
-
-template <int LG_N, int R, int DIR>
-__device__ __forceinline__ RegTw<R> load_reg_tw(const float2 *__restrict__ tw)
-{
-    constexpr int n = 1 << LG_N, LR = Log2<R>::v;
-    RegTw<R> t;
-    const int kb = (threadIdx.x & 15) << (LG_N - 4 - LR);
-    t.w[0] = make_float2(1.f, 0.f);
-#pragma unroll
-    for (int r = 1; r < R; r++) {
-        t.w[r] = __ldg(tw + ((r * kb) & (n - 1)));
-        if (DIR > 0) t.w[r].y = -t.w[r].y;
-    }
-    return t;
-}
-
-struct NoTw { float2 w[1]; };
-
-// One Stockham pass of radix R over `total` = G*n/R butterflies (G transforms of n points side by side).
-// Butterfly idx of a transform reads points idx + r*n/R and, with k = idx mod Ns, writes (idx-k)*R + k + r*Ns.
-// SRC_LIN / DST_LIN: linear indexing (global memory or the unpadded staging buffer), else the padded work buffer.
-// INPLACE: src == dst; every thread owns at most one butterfly (total <= blockDim), so one barrier between its
-// loads and its stores is all the ordering the autosort permutation needs.
-template <int LG_N, int R, int LG_NS, int DIR, bool SRC_LIN, bool DST_LIN, bool INPLACE, class TW>
-__device__ __forceinline__ void stockham_pass(const float2 *src, float2 *dst, int total, const float2 *__restrict__ tw,
-                                              const TW &rtw)
-{
-    constexpr int LR = Log2<R>::v, LG_PER = LG_N - LR, per = 1 << LG_PER, Ns = 1 << LG_NS;
-    static_assert(SRC_LIN || per >= 16, "r*per must stay a multiple of the padding period");
-    if (INPLACE && (int)threadIdx.x >= total) __syncthreads();
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int g = i >> LG_PER, idx = i & (per - 1), k = idx & (Ns - 1);
-        const int base = g << LG_N;
-        float2 v[R];
-        if (SRC_LIN) {
-            const float2 *s = src + base + idx;
-#pragma unroll
-            for (int r = 0; r < R; r++) v[r] = s[r * per];
-        } else {                              // r*per is a multiple of 16: the padding of the offset is a constant
-            const float2 *s = src + pad(base + idx);
-#pragma unroll
-            for (int r = 0; r < R; r++) v[r] = s[r * per + r * per / 16];
-        }
-        if constexpr (LG_NS == 4) {
-#pragma unroll
-            for (int r = 1; r < R; r++) v[r] = cmul(v[r], rtw.w[r]);
-        } else if constexpr (LG_NS > 0) {
-            // w^r, w = exp(DIR * 2 pi i k / (Ns R)); up to four table loads, the other powers are products
-            const int kb = k << (LG_N - LG_NS - LR);
-            float2 w[R];
-            w[1] = __ldg(tw + kb);
-            if (R > 2) w[2] = __ldg(tw + 2 * kb);
-            if (R > 4) w[4] = __ldg(tw + 4 * kb);
-            if (R > 8) w[8] = __ldg(tw + 8 * kb);
-            if (DIR > 0) {
-                w[1].y = -w[1].y;
-                if (R > 2) w[2].y = -w[2].y;
-                if (R > 4) w[4].y = -w[4].y;
-                if (R > 8) w[8].y = -w[8].y;
-            }
-            if (R > 2) w[3] = cmul(w[2], w[1]);
-            if (R > 4) { w[5] = cmul(w[4], w[1]); w[6] = cmul(w[4], w[2]); w[7] = cmul(w[4], w[3]); }
-            if (R > 8) {
-#pragma unroll
-                for (int r = 9; r < R; r++) w[r] = cmul(w[8], w[r - 8]);
-            }
-#pragma unroll
-            for (int r = 1; r < R; r++) v[r] = cmul(v[r], w[r]);
-        }
-        dft<R, DIR>(v);
-        if (INPLACE) __syncthreads();
-        const int j0 = base + ((idx - k) << LR) + k;
-        if (DST_LIN) {
-            float2 *d = dst + j0;
-#pragma unroll
-            for (int r = 0; r < R; r++) d[r * Ns] = v[r];
-        } else if (Ns >= 16) {
-            float2 *d = dst + pad(j0);
-#pragma unroll
-            for (int r = 0; r < R; r++) d[r * Ns + r * Ns / 16] = v[r];
-        } else {                              // Ns == 1: j0 is a multiple of 16, the R outputs are one padded row
-            float2 *d = dst + pad(j0);
-#pragma unroll
-            for (int r = 0; r < R; r++) d[r] = v[r];
-        }
-    }
-}
-
-template <int LG_N>
-struct SecondRadix { static constexpr int v = (LG_N - 4 >= 4) ? 16 : (1 << (LG_N - 4)); };
-
-// Passes after the first one, for n = 2^LG_N >= 32: radix 16 with Ns = 16, 256 in place while more than 16 points
-// per butterfly column remain, then one pass of radix n / Ns straight to global memory.
-template <int LG_N, int DIR, class TW2>
-__device__ __forceinline__ void remaining_passes(float2 *work, float2 *dst, int tot16, const float2 *tw, const TW2 &tw2)
-{
-    NoTw none;
-    constexpr int REST = LG_N - 4;            // log2 of what is left after the first pass
-    if constexpr (REST <= 4) {
-        stockham_pass<LG_N, (1 << REST), 4, DIR, false, true, false>(work, dst, tot16 * (16 >> REST), tw, tw2);
-    } else {
-        stockham_pass<LG_N, 16, 4, DIR, false, false, true>(work, work, tot16, tw, tw2);
-        __syncthreads();
-        if constexpr (REST <= 8) {
-            stockham_pass<LG_N, (1 << (REST - 4)), 8, DIR, false, true, false>(work, dst, tot16 * (16 >> (REST - 4)), tw, none);
-        } else {
-            stockham_pass<LG_N, 16, 8, DIR, false, false, true>(work, work, tot16, tw, none);
-            __syncthreads();
-            stockham_pass<LG_N, (1 << (REST - 8)), 12, DIR, false, true, false>(work, dst, tot16 * (16 >> (REST - 8)), tw, none);
-        }
-    }
-}
+using namespace pvsmem;
 
 // grid: ceil(batch / G) CTAs, G transforms each; blockDim = a multiple of 32 >= G*n/16
 template <int LG_N, int DIR>
 __global__ void __launch_bounds__(512)
 fft_batch_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, int G, long long batch,
-                 const float2 *__restrict__ tw)
+                 const float2 *__restrict__ twp)
 {
     extern __shared__ float2 sm[];
     const long long t0 = (long long)blockIdx.x * G;
     const int g_here = (int)(batch - t0 < G ? batch - t0 : G);
     const int tot16 = (g_here << LG_N) >> 4;
+    const FullTw tw{twp};
     const auto tw2 = load_reg_tw<LG_N, SecondRadix<LG_N>::v, DIR>(tw);
     NoTw none;
     stockham_pass<LG_N, 16, 0, DIR, true, false, false>(in + (t0 << LG_N), sm, tot16, tw, none);
@@ -187,12 +65,13 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 template <int LG_N, int DIR>
 __global__ void __launch_bounds__(512)
 fft_batch_pipelined_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, int G, long long batch,
-                           const float2 *__restrict__ tw)
+                           const float2 *__restrict__ twp)
 {
     extern __shared__ float2 sm[];
     const int tile_pts = G << LG_N;
     float2 *stage = sm, *work = sm + tile_pts;
     const long long n_tiles = (batch + G - 1) / G;
+    const FullTw tw{twp};
     const auto tw2 = load_reg_tw<LG_N, SecondRadix<LG_N>::v, DIR>(tw);
     auto prefetch = [&](long long t) {
         const long long left = batch - t * G;

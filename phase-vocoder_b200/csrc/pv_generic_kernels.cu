@@ -20,6 +20,7 @@
 //   I emit hop            src/main.cpp:281-295
 #include <algorithm>
 
+#include "pv_fft_smem.cuh"
 #include "pv_internal.h"
 
 namespace {
@@ -108,6 +109,65 @@ __device__ float2 *fft_stockham4(float2 *x, float2 *y, int M, int tws, const flo
         float2 *t = x; x = y; y = t;
     }
     return x;
+}
+
+// ---- radix-16 Stockham (pv_fft_smem.cuh) for the stream kernels ----
+// exp(-2 pi i k / M) out of the handle's half circle of 2N-th roots: tw[j] = exp(-j pi j / N), j < N.
+struct HalfTw {
+    const float2 *p;
+    int stride, half;                                // stride = 2N / M, half = M / 2
+    __device__ __forceinline__ float2 operator()(int k) const
+    {
+        const bool neg = k >= half;
+        float2 w = p[(neg ? k - half : k) * stride];
+        if (neg) { w.x = -w.x; w.y = -w.y; }
+        return w;
+    }
+};
+
+template <int LG, int DIR>
+__device__ __forceinline__ void fft16_fixed(float2 *x, float2 *work, const HalfTw &tw)
+{
+    using namespace pvsmem;
+    constexpr int tot16 = 1 << (LG - 4);
+    const auto tw2 = load_reg_tw<LG, SecondRadix<LG>::v, DIR>(tw);
+    NoTw none;
+    stockham_pass<LG, 16, 0, DIR, true, false, false>(x, work, tot16, tw, none);
+    __syncthreads();
+    remaining_passes<LG, DIR>(work, x, tot16, tw, tw2);
+    __syncthreads();
+}
+
+// One compiled copy per direction for all the kernels of this file (the transform works through shared memory
+// only, so an out-of-line call costs nothing that matters).
+template <int DIR>
+__device__ __noinline__ void fft16_dispatch(float2 *x, float2 *work, int M, HalfTw tw)
+{
+    switch (M) {
+        case 64: fft16_fixed<6, DIR>(x, work, tw); break;
+        case 128: fft16_fixed<7, DIR>(x, work, tw); break;
+        case 256: fft16_fixed<8, DIR>(x, work, tw); break;
+        case 512: fft16_fixed<9, DIR>(x, work, tw); break;
+        case 1024: fft16_fixed<10, DIR>(x, work, tw); break;
+        case 2048: fft16_fixed<11, DIR>(x, work, tw); break;
+        default: fft16_fixed<12, DIR>(x, work, tw); break;
+    }
+}
+
+// Work-buffer elements fft_auto needs behind an M-point transform (one float2 of padding every 16).
+__host__ __device__ constexpr int fft_work_elems(int M) { return M + M / 16 + 2; }
+
+// M-point transform of x (linear) with y (>= fft_work_elems(M)) as scratch; returns the buffer holding the result.
+// 64 <= M <= 4096 with at least M/16 threads: radix-16 passes, result back in x.  Else the radix-4 ping-pong.
+__device__ float2 *fft_auto(float2 *x, float2 *y, int M, int tws, const float2 *__restrict__ tw, int N, bool inverse)
+{
+    if (M >= 64 && M <= 4096 && (M >> 4) <= (int)blockDim.x && (blockDim.x & 15) == 0) {
+        const HalfTw t{tw, tws, M >> 1};
+        if (inverse) fft16_dispatch<1>(x, y, M, t);
+        else fft16_dispatch<-1>(x, y, M, t);
+        return x;
+    }
+    return fft_stockham4(x, y, M, tws, tw, N, inverse);
 }
 
 // Steps A+B: window, zero-phase shift, zero pad to 2N, packed as N complex points.
@@ -286,7 +346,7 @@ compat_generic_kernel(PvDev d, PvProcessArgs a)
     extern __shared__ float2 sm[];
     const int N = d.N, h = N >> 1;
     float2 *bufA = sm, *bufB = sm + N;
-    float *acc = reinterpret_cast<float *>(sm + 2 * N);
+    float *acc = reinterpret_cast<float *>(sm + N + fft_work_elems(N));
     const PvSegment seg = a.segs[blockIdx.x];
     const float *in = a.in + seg.stream * a.in_stride;
     float *out = a.out + seg.stream * a.out_stream_stride;
@@ -303,12 +363,12 @@ compat_generic_kernel(PvDev d, PvProcessArgs a)
         if (analysed) {
             load_frame_compat(bufA, in, k * (int64_t)d.Ha, a.n_in, d);
             __syncthreads();
-            float2 *C = fft_stockham4(bufA, bufB, N, 2, d.tw, d.N, false);
+            float2 *C = fft_auto(bufA, bufB, N, 2, d.tw, d.N, false);
             float2 *Z = (C == bufA) ? bufB : bufA;
             build_inverse_input(Z, [&](int kk) {
                 return polar_to_rect_d2(mag_phase(split_bin(C, kk, d), d.flags)); }, d);
             __syncthreads();
-            r = fft_stockham4(Z, C, h, 4, d.tw, d.N, true);
+            r = fft_auto(Z, C, h, 4, d.tw, d.N, true);
         }
         ola_accumulate(acc, r, pos0, !analysed, d);
         __syncthreads();
@@ -339,8 +399,8 @@ corrected_generic_kernel(PvDev d, PvProcessArgs a)
 {
     extern __shared__ float2 sm[];
     const int N = d.N, M = N >> 1, NB = M + 1, V = d.V, Hs = d.Hs;
-    float2 *bufA = sm, *bufB = sm + NB, *Ys = sm + 2 * NB;
-    float *magS = reinterpret_cast<float *>(sm + 3 * NB);
+    float2 *bufA = sm, *bufB = sm + NB, *Ys = bufB + fft_work_elems(M);
+    float *magS = reinterpret_cast<float *>(Ys + NB);
     int32_t *dS = reinterpret_cast<int32_t *>(magS + NB);
     const PvSegment seg = a.segs[blockIdx.x];
     const float *in = a.in + seg.stream * a.in_stride;
@@ -373,7 +433,7 @@ corrected_generic_kernel(PvDev d, PvProcessArgs a)
             bufA[m] = make_float2(x0 * d.win[i], x1 * d.win[i + 1]);
         }
         __syncthreads();
-        const float2 *C = fft_stockham4(bufA, bufB, M, 4, d.tw, d.N, false);
+        const float2 *C = fft_auto(bufA, bufB, M, 4, d.tw, d.N, false);
         for (int kk = threadIdx.x; kk <= M / 2; kk += blockDim.x) {
             float2 xk, xm;
             if (kk == 0) {
@@ -426,7 +486,7 @@ corrected_generic_kernel(PvDev d, PvProcessArgs a)
             float2 *Z = bufA;
             build_inverse_input(Z, [&](int kk) { return Ys[kk]; }, d);
             __syncthreads();
-            const float2 *r = fft_stockham4(Z, bufB, M, 4, d.tw, d.N, true);
+            const float2 *r = fft_auto(Z, bufB, M, 4, d.tw, d.N, true);
             float *ac = acc + (size_t)v * N;
             ola_accumulate(ac, r, pos0, false, d, scale);
             __syncthreads();
@@ -460,7 +520,7 @@ aggregate_generic_kernel(PvDev d, PvAggArgs a)
     extern __shared__ float2 sm[];
     const int N = d.N, M = N >> 1, NB = M + 1, lsh = 32 - d.lgN;
     float2 *bufA = sm, *bufB = sm + NB;
-    uint32_t *Pp = reinterpret_cast<uint32_t *>(sm + 2 * NB);
+    uint32_t *Pp = reinterpret_cast<uint32_t *>(bufB + fft_work_elems(M));
     const long long sg = blockIdx.x;
     const PvSegment seg = a.segs[sg];
     const float *in = a.in + seg.stream * a.in_stride;
@@ -484,7 +544,7 @@ aggregate_generic_kernel(PvDev d, PvAggArgs a)
             bufA[m] = make_float2(x0 * d.win[i], x1 * d.win[i + 1]);
         }
         __syncthreads();
-        const float2 *C = fft_stockham4(bufA, bufB, M, 4, d.tw, d.N, false);
+        const float2 *C = fft_auto(bufA, bufB, M, 4, d.tw, d.N, false);
         for (int kk = threadIdx.x; kk <= M / 2; kk += blockDim.x) {
             float2 xk, xm;
             if (kk == 0) {
@@ -523,7 +583,7 @@ cudaError_t pv_launch_aggregate_generic(const PvDev &d, const PvAggArgs &a, cuda
 {
     if (a.n_segs <= 0) return cudaSuccess;
     const size_t NB = d.N / 2 + 1;
-    const size_t smem = sizeof(float2) * 2 * NB + sizeof(uint32_t) * NB;
+    const size_t smem = sizeof(float2) * (NB + fft_work_elems(d.N / 2)) + sizeof(uint32_t) * NB;
     cudaError_t e = cudaFuncSetAttribute(aggregate_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     aggregate_generic_kernel<<<(unsigned)a.n_segs, generic_threads(d.N), smem, st>>>(d, a);
@@ -603,7 +663,7 @@ cudaError_t pv_launch_corrected_generic(const PvDev &d, const PvProcessArgs &a, 
 {
     if (a.n_segs <= 0) return cudaSuccess;
     const size_t NB = d.N / 2 + 1;
-    const size_t smem = std::max(sizeof(float2) * 3 * NB + sizeof(float) * 2 * NB, sizeof(float) * (size_t)d.N);
+    const size_t smem = std::max(sizeof(float2) * (2 * NB + fft_work_elems(d.N / 2)) + sizeof(float) * 2 * NB, sizeof(float) * (size_t)d.N);
     cudaError_t e = cudaFuncSetAttribute(corrected_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     corrected_generic_kernel<<<a.n_segs, generic_threads(d.N), smem, st>>>(d, a);
@@ -656,7 +716,7 @@ cudaError_t pv_launch_test_overlap_add(const PvDev &d, const float *in, const fl
 cudaError_t pv_launch_compat_generic(const PvDev &d, const PvProcessArgs &a, cudaStream_t st)
 {
     if (a.n_segs <= 0) return cudaSuccess;
-    const size_t smem = sizeof(float2) * 2 * (size_t)d.N + sizeof(float) * (size_t)d.N;
+    const size_t smem = sizeof(float2) * (size_t)(d.N + fft_work_elems(d.N)) + sizeof(float) * (size_t)d.N;
     cudaError_t e = cudaFuncSetAttribute(compat_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     compat_generic_kernel<<<a.n_segs, generic_threads(d.N), smem, st>>>(d, a);
