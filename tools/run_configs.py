@@ -98,7 +98,25 @@ def realtime_step(streams=4096, N=256, H=64, betas=(1.0, 2 ** (4 / 12), 2 ** (7 
         rt.close()
 
 
+def sweep():
+    """Window sweep at equal total audio per launch (profiles/r01_window_sweep.md)."""
+    print("| mode | window | Ha/Hs | streams x frames | ms/launch | frames/s | audio-s/s | algorithmic GB/s | SNR dB |")
+    print("|---|---|---|---|---|---|---|---|---|")
+    noisy = lambda n, s: multitone(n, seed=s, noise=1e-3)
+    for mode, betas, label in (("compat", [1.0], "compat"), ("corrected", [f32(2 ** (7 / 12))], "corrected (+7 st)")):
+        for N in (256, 512, 1024, 2048):
+            streams, frames, H = 2368 * 2048 // N // 2, 1720, N // 4
+            import io, contextlib
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                run("x", N, H, H, mode, betas, streams, frames, 44100, noisy, check_frames=60)
+            c = [t.strip() for t in buf.getvalue().strip().split("|")]
+            print(f"| {label} | {N} | {H}/{H} | {streams} x {frames} | {c[7]} | {c[8]} | {c[9]} | {c[10]} | {c[11]} |", flush=True)
+
+
 def main():
+    if "--sweep" in sys.argv:
+        return sweep()
     print("| config | window | Ha/Hs | mode | voices | streams x frames | ms/launch | frames/s | audio-s/s (input) | "
           "algorithmic GB/s | worst SNR vs fp64 oracle (dB) |")
     print("|---|---|---|---|---|---|---|---|---|---|---|")
