@@ -865,49 +865,61 @@ static int process_host_impl(pv_handle *h, const void *in_v, int64_t n_streams, 
     unsigned char *out = (unsigned char *)out_v;
     int16_t *d16 = reinterpret_cast<int16_t *>(h->d_in16), *o16 = reinterpret_cast<int16_t *>(h->d_out16);
     int64_t e0 = 0;                                       // input samples already on the device
+    // inside the pipeline a failed call must not return before the streams have drained: the caller's buffers are
+    // still the source / target of copies in flight
+#define PIPE_CUDA(call)                                                                                         \
+    do {                                                                                                        \
+        cudaError_t e_ = (call);                                                                                \
+        if (e_ != cudaSuccess) {                                                                                \
+            rc = fail(PV_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            goto drain;                                                                                         \
+        }                                                                                                       \
+    } while (0)
     for (int64_t c = 0; c < n_chunks && rc == PV_OK; ++c) {
         const int64_t k0 = c * fc, k1 = std::min(n_frames, k0 + fc);
         const int64_t e1 = std::max(e0, std::min(n_in, (k1 - 1) * Ha + N));
         cudaEvent_t ev_in = h->pipe_events[(size_t)(2 * c)], ev_k = h->pipe_events[(size_t)(2 * c + 1)];
         if (e1 > e0) {
             if (PCM16)
-                PV_CUDA(cudaMemcpy2DAsync(d16 + e0, 2 * n_in_p, in + (size_t)e0 * 2, 2 * in_stride, 2 * (size_t)(e1 - e0),
+                PIPE_CUDA(cudaMemcpy2DAsync(d16 + e0, 2 * n_in_p, in + (size_t)e0 * 2, 2 * in_stride, 2 * (size_t)(e1 - e0),
                                           (size_t)n_streams, cudaMemcpyHostToDevice, s_in));
             else
-                PV_CUDA(cudaMemcpy2DAsync(h->d_in + e0, 4 * n_in_p, in + (size_t)e0 * 4, 4 * in_stride, 4 * (size_t)(e1 - e0),
+                PIPE_CUDA(cudaMemcpy2DAsync(h->d_in + e0, 4 * n_in_p, in + (size_t)e0 * 4, 4 * in_stride, 4 * (size_t)(e1 - e0),
                                           (size_t)n_streams, cudaMemcpyHostToDevice, s_in));
         }
-        PV_CUDA(cudaEventRecord(ev_in, s_in));
-        PV_CUDA(cudaStreamWaitEvent(s_k, ev_in, 0));
+        PIPE_CUDA(cudaEventRecord(ev_in, s_in));
+        PIPE_CUDA(cudaStreamWaitEvent(s_k, ev_in, 0));
         if (PCM16 && e1 > e0) {
-            PV_CUDA(pv_launch_pcm16_to_float(d16, h->d_in, n_streams, n_in_p, e0 & ~int64_t(3), e1, n_in, s_k));
+            PIPE_CUDA(pv_launch_pcm16_to_float(d16, h->d_in, n_streams, n_in_p, e0 & ~int64_t(3), e1, n_in, s_k));
             h->launches++;
         }
         e0 = e1;
         const int64_t an = std::min(k1 - k0, std::max<int64_t>(0, n_analysed - k0));
         rc = process_impl(h, h->d_in + k0 * Ha, n_streams, n_streams, n_in_p, std::max<int64_t>(0, n_in - k0 * Ha), an, k1 - k0, 0,
                           h->d_out + k0 * Hs, V * n_out, n_out, use_state ? h->d_state : nullptr, cflags, s_k);
-        if (rc != PV_OK) break;
+        if (rc != PV_OK) goto drain;
         if (PCM16) {
-            PV_CUDA(pv_launch_float_to_pcm16(h->d_out, o16, n_streams * V, n_out, k0 * Hs, k1 * Hs, s_k));
+            PIPE_CUDA(pv_launch_float_to_pcm16(h->d_out, o16, n_streams * V, n_out, k0 * Hs, k1 * Hs, s_k));
             h->launches++;
         }
-        PV_CUDA(cudaEventRecord(ev_k, s_k));
-        PV_CUDA(cudaStreamWaitEvent(s_out, ev_k, 0));
+        PIPE_CUDA(cudaEventRecord(ev_k, s_k));
+        PIPE_CUDA(cudaStreamWaitEvent(s_out, ev_k, 0));
         const size_t w = (size_t)(k1 - k0) * Hs;
         for (int64_t v = 0; v < V; v++) {
             if (PCM16)
-                PV_CUDA(cudaMemcpy2DAsync(out + ((size_t)v * out_voice_stride + (size_t)k0 * Hs) * 2, 2 * out_stream_stride,
+                PIPE_CUDA(cudaMemcpy2DAsync(out + ((size_t)v * out_voice_stride + (size_t)k0 * Hs) * 2, 2 * out_stream_stride,
                                           o16 + v * n_out + k0 * Hs, 2 * V * n_out, 2 * w, (size_t)n_streams,
                                           cudaMemcpyDeviceToHost, s_out));
             else
-                PV_CUDA(cudaMemcpy2DAsync(out + ((size_t)v * out_voice_stride + (size_t)k0 * Hs) * 4, 4 * out_stream_stride,
+                PIPE_CUDA(cudaMemcpy2DAsync(out + ((size_t)v * out_voice_stride + (size_t)k0 * Hs) * 4, 4 * out_stream_stride,
                                           h->d_out + v * n_out + k0 * Hs, 4 * V * n_out, 4 * w, (size_t)n_streams,
                                           cudaMemcpyDeviceToHost, s_out));
         }
     }
     if (rc == PV_OK && use_state && (flags & PV_PROCESS_CARRY_OUT))
-        PV_CUDA(cudaMemcpyAsync(state, h->d_state, (size_t)n_streams * sb, cudaMemcpyDeviceToHost, s_k));
+        PIPE_CUDA(cudaMemcpyAsync(state, h->d_state, (size_t)n_streams * sb, cudaMemcpyDeviceToHost, s_k));
+#undef PIPE_CUDA
+drain:
     for (auto &ps : h->pipe) {
         cudaError_t e = cudaStreamSynchronize(ps);
         if (e != cudaSuccess && rc == PV_OK) rc = fail(PV_ERR_CUDA, "pipeline stream: %s", cudaGetErrorString(e));
