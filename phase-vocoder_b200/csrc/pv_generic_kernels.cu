@@ -394,6 +394,9 @@ __device__ __forceinline__ uint32_t g_phase_turns32(float re, float im)
     return (uint32_t)__float2ll_rn(t * 4294967296.0f);
 }
 
+// SMEM_STATE: the stream state is copied into shared memory for the segment (when it fits next to the transform
+// buffers with two CTAs per SM) and written back at the end; otherwise every frame works on it in global memory.
+template <bool SMEM_STATE>
 __global__ void __launch_bounds__(kGenericThreads)
 corrected_generic_kernel(PvDev d, PvProcessArgs a)
 {
@@ -407,11 +410,19 @@ corrected_generic_kernel(PvDev d, PvProcessArgs a)
     float *out = a.out + seg.stream * a.out_stream_stride;
     unsigned char *state = a.state + (long long)seg.state_idx * a.state_stride;   // always present (caller or scratch)
     uint32_t *hdr = reinterpret_cast<uint32_t *>(state);
-    uint32_t *Pprev = hdr + 2;
-    unsigned long long *psi = reinterpret_cast<unsigned long long *>(state + 8 + ((NB * 4 + 7) / 8) * 8);
-    float *acc = reinterpret_cast<float *>(psi + (size_t)V * NB);
+    uint32_t *gPprev = hdr + 2;
+    unsigned long long *gpsi = reinterpret_cast<unsigned long long *>(state + 8 + ((NB * 4 + 7) / 8) * 8);
+    float *gacc = reinterpret_cast<float *>(gpsi + (size_t)V * NB);
+    unsigned long long *psi = SMEM_STATE ? reinterpret_cast<unsigned long long *>(dS + NB) : gpsi;   // 8*NB bytes of mag + D: aligned
+    float *acc = SMEM_STATE ? reinterpret_cast<float *>(psi + (size_t)V * NB) : gacc;
+    uint32_t *Pprev = SMEM_STATE ? reinterpret_cast<uint32_t *>(acc + (size_t)V * N) : gPprev;
     const float scale = d.gain / (float)N;
     const int lsh = 32 - d.lgN;
+    if (SMEM_STATE && seg.carry_in) {
+        for (int i = threadIdx.x; i < NB; i += blockDim.x) Pprev[i] = gPprev[i];
+        for (int i = threadIdx.x; i < V * NB; i += blockDim.x) psi[i] = gpsi[i];
+        for (int i = threadIdx.x; i < V * N; i += blockDim.x) acc[i] = gacc[i];
+    }
 
     // The state stores each voice's accumulated frame linearly (index 0 = first sample of the LAST frame).
     // It is used in place as a ring: the next frame starts at linear index Hs, and its last Hs samples
@@ -502,6 +513,13 @@ corrected_generic_kernel(PvDev d, PvProcessArgs a)
     // leave the state in its linear form: accumulated frame after the last frame at index 0
     const int plast = (pos0 - Hs) & (N - 1);
     if (threadIdx.x == 0) { hdr[0] = 1u; hdr[1] = 0u; }
+    if (SMEM_STATE) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < NB; i += blockDim.x) gPprev[i] = Pprev[i];
+        for (int i = threadIdx.x; i < V * NB; i += blockDim.x) gpsi[i] = psi[i];
+        for (int i = threadIdx.x; i < V * N; i += blockDim.x) gacc[i] = acc[(i & ~(N - 1)) + ((plast + i) & (N - 1))];
+        return;
+    }
     for (int v = 0; v < V; v++) {
         float *ac = acc + (size_t)v * N;
         // rotate the ring by plast through shared memory
@@ -664,9 +682,16 @@ cudaError_t pv_launch_corrected_generic(const PvDev &d, const PvProcessArgs &a, 
     if (a.n_segs <= 0) return cudaSuccess;
     const size_t NB = d.N / 2 + 1;
     const size_t smem = std::max(sizeof(float2) * (2 * NB + fft_work_elems(d.N / 2)) + sizeof(float) * 2 * NB, sizeof(float) * (size_t)d.N);
-    cudaError_t e = cudaFuncSetAttribute(corrected_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t with_state = smem + (size_t)d.V * NB * 8 + (size_t)d.V * d.N * 4 + NB * 4;
+    if (with_state <= 113 * 1024) {         // two CTAs per SM still fit
+        cudaError_t e = cudaFuncSetAttribute(corrected_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_state);
+        if (e != cudaSuccess) return e;
+        corrected_generic_kernel<true><<<a.n_segs, generic_threads(d.N), with_state, st>>>(d, a);
+        return cudaGetLastError();
+    }
+    cudaError_t e = cudaFuncSetAttribute(corrected_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    corrected_generic_kernel<<<a.n_segs, generic_threads(d.N), smem, st>>>(d, a);
+    corrected_generic_kernel<false><<<a.n_segs, generic_threads(d.N), smem, st>>>(d, a);
     return cudaGetLastError();
 }
 
