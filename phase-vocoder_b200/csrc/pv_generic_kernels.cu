@@ -19,8 +19,10 @@
 //   H overlap-add         karnel/kernel.cu:111-119
 //   I emit hop            src/main.cpp:281-295
 #include <algorithm>
+#include <cstdlib>
 
 #include "pv_fft_smem.cuh"
+#include "pv_fused_corrected.cuh"
 #include "pv_internal.h"
 
 namespace {
@@ -384,6 +386,371 @@ compat_generic_kernel(PvDev d, PvProcessArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Large-window compat stream kernel (window 4096 = 16^3 packed points): the whole frame lives in ONE padded
+// shared-memory buffer.  Pass 1 reads the windowed, zero-phase, zero-padded frame straight from global memory
+// (the zero half prunes the butterfly), every later pass of both transforms runs in place (load, barrier,
+// store), the real-FFT split / collapsed steps D+E / Hermitian pack go through registers between two barriers,
+// and the overlap-add ring sits next to the buffer: 51 KB per CTA of N/16 threads instead of 84 KB, three CTAs
+// per SM by registers.  Same segment contract as compat_generic_kernel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 compat_map_fast(float2 X, bool nan_compat)
+{
+    // steps D+E collapsed (re' = |Re X|, im' = Re X Im X / |X|), as in the tuned kernels (pv_fused_core.cuh)
+    const float m2 = X.x * X.x + X.y * X.y;
+    if (m2 == 0.f) {
+        const float z = nan_compat ? __builtin_nanf("") : 0.f;
+        return make_float2(z, z);
+    }
+    if (m2 < 1.17549435e-38f) return make_float2(fabsf(X.x), 0.f);
+    return make_float2(fabsf(X.x), X.x * X.y * rsqrtf(m2));
+}
+
+template <int LG_N>
+__global__ void __launch_bounds__(1 << (LG_N - 4), 3)
+compat_inplace_kernel(PvDev d, PvProcessArgs a)
+{
+    using namespace pvsmem;
+    constexpr int N = 1 << LG_N, T = N / 16, H = N / 2, Q = N / 4, J = Q / T + 1;
+    static_assert(LG_N == 12, "the in-place schedule below is written for 16^3 packed points");
+    extern __shared__ float2 sm[];
+    float2 *W = sm;
+    float *acc = reinterpret_cast<float *>(sm + fft_work_elems(N));
+    const int tid = threadIdx.x;
+    const PvSegment seg = a.segs[blockIdx.x];
+    const float *in = a.in + seg.stream * a.in_stride;
+    float *out = a.out + seg.stream * a.out_stream_stride;
+    float *state = a.state ? reinterpret_cast<float *>(a.state + seg.stream * a.state_stride) : nullptr;
+    const bool nan_compat = (d.flags & PV_FLAG_NAN_COMPAT) != 0;
+    const int Hs = d.Hs, keep = N - Hs;
+    const float scale = 1.0f / (float)N;
+    const HalfTw twF{d.tw, 2, N / 2}, twI{d.tw, 4, H / 2};
+    NoTw none;
+
+    for (int i = tid; i < N; i += T) acc[i] = (seg.carry_in && state && i + Hs < N) ? state[i + Hs] : 0.f;
+    __syncthreads();
+
+    int pos0 = 0;
+    for (int64_t k = seg.k_begin; k < seg.k_end; ++k) {
+        const bool analysed = k < a.n_analysed;
+        if (analysed) {
+            {   // forward pass 1 (Ns = 1): c[n] = f[N/2 + 2n] for n < N/4, f[2(n - 3N/4)] for n >= 3N/4, else 0
+                const int64_t base = k * (int64_t)d.Ha;
+                float2 v[16];
+#pragma unroll
+                for (int r = 0; r < 16; r++) {
+                    if (r >= 4 && r < 12) { v[r] = make_float2(0.f, 0.f); continue; }
+                    const int n = tid + r * T;
+                    const int i = r < 4 ? H + 2 * n : 2 * (n - 3 * Q);
+                    const int64_t g = base + i;
+                    const float x0 = g < a.n_in ? in[g] : 0.f, x1 = g + 1 < a.n_in ? in[g + 1] : 0.f;
+                    v[r] = make_float2(x0 * d.win[i], x1 * d.win[i + 1]);
+                }
+                dft_pruned_fwd<16>(v);
+                float2 *dst = W + pad(tid * 16);
+#pragma unroll
+                for (int r = 0; r < 16; r++) dst[r] = v[r];
+            }
+            __syncthreads();
+            {
+                const auto tw2 = load_reg_tw<LG_N, 16, -1>(twF);
+                stockham_pass<LG_N, 16, 4, -1, false, false, true>(W, W, T, twF, tw2);
+            }
+            __syncthreads();
+            stockham_pass<LG_N, 16, 8, -1, false, false, true>(W, W, T, twF, none);
+            __syncthreads();
+            // split + steps D/E + Hermitian pack for kk and H - kk, through registers
+            float2 z0[J], z1[J];
+#pragma unroll
+            for (int j = 0; j < J; j++) {
+                const int kk = tid + j * T;
+                if (kk > Q) break;
+                auto bin = [&](int b) -> float2 {      // bin b <= N/2 of the 2N-point real spectrum
+                    const float2 aa = W[pad(b)];
+                    float2 bb = W[pad((N - b) & (N - 1))];
+                    bb.y = -bb.y;
+                    const float2 e = make_float2(0.5f * (aa.x + bb.x), 0.5f * (aa.y + bb.y));
+                    const float2 dd = make_float2(aa.x - bb.x, aa.y - bb.y);
+                    const float2 o = make_float2(0.5f * dd.y, -0.5f * dd.x);
+                    const float2 t = cmul(d.tw[b], o);
+                    return make_float2(e.x + t.x, e.y + t.y);
+                };
+                float2 yk = compat_map_fast(bin(kk), nan_compat), ym = compat_map_fast(bin(H - kk), nan_compat);
+                if (kk == 0) { yk.y = 0.f; ym.y = 0.f; }            // C2R ignores Im of bins 0 and N/2
+                const float2 t = d.tw[2 * kk];                       // e^{-2 pi i kk / N}
+                z0[j] = herm_pack(yk, ym, make_float2(t.x, -t.y));
+                z1[j] = herm_pack(ym, yk, make_float2(-t.x, -t.y));
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < J; j++) {
+                const int kk = tid + j * T;
+                if (kk > Q) break;
+                W[pad(kk)] = z0[j];
+                if (kk != 0 && kk != Q) W[pad(H - kk)] = z1[j];
+            }
+            __syncthreads();
+            // inverse: H = 16 * 16 * 8 packed points, all in place
+            stockham_pass<LG_N - 1, 16, 0, 1, false, false, true>(W, W, H / 16, twI, none);
+            __syncthreads();
+            {
+                const auto tw2 = load_reg_tw<LG_N - 1, 16, 1>(twI);
+                stockham_pass<LG_N - 1, 16, 4, 1, false, false, true>(W, W, H / 16, twI, tw2);
+            }
+            __syncthreads();
+            stockham_pass<LG_N - 1, 8, 8, 1, false, false, true>(W, W, H / 8, twI, none);
+            __syncthreads();
+        }
+        // steps G+H: /N, half swap, window, overlap-add into the ring (the fresh tail replaces what was emitted)
+        for (int n = tid; n < H; n += T) {
+            const float2 v = analysed ? W[pad(n)] : make_float2(0.f, 0.f);
+            const int i = (2 * n + H) & (N - 1);
+            const float y0 = (v.x * scale) * d.win[i], y1 = (v.y * scale) * d.win[i + 1];
+            const int p0 = (pos0 + i) & (N - 1), p1 = (pos0 + i + 1) & (N - 1);
+            acc[p0] = (i < keep ? acc[p0] : 0.f) + y0;
+            acc[p1] = (i + 1 < keep ? acc[p1] : 0.f) + y1;
+        }
+        __syncthreads();
+        if (k >= seg.k_emit)
+            for (int j = tid; j < Hs; j += T) out[k * (int64_t)Hs + j] = acc[(pos0 + j) & (N - 1)];
+        if (seg.carry_out && state && k + 1 == seg.k_end)
+            for (int i = tid; i < N; i += T) state[i] = acc[(pos0 + i) & (N - 1)];
+        __syncthreads();
+        pos0 = (pos0 + Hs) & (N - 1);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Large-window corrected stream kernels (window 4096: 2048 = 16 * 16 * 8 packed points each way), same in-place
+// scheme as compat_inplace_kernel, stream state (previous phase, accumulators, OLA rings) in shared memory.
+// The forward half -- transform, real-FFT split, magnitude and phase -- is ONE out-of-line function shared by the
+// processing kernel and the phase-carry aggregate: both run the very same instructions, so their phases agree
+// bit for bit, which is what makes frame-range splitting and sharding exact.
+// ---------------------------------------------------------------------------------------------
+template <int LG_N>
+__device__ __noinline__ void analysis_inplace(float2 *W, const float *__restrict__ in, long long base, long long n_in,
+                                              const float *__restrict__ win, const float2 *__restrict__ tw, float *magS,
+                                              uint32_t *Pc)
+{
+    using namespace pvsmem;
+    constexpr int N = 1 << LG_N, M = N / 2, T = N / 16, LG_M = LG_N - 1;
+    const int tid = threadIdx.x;
+    const HalfTw twF{tw, 4, M / 2};
+    NoTw none;
+    if (tid < M / 16) {     // forward pass 1 (Ns = 1) straight from global memory: c[m] = windowed pair (M + 2m) mod N
+        float2 v[16];
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const int m = tid + r * (M / 16);
+            const int i = (M + 2 * m) & (N - 1);
+            const long long g = base + i;
+            const float x0 = g < n_in ? in[g] : 0.f, x1 = g + 1 < n_in ? in[g + 1] : 0.f;
+            v[r] = make_float2(x0 * win[i], x1 * win[i + 1]);
+        }
+        dft<16, -1>(v);
+        float2 *dst = W + pad(tid * 16);
+#pragma unroll
+        for (int r = 0; r < 16; r++) dst[r] = v[r];
+    }
+    __syncthreads();
+    {
+        const auto tw2 = load_reg_tw<LG_M, 16, -1>(twF);
+        stockham_pass<LG_M, 16, 4, -1, false, false, true>(W, W, M / 16, twF, tw2);
+    }
+    __syncthreads();
+    stockham_pass<LG_M, 8, 8, -1, false, false, true>(W, W, M / 8, twF, none);
+    __syncthreads();
+    for (int kk = tid; kk <= M / 2; kk += T) {
+        float2 xk, xm;
+        if (kk == 0) {
+            const float2 c0 = W[0];
+            xk = make_float2(c0.x + c0.y, 0.f);
+            xm = make_float2(c0.x - c0.y, 0.f);
+        } else {
+            const float2 aa = W[pad(kk)], bb = W[pad(M - kk)];
+            const float2 e = make_float2(0.5f * (aa.x + bb.x), 0.5f * (aa.y - bb.y));
+            const float2 o = make_float2(0.5f * (aa.y + bb.y), -0.5f * (aa.x - bb.x));
+            const float2 t = cmul(tw[2 * kk], o);          // W_N^k = exp(-j*pi*2k/N)
+            xk = make_float2(e.x + t.x, e.y + t.y);
+            xm = make_float2(e.x - t.x, -(e.y - t.y));
+        }
+        magS[kk] = sqrtf(xk.x * xk.x + xk.y * xk.y);
+        Pc[kk] = pvfused::phase_turns32(xk.x, xk.y);
+        if (kk != M - kk) {
+            magS[M - kk] = sqrtf(xm.x * xm.x + xm.y * xm.y);
+            Pc[M - kk] = pvfused::phase_turns32(xm.x, xm.y);
+        }
+    }
+}
+
+template <int LG_N>
+struct InplaceLayout {
+    static constexpr int N = 1 << LG_N, M = N / 2, NB = M + 1, NBP = (NB + 3) & ~3;
+    // W | mag | phase/D | previous phase | psi[V] | acc[V]
+    static size_t bytes(int V, bool with_state)
+    {
+        size_t b = sizeof(float2) * (size_t)fft_work_elems(M) + 3 * sizeof(float) * NBP;
+        if (with_state) b += (size_t)V * NBP * 8 + (size_t)V * N * 4;
+        return b;
+    }
+};
+
+template <int LG_N>
+__global__ void __launch_bounds__(1 << (LG_N - 4), 3)
+corrected_inplace_kernel(PvDev d, PvProcessArgs a)
+{
+    using namespace pvsmem;
+    using L = InplaceLayout<LG_N>;
+    constexpr int N = L::N, M = L::M, NB = L::NB, NBP = L::NBP, T = N / 16, LG_M = LG_N - 1;
+    extern __shared__ float2 sm[];
+    float2 *W = sm;
+    float *magS = reinterpret_cast<float *>(sm + fft_work_elems(M));
+    uint32_t *Pc = reinterpret_cast<uint32_t *>(magS + NBP);          // phase of the frame, then its D in place
+    int32_t *dS = reinterpret_cast<int32_t *>(Pc);
+    uint32_t *Pprev = Pc + NBP;
+    unsigned long long *psi = reinterpret_cast<unsigned long long *>(Pprev + NBP);
+    const int V = d.V, Hs = d.Hs, tid = threadIdx.x, keep = N - Hs, lsh = 32 - d.lgN;
+    float *acc = reinterpret_cast<float *>(psi + (size_t)V * NBP);
+    const PvSegment seg = a.segs[blockIdx.x];
+    const float *in = a.in + seg.stream * a.in_stride;
+    float *out = a.out + seg.stream * a.out_stream_stride;
+    unsigned char *state = a.state + (long long)seg.state_idx * a.state_stride;   // always present (caller or scratch)
+    uint32_t *hdr = reinterpret_cast<uint32_t *>(state);
+    uint32_t *gPprev = hdr + 2;
+    unsigned long long *gpsi = reinterpret_cast<unsigned long long *>(state + 8 + ((NB * 4 + 7) / 8) * 8);
+    float *gacc = reinterpret_cast<float *>(gpsi + (size_t)V * NB);
+    const float scale = d.gain / (float)N;
+    const HalfTw twI{d.tw, 4, M / 2};
+    NoTw none;
+
+    bool have_prev = seg.carry_in ? hdr[0] != 0 : false;
+    int pos0 = seg.carry_in ? (Hs & (N - 1)) : 0;       // the state keeps each ring linear, last frame at index 0
+    for (int i = tid; i < NB; i += T) Pprev[i] = seg.carry_in ? gPprev[i] : 0u;
+    for (int v = 0; v < V; v++) {
+        for (int i = tid; i < NB; i += T) psi[(size_t)v * NBP + i] = seg.carry_in ? gpsi[(size_t)v * NB + i] : 0ull;
+        for (int i = tid; i < N; i += T) acc[(size_t)v * N + i] = seg.carry_in ? gacc[(size_t)v * N + i] : 0.f;
+    }
+    __syncthreads();
+
+    for (long long k = seg.k_begin; k < seg.k_end; ++k) {
+        analysis_inplace<LG_N>(W, in, k * (long long)d.Ha, a.n_in, d.win, d.tw, magS, Pc);
+        __syncthreads();
+        for (int b = tid; b < NB; b += T) {              // unwrapped phase difference, integer wrap-around
+            const uint32_t P = Pc[b];
+            const uint32_t nomA = ((uint32_t)b * (uint32_t)d.Ha) << lsh;
+            dS[b] = have_prev ? (int32_t)(P - Pprev[b] - nomA) : (int32_t)P;
+            Pprev[b] = P;
+        }
+        __syncthreads();
+        for (int v = 0; v < V; v++) {
+            unsigned long long *ps = psi + (size_t)v * NBP;
+            const unsigned long long Rq = d.Rq[v];
+            auto synth = [&](int s) -> float2 {
+                const int lo = d.a_lo[v * NB + s], hi = d.a_hi[v * NB + s];
+                if (lo > hi) return make_float2(0.f, 0.f);
+                float m = 0.f;
+                for (int b = lo; b <= hi; b++) m += magS[b];
+                const int32_t dd = dS[hi];
+                unsigned long long p;
+                if (!have_prev) p = (unsigned long long)(uint32_t)dd << 32;
+                else p = ps[s] + d.nomS[v * NB + s] + (unsigned long long)((long long)dd * (long long)Rq);
+                ps[s] = p;
+                const float2 cs = pvfused::cis_turns64(p);
+                return make_float2(m * cs.x, m * cs.y);
+            };
+            // Hermitian pack of the N-point inverse: Z[kk], Z[M - kk] from Y[kk], Y[M - kk]; every pair has one owner
+            for (int kk = tid; kk <= M / 2; kk += T) {
+                float2 yk = synth(kk);
+                float2 ym = (kk == M - kk) ? yk : synth(M - kk);
+                if (kk == 0) { yk.y = 0.f; ym.y = 0.f; }            // the inverse ignores Im of bins 0 and N/2
+                const float2 t = d.tw[2 * kk];
+                W[pad(kk)] = herm_pack(yk, ym, make_float2(t.x, -t.y));
+                if (kk != 0 && kk != M / 2) W[pad(M - kk)] = herm_pack(ym, yk, make_float2(-t.x, -t.y));
+            }
+            __syncthreads();
+            stockham_pass<LG_M, 16, 0, 1, false, false, true>(W, W, M / 16, twI, none);
+            __syncthreads();
+            {
+                const auto tw2 = load_reg_tw<LG_M, 16, 1>(twI);
+                stockham_pass<LG_M, 16, 4, 1, false, false, true>(W, W, M / 16, twI, tw2);
+            }
+            __syncthreads();
+            stockham_pass<LG_M, 8, 8, 1, false, false, true>(W, W, M / 8, twI, none);
+            __syncthreads();
+            float *ac = acc + (size_t)v * N;
+            for (int n = tid; n < M; n += T) {
+                const float2 r = W[pad(n)];
+                const int i = (2 * n + M) & (N - 1);
+                const float y0 = (r.x * scale) * d.win[i], y1 = (r.y * scale) * d.win[i + 1];
+                const int p0 = (pos0 + i) & (N - 1), p1 = (pos0 + i + 1) & (N - 1);
+                ac[p0] = (i < keep ? ac[p0] : 0.f) + y0;
+                ac[p1] = (i + 1 < keep ? ac[p1] : 0.f) + y1;
+            }
+            __syncthreads();
+            if (k >= seg.k_emit) {
+                float *o = out + v * a.out_voice_stride + k * (long long)Hs;
+                for (int j = tid; j < Hs; j += T) o[j] = ac[(pos0 + j) & (N - 1)];
+            }
+        }
+        __syncthreads();
+        have_prev = true;
+        pos0 = (pos0 + Hs) & (N - 1);
+    }
+    // leave the state in its linear form: accumulated frame after the last frame at index 0
+    const int plast = (pos0 - Hs) & (N - 1);
+    if (tid == 0) { hdr[0] = 1u; hdr[1] = 0u; }
+    for (int i = tid; i < NB; i += T) gPprev[i] = Pprev[i];
+    for (int v = 0; v < V; v++) {
+        for (int i = tid; i < NB; i += T) gpsi[(size_t)v * NB + i] = psi[(size_t)v * NBP + i];
+        for (int i = tid; i < N; i += T) gacc[(size_t)v * N + i] = acc[(size_t)v * N + ((plast + i) & (N - 1))];
+    }
+}
+
+// phase-carry aggregate on the same forward half (PvAggArgs), one CTA per frame-range segment
+template <int LG_N>
+__global__ void __launch_bounds__(1 << (LG_N - 4), 3)
+aggregate_inplace_kernel(PvDev d, PvAggArgs a)
+{
+    using L = InplaceLayout<LG_N>;
+    constexpr int N = L::N, M = L::M, NB = L::NB, NBP = L::NBP, T = N / 16;
+    extern __shared__ float2 sm[];
+    float2 *W = sm;
+    float *magS = reinterpret_cast<float *>(sm + fft_work_elems(M));
+    uint32_t *Pc = reinterpret_cast<uint32_t *>(magS + NBP);
+    uint32_t *Pp = Pc + NBP;
+    const int tid = threadIdx.x, lsh = 32 - d.lgN;
+    const long long sg = blockIdx.x;
+    const PvSegment seg = a.segs[sg];
+    const float *in = a.in + seg.stream * a.in_stride;
+    const bool carried = seg.carry_in && a.P_prev != nullptr &&
+                         (!a.P_prev_in_state || a.P_prev[(long long)seg.stream * a.P_prev_stride - 2] != 0u);
+    bool have_prev = carried;
+    for (int b = tid; b < NB; b += T) {
+        Pp[b] = carried ? a.P_prev[(long long)seg.stream * a.P_prev_stride + b] : 0u;
+        a.S[sg * NB + b] = 0;
+        if (a.H) a.H[sg * NB + b] = 0;
+        if (a.P_first) a.P_first[sg * NB + b] = 0u;
+    }
+    __syncthreads();
+    for (long long k = seg.k_begin; k < seg.k_end; ++k) {
+        long long *dst = reinterpret_cast<long long *>((k < seg.k_emit) ? a.H : a.S);
+        analysis_inplace<LG_N>(W, in, k * (long long)d.Ha, a.n_in, d.win, d.tw, magS, Pc);
+        __syncthreads();
+        for (int b = tid; b < NB; b += T) {
+            const uint32_t P = Pc[b];
+            const uint32_t nomA = ((uint32_t)b * (uint32_t)d.Ha) << lsh;
+            if (have_prev) { if (dst) dst[sg * NB + b] += (long long)(int32_t)(P - Pp[b] - nomA); }
+            else if (a.P_first) a.P_first[sg * NB + b] = P;
+            Pp[b] = P;
+        }
+        have_prev = true;
+        __syncthreads();
+    }
+    if (a.P_last)
+        for (int b = tid; b < NB; b += T) a.P_last[sg * NB + b] = Pp[b];
+}
+
+// ---------------------------------------------------------------------------------------------
 // generic fused CORRECTED stream kernel: one CTA per stream, any power-of-two window.
 // Stream state (previous phase, phase accumulators, OLA rings) lives in the per-stream state buffer in
 // global memory (L2 resident); the arithmetic is the specification of DESIGN.md "corrected mode".
@@ -422,6 +789,11 @@ corrected_generic_kernel(PvDev d, PvProcessArgs a)
         for (int i = threadIdx.x; i < NB; i += blockDim.x) Pprev[i] = gPprev[i];
         for (int i = threadIdx.x; i < V * NB; i += blockDim.x) psi[i] = gpsi[i];
         for (int i = threadIdx.x; i < V * N; i += blockDim.x) acc[i] = gacc[i];
+    } else if (SMEM_STATE) {
+        // accumulators of synthesis bins without a source bin are never written: start them at zero so that the
+        // state written back does not carry stale shared memory
+        for (int i = threadIdx.x; i < NB; i += blockDim.x) Pprev[i] = 0u;
+        for (int i = threadIdx.x; i < V * NB; i += blockDim.x) psi[i] = 0ull;
     }
 
     // The state stores each voice's accumulated frame linearly (index 0 = first sample of the LAST frame).
@@ -597,9 +969,22 @@ aggregate_generic_kernel(PvDev d, PvAggArgs a)
 
 }  // namespace
 
+// window 4096 with the state of all voices next to the transform buffer and at least two CTAs per SM
+static bool use_inplace_corrected(const PvDev &d)
+{
+    return d.N == 4096 && InplaceLayout<12>::bytes(d.V, true) <= 113 * 1024 && !getenv("PV_NO_INPLACE");
+}
+
 cudaError_t pv_launch_aggregate_generic(const PvDev &d, const PvAggArgs &a, cudaStream_t st)
 {
     if (a.n_segs <= 0) return cudaSuccess;
+    if (use_inplace_corrected(d)) {         // must be the aggregate that shares analysis_inplace with the processing kernel
+        const size_t smem = InplaceLayout<12>::bytes(d.V, false);
+        cudaError_t e = cudaFuncSetAttribute(aggregate_inplace_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        aggregate_inplace_kernel<12><<<a.n_segs, 256, smem, st>>>(d, a);
+        return cudaGetLastError();
+    }
     const size_t NB = d.N / 2 + 1;
     const size_t smem = sizeof(float2) * (NB + fft_work_elems(d.N / 2)) + sizeof(uint32_t) * NB;
     cudaError_t e = cudaFuncSetAttribute(aggregate_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -680,6 +1065,13 @@ cudaError_t pv_launch_float_to_pcm16(const float *in, int16_t *out, int64_t rows
 cudaError_t pv_launch_corrected_generic(const PvDev &d, const PvProcessArgs &a, cudaStream_t st)
 {
     if (a.n_segs <= 0) return cudaSuccess;
+    if (use_inplace_corrected(d)) {
+        const size_t smem = InplaceLayout<12>::bytes(d.V, true);
+        cudaError_t e = cudaFuncSetAttribute(corrected_inplace_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        corrected_inplace_kernel<12><<<a.n_segs, 256, smem, st>>>(d, a);
+        return cudaGetLastError();
+    }
     const size_t NB = d.N / 2 + 1;
     const size_t smem = std::max(sizeof(float2) * (2 * NB + fft_work_elems(d.N / 2)) + sizeof(float) * 2 * NB, sizeof(float) * (size_t)d.N);
     const size_t with_state = smem + (size_t)d.V * NB * 8 + (size_t)d.V * d.N * 4 + NB * 4;
@@ -741,6 +1133,13 @@ cudaError_t pv_launch_test_overlap_add(const PvDev &d, const float *in, const fl
 cudaError_t pv_launch_compat_generic(const PvDev &d, const PvProcessArgs &a, cudaStream_t st)
 {
     if (a.n_segs <= 0) return cudaSuccess;
+    if (d.N == 4096 && !getenv("PV_NO_INPLACE")) {
+        const size_t smem = sizeof(float2) * (size_t)fft_work_elems(d.N) + sizeof(float) * (size_t)d.N;
+        cudaError_t e = cudaFuncSetAttribute(compat_inplace_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        compat_inplace_kernel<12><<<a.n_segs, 256, smem, st>>>(d, a);
+        return cudaGetLastError();
+    }
     const size_t smem = sizeof(float2) * (size_t)(d.N + fft_work_elems(d.N)) + sizeof(float) * (size_t)d.N;
     cudaError_t e = cudaFuncSetAttribute(compat_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
