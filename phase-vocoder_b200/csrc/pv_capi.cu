@@ -420,6 +420,10 @@ int pv_create(const pv_params *params, pv_handle **out)
             std::vector<uint32_t> gath;
             build_gather_table(N, V, alo.data(), ahi.data(), gath, d.multi);
             rc = upload(&h->d_gather, gath);
+        } else if (rc == PV_OK && N == 4096) {           // natural bin order for the in-place large-window kernel
+            std::vector<uint32_t> gath;
+            build_gather_natural(N, V, alo.data(), ahi.data(), gath, d.multi);
+            rc = upload(&h->d_gather, gath);
         }
     }
     h->capacity = h->sm_count * 8;

@@ -52,6 +52,24 @@ inline void build_tables(int log2n, HostTables &t)
         for (int n3 = 0; n3 < R2; n3++) t.itw2[(size_t)(m2 - 1) * R2 + n3] = pv_cis((double)(m2 * n3) / B3);
 }
 
+// The same packing in natural bin order, [v][NB], for the large-window in-place kernel (pv_generic_kernels.cu).
+inline void build_gather_natural(int N, int V, const int32_t *a_lo, const int32_t *a_hi, std::vector<uint32_t> &out,
+                                 int32_t *multi = nullptr)
+{
+    const int NB = N / 2 + 1;
+    const uint32_t dummy = (uint32_t)NB | ((uint32_t)NB << 16);
+    out.assign((size_t)V * NB, dummy);
+    for (int v = 0; v < V; v++) {
+        if (multi) multi[v] = 0;
+        for (int s = 0; s < NB; s++) {
+            const size_t i = (size_t)v * NB + s;
+            if (a_lo[i] > a_hi[i]) continue;
+            if (multi && a_hi[i] > a_lo[i]) multi[v] = 1;
+            out[i] = (uint32_t)a_lo[i] | ((uint32_t)a_hi[i] << 16);
+        }
+    }
+}
+
 // Per-thread packed gather table of the corrected kernel: entry [v][u][slot] = a_lo | a_hi << 16 for the
 // synthesis bin owned by slot `slot` of thread `u` (pvfused::slot_bin).  A synthesis bin that no analysis bin maps
 // to points at the DUMMY bin NB (both halves): the kernel keeps magnitude 0 and phase difference 0 there, so the

@@ -645,15 +645,18 @@ corrected_inplace_kernel(PvDev d, PvProcessArgs a)
         for (int v = 0; v < V; v++) {
             unsigned long long *ps = psi + (size_t)v * NBP;
             const unsigned long long Rq = d.Rq[v];
+            const unsigned long long bqs = (d.beta_q[v] * (unsigned long long)Hs) << lsh;    // nomS[s] = a_hi * bqs mod 2^64
+            const uint32_t *gt = d.gather + (size_t)v * NB;                                 // a_lo | a_hi << 16, NB = no source bin
             auto synth = [&](int s) -> float2 {
-                const int lo = d.a_lo[v * NB + s], hi = d.a_hi[v * NB + s];
-                if (lo > hi) return make_float2(0.f, 0.f);
-                float m = 0.f;
-                for (int b = lo; b <= hi; b++) m += magS[b];
+                const uint32_t ge = __ldg(gt + s);
+                const uint32_t lo = ge & 0xffffu, hi = ge >> 16;
+                if (lo == (uint32_t)NB) return make_float2(0.f, 0.f);
+                float m = magS[lo];
+                for (uint32_t b = lo + 1; b <= hi; b++) m += magS[b];
                 const int32_t dd = dS[hi];
                 unsigned long long p;
                 if (!have_prev) p = (unsigned long long)(uint32_t)dd << 32;
-                else p = ps[s] + d.nomS[v * NB + s] + (unsigned long long)((long long)dd * (long long)Rq);
+                else p = pvfused::mad_s32_u64(dd, Rq, pvfused::mad_u32_u64(hi, bqs, ps[s]));
                 ps[s] = p;
                 const float2 cs = pvfused::cis_turns64(p);
                 return make_float2(m * cs.x, m * cs.y);
