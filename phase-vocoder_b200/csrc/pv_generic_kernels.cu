@@ -393,6 +393,14 @@ compat_generic_kernel(PvDev d, PvProcessArgs a)
 // and the overlap-add ring sits next to the buffer: 51 KB per CTA of N/16 threads instead of 84 KB, three CTAs
 // per SM by registers.  Same segment contract as compat_generic_kernel.
 // ---------------------------------------------------------------------------------------------
+// Pulls the NEW hop of the next frame (samples [base + N, base + N + Ha)) into L2 while the current frame is being
+// transformed: the in-place kernels read their input with plain loads in pass 1, and each line is used once.
+__device__ __forceinline__ void prefetch_next_hop(const float *__restrict__ in, long long base, int N, int Ha, long long n_in)
+{
+    for (long long s = base + N + 32ll * threadIdx.x; s < base + N + Ha && s < n_in; s += 32ll * blockDim.x)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(in + s));
+}
+
 __device__ __forceinline__ float2 compat_map_fast(float2 X, bool nan_compat)
 {
     // steps D+E collapsed (re' = |Re X|, im' = Re X Im X / |X|), as in the tuned kernels (pv_fused_core.cuh)
@@ -432,9 +440,10 @@ compat_inplace_kernel(PvDev d, PvProcessArgs a)
     int pos0 = 0;
     for (int64_t k = seg.k_begin; k < seg.k_end; ++k) {
         const bool analysed = k < a.n_analysed;
+        const int64_t base0 = k * (int64_t)d.Ha;
         if (analysed) {
             {   // forward pass 1 (Ns = 1): c[n] = f[N/2 + 2n] for n < N/4, f[2(n - 3N/4)] for n >= 3N/4, else 0
-                const int64_t base = k * (int64_t)d.Ha;
+                const int64_t base = base0;
                 float2 v[16];
 #pragma unroll
                 for (int r = 0; r < 16; r++) {
@@ -451,6 +460,7 @@ compat_inplace_kernel(PvDev d, PvProcessArgs a)
                 for (int r = 0; r < 16; r++) dst[r] = v[r];
             }
             __syncthreads();
+            if (k + 1 < seg.k_end) prefetch_next_hop(in, base0, N, d.Ha, a.n_in);
             {
                 const auto tw2 = load_reg_tw<LG_N, 16, -1>(twF);
                 stockham_pass<LG_N, 16, 4, -1, false, false, true>(W, W, T, twF, tw2);
@@ -634,6 +644,7 @@ corrected_inplace_kernel(PvDev d, PvProcessArgs a)
 
     for (long long k = seg.k_begin; k < seg.k_end; ++k) {
         analysis_inplace<LG_N>(W, in, k * (long long)d.Ha, a.n_in, d.win, d.tw, magS, Pc);
+        if (k + 1 < seg.k_end) prefetch_next_hop(in, k * (long long)d.Ha, N, d.Ha, a.n_in);
         __syncthreads();
         for (int b = tid; b < NB; b += T) {              // unwrapped phase difference, integer wrap-around
             const uint32_t P = Pc[b];
