@@ -16,4 +16,4 @@ python bench.py --impl reference --steps 5 --warmup 2 > $O/${R}_bench_reference.
 python tools/run_configs.py > $O/${R}_configs_body.md 2> $O/configs.err
 python tools/run_configs.py --sweep > $O/${R}_sweep_body.md 2> $O/sweep.err
 python tools/fft_bench.py > $O/${R}_fft_bench.md 2> $O/fft.err
-tail -2 $O/ncu1.log $O/ncu2.log; tail -c 300 $O/${R}_bench.json; tail -3 $O/${R}_configs_body.md
+tail -n 2 $O/ncu1.log $O/ncu2.log; tail -c 300 $O/${R}_bench.json; tail -3 $O/${R}_configs_body.md
