@@ -67,8 +67,8 @@ class TorchComm:
 
 
 def process_compat_sharded(engine, x, n_frames, n_analysed, comm, Ha, Hs, N):
-    """x: the rank's view of the stream as a [1, n] tensor starting at sample ks*Ha.  Returns this
-    rank's output block [1, 1, (k1-k0)*Hs] and its plan."""
+    """x: the rank's view of the stream(s) as a [S, n] tensor starting at sample ks*Ha.  Returns this
+    rank's output block [S, 1, (k1-k0)*Hs] and its plan."""
     p = plan(n_frames, comm.world, comm.rank, N, Hs)
     nf = p.k1 - p.ks
     if p.k1 <= p.k0:
@@ -78,8 +78,9 @@ def process_compat_sharded(engine, x, n_frames, n_analysed, comm, Ha, Hs, N):
 
 
 def process_corrected_sharded(engine, x_from, n_frames, comm, Ha, Hs, N):
-    """Corrected mode.  `x_from(first_frame)` returns the stream from sample first_frame*Ha on as a
-    [1, n] tensor on the engine's device.  Returns (out [1, V, (k1-k0)*Hs], plan)."""
+    """Corrected mode.  `x_from(first_frame)` returns the stream(s) from sample first_frame*Ha on as a
+    [S, n] tensor on the engine's device (S streams cut at the same frames, e.g. the channels of a file).
+    Returns (out [S, V, (k1-k0)*Hs], plan)."""
     p = plan(n_frames, comm.world, comm.rank, N, Hs)
     empty = p.k1 <= p.k0
     # 1. local aggregate over [k0, k1): D_k needs P_{k0-1}, so start one frame early (rank 0: frame 0)

@@ -44,15 +44,11 @@ def main():
     comm = sharding.TorchComm()
 
     def run_sharded():
-        outs = []
-        for c in range(2):                                   # the two channels are independent streams
-            if corrected:
-                o, p = sharding.process_corrected_sharded(pv, lambda k, c=c: x[c:c + 1, k * H:], nf, comm, H, H, N)
-            else:
-                p = sharding.plan(nf, world, rank, N, H)
-                o, _ = sharding.process_compat_sharded(pv, x[c:c + 1, p.ks * H:], nf, nf, comm, H, H, N)
-            outs.append(o)
-        return torch.cat(outs, 0), p
+        # both channels in one call: they are independent streams with the same frame ranges
+        if corrected:
+            return sharding.process_corrected_sharded(pv, lambda k: x[:, k * H:], nf, comm, H, H, N)
+        p = sharding.plan(nf, world, rank, N, H)
+        return sharding.process_compat_sharded(pv, x[:, p.ks * H:], nf, nf, comm, H, H, N)
 
     for _ in range(2):
         out, p = run_sharded()
