@@ -148,7 +148,7 @@ size_t pv_state_bytes(const pv_handle *h);
  *               caller may zero it once and pass both flags on every call.
  * Long streams are split into frame-range segments processed concurrently (the (N-Hs) OLA
  * halo is recomputed, so the result does not depend on the split).                            */
-enum { PV_PROCESS_CARRY_IN = 1, PV_PROCESS_CARRY_OUT = 2 };
+enum { PV_PROCESS_CARRY_IN = 1, PV_PROCESS_CARRY_OUT = 2, PV_PROCESS_REUSE_AGGREGATE = 4 };
 
 int pv_process_device(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride,
                       int64_t n_in, int64_t n_analysed, int64_t n_frames, float *out,
@@ -182,6 +182,18 @@ int pv_corrected_aggregate(pv_handle *h, const float *in, int64_t n_streams, int
 int pv_corrected_state_from_carry(pv_handle *h, int64_t n_streams, const uint32_t *P_first,
                                   const int64_t *sumD, int64_t n_before, const uint32_t *P_prev,
                                   void *state, void *cuda_stream);
+
+/* The analysis pass of pv_process_device_ex(h, in, ..., n_frames, skip_frames, ..., state, flags, stream) on its own:
+ * sumD[stream][bin] = sum of the unwrapped phase differences over ALL frames of that call (halo / skipped frames
+ * included; frame 0 counts only when a state is carried in, which supplies the previous phase).  When the call is
+ * one that the library cuts into frame-range parts (few streams), the per-part sums stay in the handle, and the
+ * matching pv_process_device_ex call -- same arguments, issued next on the same stream, with
+ * PV_PROCESS_REUSE_AGGREGATE added to its flags -- skips its own analysis pass.  This is what lets a rank of a
+ * sharded long stream learn its phase-carry contribution, exchange it, and then finish with one pass instead of
+ * two; the flag is ignored whenever nothing reusable is there, so it is always safe to pass.                     */
+int pv_corrected_split_aggregate(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride,
+                                 int64_t n_in, int64_t n_frames, int64_t skip_frames, const void *state,
+                                 int32_t flags, int64_t *sumD, void *cuda_stream);
 
 /* Same with HOST buffers (pinned or pageable): H2D, kernel, D2H, synchronise.  This is the
  * call the C++ PhaseVocoder shim and the CLI make, and what bench.py times as `e2e`.         */

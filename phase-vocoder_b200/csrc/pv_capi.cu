@@ -58,6 +58,7 @@ struct pv_handle {
     };
     Plan plans[8];
     uint64_t plan_clock = 0;
+    const Plan *agg_valid_for = nullptr;   // plan whose per-part sums pv_corrected_split_aggregate left in d_S / d_H / d_Pf
     float2 *d_fft_tw[14] = {};      // stand-alone FFT: n-th roots of unity per log2 n, built on first use
     // staging for the host-pointer entry point
     float *d_in = nullptr, *d_out = nullptr;
@@ -603,6 +604,14 @@ int pv_process_device(pv_handle *h, const float *in, int64_t n_streams, int64_t 
                                 out_voice_stride, state, flags, cuda_stream);
 }
 
+static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_t plan_streams, int64_t in_stride,
+                        int64_t n_in, int64_t n_analysed, int64_t n_frames, int64_t skip_frames, float *out,
+                        int64_t out_stream_stride, int64_t out_voice_stride, void *state, int32_t flags,
+                        void *cuda_stream, int64_t *agg_only = nullptr);
+static int aggregate_plain(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride, int64_t n_in, int64_t n_frames,
+                           const uint32_t *P_prev, int64_t P_prev_stride, int32_t in_state, int64_t *sumD, uint32_t *P_first,
+                           uint32_t *P_last, void *cuda_stream);
+
 int pv_corrected_aggregate(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride, int64_t n_in,
                            int64_t n_frames, const uint32_t *P_prev, int64_t *sumD, uint32_t *P_first,
                            uint32_t *P_last, void *cuda_stream)
@@ -617,6 +626,7 @@ int pv_corrected_aggregate(pv_handle *h, const float *in, int64_t n_streams, int
             pv_handle::Plan *pl = nullptr;
             int rc0 = plan_corrected_split(h, n_streams, n_frames, (int32_t)parts, false, 0, &pl);
             if (rc0 != PV_OK) return rc0;
+            h->agg_valid_for = nullptr;          // the shared per-part sums are about to be overwritten
             const int nb = h->p.window / 2 + 1;
             PvAggArgs ag{in, in_stride, n_in, pl->d_agg_segs, pl->n_segs, P_prev, (int64_t)nb, h->d_S, nullptr, h->d_Pf, h->d_Pl, 0};
             if (h->fused && !getenv("PV_FORCE_GENERIC")) PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, ag, (cudaStream_t)cuda_stream));
@@ -627,6 +637,16 @@ int pv_corrected_aggregate(pv_handle *h, const float *in, int64_t n_streams, int
             return PV_OK;
         }
     }
+    return aggregate_plain(h, in, n_streams, in_stride, n_in, n_frames, P_prev, (int64_t)(h->p.window / 2 + 1), 0, sumD, P_first,
+                           P_last, cuda_stream);
+}
+
+// One analysis segment per stream (no frame-range split).  P_prev rows: a dense [stream][bin] array, or the previous
+// phase inside state records (in_state: the record's have_prev word gates the carry).
+static int aggregate_plain(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride, int64_t n_in, int64_t n_frames,
+                           const uint32_t *P_prev, int64_t P_prev_stride, int32_t in_state, int64_t *sumD, uint32_t *P_first,
+                           uint32_t *P_last, void *cuda_stream)
+{
     std::vector<PvSegment> segs((size_t)n_streams);
     for (int64_t s = 0; s < n_streams; s++) {
         PvSegment g{};
@@ -646,11 +666,21 @@ int pv_corrected_aggregate(pv_handle *h, const float *in, int64_t n_streams, int
         h->api_cap = segs.size();
     }
     PV_CUDA(cudaMemcpy(h->d_api_segs, segs.data(), sizeof(PvSegment) * segs.size(), cudaMemcpyHostToDevice));
-    PvAggArgs a{in, in_stride, n_in, h->d_api_segs, (int32_t)n_streams, P_prev, (int64_t)(h->p.window / 2 + 1), sumD, nullptr, P_first, P_last, 0};
+    PvAggArgs a{in, in_stride, n_in, h->d_api_segs, (int32_t)n_streams, P_prev, P_prev_stride, sumD, nullptr, P_first, P_last, in_state};
     if (h->fused && !getenv("PV_FORCE_GENERIC")) PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, a, (cudaStream_t)cuda_stream));
     else PV_CUDA(pv_launch_aggregate_generic(h->dev, a, (cudaStream_t)cuda_stream));
     h->launches++;
     return PV_OK;
+}
+
+int pv_corrected_split_aggregate(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride, int64_t n_in,
+                                 int64_t n_frames, int64_t skip_frames, const void *state, int32_t flags, int64_t *sumD,
+                                 void *cuda_stream)
+{
+    if (!h || !in || !sumD) return fail(PV_ERR_PARAM, "pv_corrected_split_aggregate: null argument");
+    if (h->p.mode != PV_MODE_CORRECTED) return fail(PV_ERR_PARAM, "pv_corrected_split_aggregate needs a corrected-mode handle");
+    return process_impl(h, in, n_streams, n_streams, in_stride, n_in, n_frames, n_frames, skip_frames, nullptr, 0, 0,
+                        const_cast<void *>(state), flags & PV_PROCESS_CARRY_IN, cuda_stream, sumD);
 }
 
 int pv_corrected_state_from_carry(pv_handle *h, int64_t n_streams, const uint32_t *P_first, const int64_t *sumD,
@@ -667,10 +697,6 @@ int pv_corrected_state_from_carry(pv_handle *h, int64_t n_streams, const uint32_
     return PV_OK;
 }
 
-static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_t plan_streams, int64_t in_stride,
-                        int64_t n_in, int64_t n_analysed, int64_t n_frames, int64_t skip_frames, float *out,
-                        int64_t out_stream_stride, int64_t out_voice_stride, void *state, int32_t flags,
-                        void *cuda_stream);
 
 int pv_process_device_ex(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride, int64_t n_in,
                          int64_t n_analysed, int64_t n_frames, int64_t skip_frames, float *out,
@@ -686,15 +712,15 @@ int pv_process_device_ex(pv_handle *h, const float *in, int64_t n_streams, int64
 static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_t plan_streams, int64_t in_stride,
                         int64_t n_in, int64_t n_analysed, int64_t n_frames, int64_t skip_frames, float *out,
                         int64_t out_stream_stride, int64_t out_voice_stride, void *state, int32_t flags,
-                        void *cuda_stream)
+                        void *cuda_stream, int64_t *agg_only)
 {
-    if (!h || !in || !out) return fail(PV_ERR_PARAM, "pv_process: null argument");
+    if (!h || !in || (!out && !agg_only)) return fail(PV_ERR_PARAM, "pv_process: null argument");
     if (skip_frames < 0 || skip_frames > n_frames) return fail(PV_ERR_PARAM, "pv_process: bad skip_frames");
     if (n_streams < 0 || n_in < 0 || n_frames < 0 || in_stride < n_in)
         return fail(PV_ERR_PARAM, "pv_process: bad sizes (n_streams=%lld n_in=%lld n_frames=%lld in_stride=%lld)",
                     (long long)n_streams, (long long)n_in, (long long)n_frames, (long long)in_stride);
     if (n_streams > 0x7fffffffLL) return fail(PV_ERR_PARAM, "too many streams");
-    if (out_stream_stride < (n_frames - skip_frames) * h->p.hop_out * (int64_t)h->p.n_voices && n_streams > 1)
+    if (!agg_only && out_stream_stride < (n_frames - skip_frames) * h->p.hop_out * (int64_t)h->p.n_voices && n_streams > 1)
         return fail(PV_ERR_PARAM, "pv_process: out_stream_stride too small");
     if ((flags & (PV_PROCESS_CARRY_IN | PV_PROCESS_CARRY_OUT)) && !state)
         return fail(PV_ERR_PARAM, "pv_process: carry requested without a state buffer");
@@ -715,8 +741,23 @@ static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_
             PvAggArgs ag{in, in_stride, n_in, pl->d_agg_segs, pl->n_segs,
                          user_carry ? reinterpret_cast<const uint32_t *>((const unsigned char *)state + 8) : nullptr, sb / 4,
                          h->d_S, h->d_H, h->d_Pf, nullptr, 1};
-            if (fused_ok) PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, ag, st));
-            else PV_CUDA(pv_launch_aggregate_generic(h->dev, ag, st));
+            // PV_PROCESS_REUSE_AGGREGATE: pv_corrected_split_aggregate has just left the per-part sums of exactly this
+            // call in the handle (same plan, same input), so the analysis pass is not repeated
+            const bool reuse = (flags & PV_PROCESS_REUSE_AGGREGATE) && h->agg_valid_for == pl;
+            h->agg_valid_for = nullptr;
+            if (!reuse) {
+                if (fused_ok) PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, ag, st));
+                else PV_CUDA(pv_launch_aggregate_generic(h->dev, ag, st));
+                h->launches++;
+            }
+            if (agg_only) {
+                // totals over all frames of the call (halo and skipped frames included): sum of the per-part sums
+                PV_CUDA(pv_launch_reduce_parts(h->p.window / 2 + 1, n_streams, (int32_t)parts, h->d_S, nullptr, nullptr, agg_only,
+                                               nullptr, nullptr, st));
+                h->launches++;
+                h->agg_valid_for = pl;
+                return PV_OK;
+            }
             PV_CUDA(pv_launch_split_states(h->dev, n_streams, (int32_t)parts, pl->d_segs, h->d_S, h->d_H, h->d_Pf,
                                            h->d_slots, sb, user_carry ? (const unsigned char *)state : nullptr, st));
             PvProcessArgs a{};
@@ -744,7 +785,7 @@ static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_
                 PV_CUDA(cudaEventRecord(e1, st));
                 h->events.emplace_back(e0, e1);
             }
-            h->launches += 3;
+            h->launches += 2;
             if ((flags & PV_PROCESS_CARRY_OUT) && state) {
                 // the last part of every stream holds the stream's final state (the generic kernel always
                 // leaves it in the slot; the fused kernel writes it when carry_out is set -> set below)
@@ -754,6 +795,13 @@ static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_
             }
             return PV_OK;
         }
+    }
+    if (agg_only) {
+        // no frame-range split for this shape: the totals are one plain analysis pass (nothing is kept for reuse)
+        const uint32_t *P_prev = (flags & PV_PROCESS_CARRY_IN) && state
+                                     ? reinterpret_cast<const uint32_t *>((const unsigned char *)state + 8) : nullptr;
+        return aggregate_plain(h, in, n_streams, in_stride, n_in, n_frames, P_prev, (int64_t)pv_state_bytes(h) / 4, 1, agg_only,
+                               nullptr, nullptr, cuda_stream);
     }
     pv_handle::Plan *pl = nullptr;
     int rc = plan_segments(h, plan_streams, n_frames, skip_frames, flags, &pl);

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_DIR, "libpv_b200.so")
 MODE_COMPAT, MODE_CORRECTED = 0, 1
 WIN_HAMMING, WIN_HANN_SYM, WIN_HANN_PERIODIC = 0, 1, 2
 FLAG_NAN_COMPAT = 1
-CARRY_IN, CARRY_OUT = 1, 2
+CARRY_IN, CARRY_OUT, REUSE_AGGREGATE = 1, 2, 4
 MAX_VOICES = 8
 
 EXPORTS = [
@@ -28,7 +28,7 @@ EXPORTS = [
     "pv_process_host_pcm16",
     "pv_corrected_aggregate", "pv_corrected_state_from_carry", "pv_launch_count", "pv_timing_enable", "pv_timing_read",
     "pv_rt_open", "pv_rt_close", "pv_rt_reset", "pv_rt_latency_samples", "pv_rt_input", "pv_rt_output", "pv_rt_step",
-    "pv_rt_callback", "pv_fft_batch",
+    "pv_rt_callback", "pv_fft_batch", "pv_corrected_split_aggregate",
 ]
 
 
@@ -93,6 +93,7 @@ def load():
     L.pv_rt_step.argtypes = [vp]
     L.pv_rt_callback.argtypes = [vp, vp, vp, C.c_uint32]
     L.pv_fft_batch.argtypes = [vp, vp, vp, i32, i64, i32, vp]
+    L.pv_corrected_split_aggregate.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, i32, vp, vp]
     _lib = L
     return L
 
@@ -217,6 +218,18 @@ class PhaseVocoder:
         _check(load().pv_corrected_aggregate(self._h, _ptr(x), S, x.stride(0), n_in, n_frames, _ptr(P_prev), _ptr(sumD),
                                              _ptr(P_first), _ptr(P_last), _cuda_stream()))
         return sumD, P_first, P_last
+
+    def split_aggregate(self, x, n_frames, state=None, skip=0, n_in=None):
+        """The analysis pass of process(x, n_frames, state=state, flags=CARRY_IN if state is not None, skip=skip) on
+        its own: sumD int64 [S, nb] over all frames of that call.  Follow it with that process call and
+        flags | REUSE_AGGREGATE: the per-part sums kept in the handle are reused instead of recomputed."""
+        import torch
+        S = x.shape[0]
+        n_in = x.shape[1] if n_in is None else n_in
+        sumD = torch.zeros((S, self.nSamps // 2 + 1), dtype=torch.int64, device=x.device)
+        _check(load().pv_corrected_split_aggregate(self._h, _ptr(x), S, x.stride(0), n_in, n_frames, skip, _ptr(state),
+                                                   CARRY_IN if state is not None else 0, _ptr(sumD), _cuda_stream()))
+        return sumD
 
     def state_from_carry(self, P_first, sumD, n_before, P_prev):
         """Carried state [S, state_bytes] (uint8) at frame boundary n_before from a phase carry."""

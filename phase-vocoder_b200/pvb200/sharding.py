@@ -80,7 +80,12 @@ def process_compat_sharded(engine, x, n_frames, n_analysed, comm, Ha, Hs, N):
 def process_corrected_sharded(engine, x_from, n_frames, comm, Ha, Hs, N):
     """Corrected mode.  `x_from(first_frame)` returns the stream(s) from sample first_frame*Ha on as a
     [S, n] tensor on the engine's device (S streams cut at the same frames, e.g. the channels of a file).
-    Returns (out [S, V, (k1-k0)*Hs], plan)."""
+    Returns (out [S, V, (k1-k0)*Hs], plan).
+
+    Engines with `split_aggregate` (the GPU engine) learn their contribution from the very analysis pass that
+    their processing call would run anyway and reuse it afterwards: one pass over the range instead of two."""
+    if hasattr(engine, "split_aggregate"):
+        return _process_corrected_sharded_reuse(engine, x_from, n_frames, comm, Ha, Hs, N)
     p = plan(n_frames, comm.world, comm.rank, N, Hs)
     empty = p.k1 <= p.k0
     # 1. local aggregate over [k0, k1): D_k needs P_{k0-1}, so start one frame early (rank 0: frame 0)
@@ -104,4 +109,35 @@ def process_corrected_sharded(engine, x_from, n_frames, comm, Ha, Hs, N):
     # 4. halo frames fill the OLA accumulators, then the owned range is written
     CARRY_IN = 1
     out = engine.process(x_from(p.ks), p.k1 - p.ks, state=state, flags=CARRY_IN, skip=p.k0 - p.ks)
+    return out, p
+
+
+def _process_corrected_sharded_reuse(engine, x_from, n_frames, comm, Ha, Hs, N):
+    CARRY_IN, REUSE = 1, 4
+    p = plan(n_frames, comm.world, comm.rank, N, Hs)
+    empty = p.k1 <= p.k0
+    # phase of frame 0 (rank 0's is the one everybody needs) and a zero of the right shape
+    zero, P_0, _ = engine.aggregate(x_from(0), 1)
+    zero = zero * 0
+    owned, h_sum, P_ksm1 = zero, None, None
+    if not empty and p.ks == 0:
+        # the range reaches frame 0: fresh start, D over [1, k1); what lies before k0 is not this rank's to report
+        total = engine.split_aggregate(x_from(0), p.k1, skip=p.k0)
+        owned = total - engine.aggregate(x_from(0), p.k0)[0] if p.k0 > 1 else total
+    elif not empty:
+        # D over the halo [ks, k0) and the phase of frame ks-1, from a handful of frames
+        h_sum, P_ksm1, _ = engine.aggregate(x_from(p.ks - 1), p.k0 - p.ks + 1)
+        st0 = engine.state_from_carry(P_0 * 0, zero, 1, P_ksm1)          # previous phase only; accumulators unknown yet
+        total = engine.split_aggregate(x_from(p.ks), p.k1 - p.ks, state=st0, skip=p.k0 - p.ks)   # D over [ks, k1)
+        owned = total - h_sum
+    # the only exchange: per-bin sums (and rank 0's P_0)
+    sums = comm.all_gather(owned)
+    P0 = comm.all_gather(P_0)[0]
+    if empty:
+        return None, p
+    if p.ks == 0:
+        return engine.process(x_from(0), p.k1, skip=p.k0, flags=REUSE), p
+    prefix = (sum(sums[:comm.rank]) if comm.rank > 0 else zero) - h_sum      # up to ks
+    state = engine.state_from_carry(P0, prefix, p.ks, P_ksm1)
+    out = engine.process(x_from(p.ks), p.k1 - p.ks, state=state, flags=CARRY_IN | REUSE, skip=p.k0 - p.ks)
     return out, p
