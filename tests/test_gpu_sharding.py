@@ -89,3 +89,36 @@ def test_aggregate_matches_oracle():
     ds = (sumD[0].cpu().numpy() - want) / 2.0 ** 32
     frac = np.abs(ds - np.round(ds))
     assert frac.max() < 1e-3 and (np.round(ds) != 0).mean() < 0.02
+
+
+def test_split_aggregate_matches_aggregate_and_reuse_changes_nothing():
+    """pv_corrected_split_aggregate = the analysis pass of the processing call: its sums equal the plain aggregate's
+    (integer, exact) and the processing call that reuses them produces the same bits as one that recomputes them."""
+    N, H, nf = 1024, 256, 3000
+    x = torch.from_numpy(np.stack([multitone(N + nf * H, seed=90 + s, noise=1e-3) for s in range(2)])).cuda()
+    pv = pvb200.PhaseVocoder(N, hop_in=H, hop_out=H, mode=pvb200.MODE_CORRECTED, window_type=pvb200.WIN_HANN_PERIODIC,
+                             pitch=(float(np.float32(2 ** (7 / 12))),))
+    # fresh start: D over frames 1..nf-1
+    total = pv.split_aggregate(x, nf)
+    n0 = pv.launch_count()
+    a = pv.process(x, nf, flags=pvb200.REUSE_AGGREGATE)
+    assert pv.launch_count() - n0 == 2                                  # state build + process: no second analysis pass
+    plain, P_first, _ = pv.aggregate(x, nf)
+    assert torch.equal(total, plain)
+    n0 = pv.launch_count()
+    b = pv.process(x, nf)
+    assert pv.launch_count() - n0 == 3 and torch.equal(a, b)           # b: aggregate + state build + process
+    # carried in at frame k: D over frames k..nf-1, the state supplies the phase of frame k-1
+    k = 1000
+    sd, P0, _ = pv.aggregate(x, k)
+    P_km1 = pv.aggregate(x[:, (k - 1) * H:], 1)[1]
+    st = pv.state_from_carry(P0, sd, k, P_km1)
+    total_k = pv.split_aggregate(x[:, k * H:], nf - k, state=st)
+    tail, _, _ = pv.aggregate(x[:, (k - 1) * H:], nf - k + 1)
+    assert torch.equal(total_k, tail)
+    c = pv.process(x[:, k * H:], nf - k, state=st, flags=pvb200.CARRY_IN | pvb200.REUSE_AGGREGATE)
+    d = pv.process(x[:, k * H:], nf - k, state=st, flags=pvb200.CARRY_IN)
+    halo = (N - 1) // H                    # the carried state has empty OLA accumulators: the first frames lack the tail
+    assert torch.equal(c, d) and torch.equal(c[:, :, halo * H:], b[:, :, (k + halo) * H:])
+    # the flag alone (nothing to reuse) is harmless
+    assert torch.equal(pv.process(x, nf, flags=pvb200.REUSE_AGGREGATE), b)
