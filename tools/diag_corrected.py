@@ -1,5 +1,7 @@
-import sys, numpy as np, torch
-sys.path[:0]=["/root/repo","/root/repo/oracle","/root/repo/phase-vocoder_b200","/root/repo/tests"]
+"""Parity diagnostic of the corrected mode: GPU and fp32 oracle against the fp64 oracle on a few shapes."""
+import os, sys, numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "phase-vocoder_b200"), os.path.join(ROOT, "tests")]
 import pv_oracle as po, pvb200
 from signals import multitone, snr_db
 SEMI7=float(np.float32(2**(7/12)))
