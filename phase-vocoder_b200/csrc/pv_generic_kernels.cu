@@ -986,7 +986,7 @@ aggregate_generic_kernel(PvDev d, PvAggArgs a)
 // window 4096 with the state of all voices next to the transform buffer and at least two CTAs per SM
 static bool use_inplace_corrected(const PvDev &d)
 {
-    return d.N == 4096 && InplaceLayout<12>::bytes(d.V, true) <= 113 * 1024 && !getenv("PV_NO_INPLACE");
+    return d.N == 4096 && InplaceLayout<12>::bytes(d.V, true) <= 200 * 1024 && !getenv("PV_NO_INPLACE");
 }
 
 cudaError_t pv_launch_aggregate_generic(const PvDev &d, const PvAggArgs &a, cudaStream_t st)
