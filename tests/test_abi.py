@@ -52,3 +52,36 @@ def test_product_never_imports_oracle():
     # and the built library has no undefined pvo_* symbols
     out = subprocess.run(["nm", "-D", pvb200.LIB_PATH], capture_output=True, text=True).stdout
     assert "pvo_" not in out
+
+
+def test_null_arguments_are_rejected_before_any_device_work():
+    """Every entry point checks its handle / pointers first and reports through pv_last_error (no CUDA call is made
+    for these, so this runs without a GPU)."""
+    import ctypes as C
+    lib = pvb200.load()
+    vp = C.c_void_p
+    buf = (C.c_float * 8)()
+    rt = vp()
+    calls = [
+        lambda: lib.pv_process_device(None, buf, 1, 8, 8, 1, 1, buf, 8, 8, None, 0, None),
+        lambda: lib.pv_process_device_ex(None, buf, 1, 8, 8, 1, 1, 0, buf, 8, 8, None, 0, None),
+        lambda: lib.pv_process_host(None, buf, 1, 8, 8, 1, 1, buf, 8, 8, None, 0),
+        lambda: lib.pv_process_host_pcm16(None, buf, 1, 8, 8, 1, 1, buf, 8, 8, None, 0),
+        lambda: lib.pv_corrected_aggregate(None, buf, 1, 8, 8, 1, None, buf, None, None, None),
+        lambda: lib.pv_corrected_split_aggregate(None, buf, 1, 8, 8, 1, 0, None, 0, buf, None),
+        lambda: lib.pv_corrected_state_from_carry(None, 1, buf, buf, 0, buf, None, None),
+        lambda: lib.pv_fft_batch(None, buf, buf, 4, 1, -1, None),
+        lambda: lib.pv_rt_open(None, 1, 1, C.byref(rt)),
+        lambda: lib.pv_rt_step(None),
+        lambda: lib.pv_rt_reset(None),
+        lambda: lib.pv_rt_callback(None, buf, buf, 8),
+        lambda: lib.pv_timing_enable(None, 1),
+        lambda: lib.pv_create(None, C.byref(rt)),
+    ]
+    for i, call in enumerate(calls):
+        assert call() != 0, f"call {i} accepted a null argument"
+        assert lib.pv_last_error()
+    assert lib.pv_rt_latency_samples(None) == 0 and not lib.pv_rt_input(None) and not lib.pv_rt_output(None)
+    lib.pv_rt_close(None)
+    lib.pv_destroy(None)
+    assert lib.pv_launch_count(None) == 0 and lib.pv_state_bytes(None) == 0
