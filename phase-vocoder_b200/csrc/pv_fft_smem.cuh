@@ -113,6 +113,47 @@ __device__ __forceinline__ void stockham_pass(const float2 *src, float2 *dst, in
     }
 }
 
+// A pass that hands its outputs to `sink(n, value)` (n = index within the transform, natural order after the last
+// pass) instead of storing them: lets the consumer of a transform work straight from the butterfly's registers.
+// Source: the padded work buffer.  Twiddles by table lookup (any Ns > 1).
+template <int LG_N, int R, int LG_NS, int DIR, class TWF, class SINK>
+__device__ __forceinline__ void stockham_pass_sink(const float2 *src, int total, const TWF &tw, SINK sink)
+{
+    constexpr int LR = Log2<R>::v, LG_PER = LG_N - LR, per = 1 << LG_PER, Ns = 1 << LG_NS;
+    static_assert(per >= 16 && LG_NS > 0 && LG_NS != 4, "table-twiddle pass on the padded buffer");
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int idx = i & (per - 1), k = idx & (Ns - 1);
+        float2 v[R];
+        const float2 *s = src + pad(idx);
+#pragma unroll
+        for (int r = 0; r < R; r++) v[r] = s[r * per + r * per / 16];
+        const int kb = k << (LG_N - LG_NS - LR);
+        float2 w[R];
+        w[1] = tw(kb);
+        if (R > 2) w[2] = tw(2 * kb);
+        if (R > 4) w[4] = tw(4 * kb);
+        if (R > 8) w[8] = tw(8 * kb);
+        if (DIR > 0) {
+            w[1].y = -w[1].y;
+            if (R > 2) w[2].y = -w[2].y;
+            if (R > 4) w[4].y = -w[4].y;
+            if (R > 8) w[8].y = -w[8].y;
+        }
+        if (R > 2) w[3] = cmul(w[2], w[1]);
+        if (R > 4) { w[5] = cmul(w[4], w[1]); w[6] = cmul(w[4], w[2]); w[7] = cmul(w[4], w[3]); }
+        if (R > 8) {
+#pragma unroll
+            for (int r = 9; r < R; r++) w[r] = cmul(w[8], w[r - 8]);
+        }
+#pragma unroll
+        for (int r = 1; r < R; r++) v[r] = cmul(v[r], w[r]);
+        dft<R, DIR>(v);
+        const int j0 = ((idx - k) << LR) + k;
+#pragma unroll
+        for (int r = 0; r < R; r++) sink(j0 + (r << LG_NS), v[r]);
+    }
+}
+
 template <int LG_N>
 struct SecondRadix { static constexpr int v = (LG_N - 4 >= 4) ? 16 : (1 << (LG_N - 4)); };
 

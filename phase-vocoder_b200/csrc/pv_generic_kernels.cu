@@ -507,18 +507,19 @@ compat_inplace_kernel(PvDev d, PvProcessArgs a)
                 stockham_pass<LG_N - 1, 16, 4, 1, false, false, true>(W, W, H / 16, twI, tw2);
             }
             __syncthreads();
-            stockham_pass<LG_N - 1, 8, 8, 1, false, false, true>(W, W, H / 8, twI, none);
-            __syncthreads();
         }
-        // steps G+H: /N, half swap, window, overlap-add into the ring (the fresh tail replaces what was emitted)
-        for (int n = tid; n < H; n += T) {
-            const float2 v = analysed ? W[pad(n)] : make_float2(0.f, 0.f);
+        // steps G+H: /N, half swap, window, overlap-add into the ring (the fresh tail replaces what was emitted),
+        // fed straight from the registers of the last inverse pass
+        auto ola = [&](int n, float2 v) {
             const int i = (2 * n + H) & (N - 1);
             const float y0 = (v.x * scale) * d.win[i], y1 = (v.y * scale) * d.win[i + 1];
             const int p0 = (pos0 + i) & (N - 1), p1 = (pos0 + i + 1) & (N - 1);
             acc[p0] = (i < keep ? acc[p0] : 0.f) + y0;
             acc[p1] = (i + 1 < keep ? acc[p1] : 0.f) + y1;
-        }
+        };
+        if (analysed) stockham_pass_sink<LG_N - 1, 8, 8, 1>(W, H / 8, twI, ola);
+        else
+            for (int n = tid; n < H; n += T) ola(n, make_float2(0.f, 0.f));
         __syncthreads();
         if (k >= seg.k_emit)
             for (int j = tid; j < Hs; j += T) out[k * (int64_t)Hs + j] = acc[(pos0 + j) & (N - 1)];
@@ -689,17 +690,15 @@ corrected_inplace_kernel(PvDev d, PvProcessArgs a)
                 stockham_pass<LG_M, 16, 4, 1, false, false, true>(W, W, M / 16, twI, tw2);
             }
             __syncthreads();
-            stockham_pass<LG_M, 8, 8, 1, false, false, true>(W, W, M / 8, twI, none);
-            __syncthreads();
             float *ac = acc + (size_t)v * N;
-            for (int n = tid; n < M; n += T) {
-                const float2 r = W[pad(n)];
+            // last inverse pass, its outputs scaled, windowed and overlap-added straight from the registers
+            stockham_pass_sink<LG_M, 8, 8, 1>(W, M / 8, twI, [&](int n, float2 r) {
                 const int i = (2 * n + M) & (N - 1);
                 const float y0 = (r.x * scale) * d.win[i], y1 = (r.y * scale) * d.win[i + 1];
                 const int p0 = (pos0 + i) & (N - 1), p1 = (pos0 + i + 1) & (N - 1);
                 ac[p0] = (i < keep ? ac[p0] : 0.f) + y0;
                 ac[p1] = (i + 1 < keep ? ac[p1] : 0.f) + y1;
-            }
+            });
             __syncthreads();
             if (k >= seg.k_emit) {
                 float *o = out + v * a.out_voice_stride + k * (long long)Hs;
