@@ -539,9 +539,11 @@ compat_inplace_kernel(PvDev d, PvProcessArgs a)
 // bit for bit, which is what makes frame-range splitting and sharding exact.
 // ---------------------------------------------------------------------------------------------
 template <int LG_N>
+// Outputs per bin: magnitude, and the unwrapped phase difference D against the previous frame's phase (the plain
+// phase when there is no previous frame); Pprev is advanced to this frame's phase.  Every bin has one owner thread.
 __device__ __noinline__ void analysis_inplace(float2 *W, const float *__restrict__ in, long long base, long long n_in,
                                               const float *__restrict__ win, const float2 *__restrict__ tw, float *magS,
-                                              uint32_t *Pc)
+                                              int32_t *dS, uint32_t *Pprev, bool have_prev, int Ha)
 {
     using namespace pvsmem;
     constexpr int N = 1 << LG_N, M = N / 2, T = N / 16, LG_M = LG_N - 1;
@@ -585,12 +587,15 @@ __device__ __noinline__ void analysis_inplace(float2 *W, const float *__restrict
             xk = make_float2(e.x + t.x, e.y + t.y);
             xm = make_float2(e.x - t.x, -(e.y - t.y));
         }
-        magS[kk] = sqrtf(xk.x * xk.x + xk.y * xk.y);
-        Pc[kk] = pvfused::phase_turns32(xk.x, xk.y);
-        if (kk != M - kk) {
-            magS[M - kk] = sqrtf(xm.x * xm.x + xm.y * xm.y);
-            Pc[M - kk] = pvfused::phase_turns32(xm.x, xm.y);
-        }
+        auto put = [&](int b, float2 x) {
+            magS[b] = sqrtf(x.x * x.x + x.y * x.y);
+            const uint32_t P = pvfused::phase_turns32(x.x, x.y);
+            const uint32_t nomA = ((uint32_t)b * (uint32_t)Ha) << (32 - LG_N);      // integer wrap-around does the unwrap
+            dS[b] = have_prev ? (int32_t)(P - Pprev[b] - nomA) : (int32_t)P;
+            Pprev[b] = P;
+        };
+        put(kk, xk);
+        if (kk != M - kk) put(M - kk, xm);
     }
 }
 
@@ -616,9 +621,8 @@ corrected_inplace_kernel(PvDev d, PvProcessArgs a)
     extern __shared__ float2 sm[];
     float2 *W = sm;
     float *magS = reinterpret_cast<float *>(sm + fft_work_elems(M));
-    uint32_t *Pc = reinterpret_cast<uint32_t *>(magS + NBP);          // phase of the frame, then its D in place
-    int32_t *dS = reinterpret_cast<int32_t *>(Pc);
-    uint32_t *Pprev = Pc + NBP;
+    int32_t *dS = reinterpret_cast<int32_t *>(magS + NBP);
+    uint32_t *Pprev = reinterpret_cast<uint32_t *>(dS + NBP);
     unsigned long long *psi = reinterpret_cast<unsigned long long *>(Pprev + NBP);
     const int V = d.V, Hs = d.Hs, tid = threadIdx.x, keep = N - Hs, lsh = 32 - d.lgN;
     float *acc = reinterpret_cast<float *>(psi + (size_t)V * NBP);
@@ -644,15 +648,8 @@ corrected_inplace_kernel(PvDev d, PvProcessArgs a)
     __syncthreads();
 
     for (long long k = seg.k_begin; k < seg.k_end; ++k) {
-        analysis_inplace<LG_N>(W, in, k * (long long)d.Ha, a.n_in, d.win, d.tw, magS, Pc);
+        analysis_inplace<LG_N>(W, in, k * (long long)d.Ha, a.n_in, d.win, d.tw, magS, dS, Pprev, have_prev, d.Ha);
         if (k + 1 < seg.k_end) prefetch_next_hop(in, k * (long long)d.Ha, N, d.Ha, a.n_in);
-        __syncthreads();
-        for (int b = tid; b < NB; b += T) {              // unwrapped phase difference, integer wrap-around
-            const uint32_t P = Pc[b];
-            const uint32_t nomA = ((uint32_t)b * (uint32_t)d.Ha) << lsh;
-            dS[b] = have_prev ? (int32_t)(P - Pprev[b] - nomA) : (int32_t)P;
-            Pprev[b] = P;
-        }
         __syncthreads();
         for (int v = 0; v < V; v++) {
             unsigned long long *ps = psi + (size_t)v * NBP;
@@ -729,9 +726,9 @@ aggregate_inplace_kernel(PvDev d, PvAggArgs a)
     extern __shared__ float2 sm[];
     float2 *W = sm;
     float *magS = reinterpret_cast<float *>(sm + fft_work_elems(M));
-    uint32_t *Pc = reinterpret_cast<uint32_t *>(magS + NBP);
-    uint32_t *Pp = Pc + NBP;
-    const int tid = threadIdx.x, lsh = 32 - d.lgN;
+    int32_t *dS = reinterpret_cast<int32_t *>(magS + NBP);
+    uint32_t *Pp = reinterpret_cast<uint32_t *>(dS + NBP);
+    const int tid = threadIdx.x;
     const long long sg = blockIdx.x;
     const PvSegment seg = a.segs[sg];
     const float *in = a.in + seg.stream * a.in_stride;
@@ -747,14 +744,11 @@ aggregate_inplace_kernel(PvDev d, PvAggArgs a)
     __syncthreads();
     for (long long k = seg.k_begin; k < seg.k_end; ++k) {
         long long *dst = reinterpret_cast<long long *>((k < seg.k_emit) ? a.H : a.S);
-        analysis_inplace<LG_N>(W, in, k * (long long)d.Ha, a.n_in, d.win, d.tw, magS, Pc);
+        analysis_inplace<LG_N>(W, in, k * (long long)d.Ha, a.n_in, d.win, d.tw, magS, dS, Pp, have_prev, d.Ha);
         __syncthreads();
         for (int b = tid; b < NB; b += T) {
-            const uint32_t P = Pc[b];
-            const uint32_t nomA = ((uint32_t)b * (uint32_t)d.Ha) << lsh;
-            if (have_prev) { if (dst) dst[sg * NB + b] += (long long)(int32_t)(P - Pp[b] - nomA); }
-            else if (a.P_first) a.P_first[sg * NB + b] = P;
-            Pp[b] = P;
+            if (have_prev) { if (dst) dst[sg * NB + b] += (long long)dS[b]; }
+            else if (a.P_first) a.P_first[sg * NB + b] = (uint32_t)dS[b];
         }
         have_prev = true;
         __syncthreads();
