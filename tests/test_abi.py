@@ -85,3 +85,11 @@ def test_null_arguments_are_rejected_before_any_device_work():
     lib.pv_rt_close(None)
     lib.pv_destroy(None)
     assert lib.pv_launch_count(None) == 0 and lib.pv_state_bytes(None) == 0
+
+
+def test_public_header_is_plain_c():
+    """include/pv_b200.h is the FFI surface: it must compile as C99 and as C++11 on its own."""
+    hdr = os.path.join(ROOT, "include", "pv_b200.h")
+    for args in (["gcc", "-x", "c", "-std=c99"], ["g++", "-x", "c++", "-std=c++11"]):
+        r = subprocess.run(args + ["-fsyntax-only", "-Wall", "-Wextra", "-Werror", hdr], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
