@@ -64,6 +64,107 @@ def test_cpp_codec_matches_audiofile_rules(tool, tmp_path):
     assert subprocess.run([tool, "decode", str(tmp_path / "f.wav"), str(tmp_path / "f.f32")], capture_output=True).returncode == 3
 
 
+AFTOOL = os.path.join(ROOT, "oracle", "_ref", "audiofile_tool")
+
+
+@pytest.fixture(scope="module")
+def audiofile_tool():
+    """The reference's OWN codec (src/AudioFile.h, unmodified, compiled from where it lies by
+    oracle/ref_harness/Makefile into git-ignored oracle/_ref/).  The binary travels to the GPU box; the
+    reference checkout does not."""
+    if os.path.isdir("/root/reference"):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle", "ref_harness"), "../_ref/audiofile_tool"], check=True)
+    if not os.path.exists(AFTOOL):
+        pytest.skip("oracle/_ref/audiofile_tool not built (needs the reference checkout at build time)")
+    return AFTOOL
+
+
+def _decode_both(tool, aftool, path, tmp_path):
+    outs = []
+    for t, name in ((tool, "ours.f32"), (aftool, "ref.f32")):
+        r = subprocess.run([t, "decode", str(path), str(tmp_path / name)], capture_output=True, text=True)
+        if r.returncode != 0:
+            outs.append((r.returncode, None, None))
+            continue
+        ch, n, rate, bits = map(int, r.stdout.split())
+        outs.append((0, (ch, n, rate, bits), np.fromfile(tmp_path / name, np.float32).reshape(ch, n)))
+    return outs
+
+
+def test_cpp_codec_matches_audiofile_itself(tool, audiofile_tool, tmp_path):
+    """host/pv_wav.h against src/AudioFile.h ITSELF (:418-530 decode, :703-785 + :1045-1049 encode): same
+    accept/reject decision, same header fields, bit-identical samples and byte-identical 16-bit files."""
+    rng = np.random.default_rng(3)
+    # encode: random floats incl. out-of-range values and the clamp / truncation corner cases
+    x = rng.uniform(-1.3, 1.3, size=(2, 1201)).astype(np.float32)
+    x[1, :8] = [0.0, 1.0, -1.0, 0.99999, -0.99999, 1e-5, -1e-5, 0.5]
+    x.tofile(tmp_path / "x.f32")
+    subprocess.run([tool, "encode", str(tmp_path / "x.f32"), "2", str(tmp_path / "ours.wav")], check=True)
+    subprocess.run([audiofile_tool, "encode", str(tmp_path / "x.f32"), "2", str(tmp_path / "ref.wav")], check=True)
+    assert open(tmp_path / "ours.wav", "rb").read() == open(tmp_path / "ref.wav", "rb").read()
+    # decode: synthetic 16-bit stereo/mono, 24-bit with a trailing chunk, 8-bit
+    files = {"s16.wav": open(tmp_path / "ours.wav", "rb").read(),
+             "s24.wav": _wav24(rng.integers(-2 ** 23, 2 ** 23, size=(2, 333))),
+             "m24.wav": _wav24(rng.integers(-2 ** 23, 2 ** 23, size=(1, 50)), rate=44100)}
+    u8 = rng.integers(0, 256, size=200, dtype=np.uint8).tobytes()
+    files["u8.wav"] = b"RIFF" + struct.pack("<i", 36 + len(u8)) + b"WAVE" + b"fmt " + struct.pack(
+        "<ihhiihh", 16, 1, 1, 8000, 8000, 1, 8) + b"data" + struct.pack("<i", len(u8)) + u8
+    bad = bytearray(files["s16.wav"]); bad[20] = 3                       # IEEE float format tag: AudioFile.h:454
+    files["float.wav"] = bytes(bad)
+    bad = bytearray(files["s16.wav"]); bad[22] = 3                       # three channels: AudioFile.h:461
+    files["three.wav"] = bytes(bad)
+    for name, blob in files.items():
+        open(tmp_path / name, "wb").write(blob)
+        ours, ref = _decode_both(tool, audiofile_tool, tmp_path / name, tmp_path)
+        assert (ours[0] == 0) == (ref[0] == 0), name
+        if ref[0] == 0:
+            assert ours[1] == ref[1], name
+            assert np.array_equal(ours[2], ref[2]), name
+
+
+def test_cpp_codec_on_the_reference_wavs(tool, audiofile_tool, reference_dir, tmp_path):
+    """Every WAV of the reference's testtones/ (incl. the 24-bit MAT_ZO file with trailing LIST/id3 chunks, the
+    2-bytes-short *sine/*square files and the float WAVs AudioFile rejects) through both codecs."""
+    tdir = os.path.join(reference_dir, "testtones")
+    seen = 0
+    for name in sorted(os.listdir(tdir)):
+        if not name.endswith(".wav"):
+            continue
+        ours, ref = _decode_both(tool, audiofile_tool, os.path.join(tdir, name), tmp_path)
+        assert (ours[0] == 0) == (ref[0] == 0), name
+        if ref[0] != 0:
+            assert "FLOAT" in name or "float" in name, name               # only the fmt-3 files are rejected
+            continue
+        assert ours[1] == ref[1], name
+        size = os.path.getsize(os.path.join(tdir, name))
+        ch, n, _, bits = ref[1]
+        short = size < 44 + n * ch * bits // 8                            # the reference reads past its buffer here (UB):
+        k = n - 1 if short else n                                         # the frames that exist must agree; ours zero-fills
+        assert np.array_equal(ours[2][:, :k], ref[2][:, :k]), name
+        seen += 1
+    assert seen >= 10
+
+
+def test_wav_loader_rejects_malformed_files(tool, tmp_path):
+    """the loader must not trust the file (no out-of-bounds header reads, no huge allocations)."""
+    good = wo.encode_wav16(np.zeros((2, 64), np.float32))
+    cases = {
+        "trunc_fmt": good[:12] + b"fmt " + b"\x10\0\0\0" + b"\x01\0" + b"data" + b"\0" * 18,     # fmt fields cut short
+        "fmt_at_end": good[:12] + b"data" + struct.pack("<I", 8) + b"\0" * 28 + b"fmt",
+        "streaming_size": good[:40] + struct.pack("<I", 0xFFFFFFFF) + good[44:],                    # 4 GB claimed
+        "huge_size": good[:40] + struct.pack("<I", 0x7FFFFFF0) + good[44:],
+        "data_at_end": good[:36] + b"\0" * 8 + good[44:] + b"data\x01\0",
+    }
+    for name, blob in cases.items():
+        open(tmp_path / (name + ".wav"), "wb").write(blob)
+        r = subprocess.run([tool, "decode", str(tmp_path / (name + ".wav")), str(tmp_path / "o.f32")], capture_output=True, text=True)
+        assert r.returncode == 3, (name, r.returncode, r.stderr)                                    # an error, not a crash
+    # a file a little shorter than its header claims is still accepted and zero-filled (testtones/440sine.wav)
+    open(tmp_path / "short.wav", "wb").write(good[:-2])
+    r = subprocess.run([tool, "decode", str(tmp_path / "short.wav"), str(tmp_path / "o.f32")], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split()[1] == "64"
+
+
 @pytest.mark.gpu
 def test_cli_reproduces_golden_head(golden, tmp_path):
     """pv_cli in.wav t out.wav on the head of testtones/test.wav reproduces output/testout.wav +-1 LSB,
