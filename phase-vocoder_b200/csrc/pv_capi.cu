@@ -37,8 +37,6 @@ struct pv_handle {
     float2 *d_ft[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // segment plan cache
     // split of corrected streams into frame-range parts (intra-GPU phase-carry scan)
-    PvSegment *d_api_segs = nullptr;
-    size_t api_cap = 0;
     uint32_t *d_Pl = nullptr;
     int64_t *d_S = nullptr, *d_H = nullptr;
     uint32_t *d_Pf = nullptr;
@@ -56,8 +54,10 @@ struct pv_handle {
         int32_t n_segs = 0;
         uint64_t stamp = 0;
     };
-    Plan plans[8];
+    Plan plans[32];
     uint64_t plan_clock = 0;
+    // test / tuning knobs, read ONCE at pv_create (not on every call): PV_NO_SPLIT, PV_FORCE_GENERIC
+    bool env_no_split = false, env_force_generic = false;
     const Plan *agg_valid_for = nullptr;   // plan whose per-part sums pv_corrected_split_aggregate left in d_S / d_H / d_Pf
     float2 *d_fft_tw[14] = {};      // stand-alone FFT: n-th roots of unity per log2 n, built on first use
     // staging for the host-pointer entry point
@@ -313,7 +313,7 @@ int plan_corrected_split(pv_handle *h, int64_t n_streams, int64_t n_frames, int3
 // number of frame-range parts per stream for a corrected run of few streams (1 = do not split)
 int64_t corrected_parts(const pv_handle *h, int64_t n_streams, int64_t n_frames)
 {
-    if (getenv("PV_NO_SPLIT")) return 1;
+    if (h->env_no_split) return 1;
     const int64_t halo = (h->p.window - 1) / h->p.hop_out;
     const int64_t min_len = std::max<int64_t>(16 * (halo + 1), 32);     // keep the extra analysis + halo small
     int64_t parts = std::min<int64_t>(n_frames / min_len, (h->capacity * 2 + n_streams - 1) / n_streams);
@@ -382,6 +382,8 @@ int pv_create(const pv_params *params, pv_handle **out)
     h->p.device = device;
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
+    h->env_no_split = getenv("PV_NO_SPLIT") != nullptr;
+    h->env_force_generic = getenv("PV_FORCE_GENERIC") != nullptr;
     make_window(p.window_type, N, h->h_win);
     std::vector<float2> tw(N);
     for (int k = 0; k < N; k++) {
@@ -480,7 +482,6 @@ void pv_destroy(pv_handle *h)
     }
     for (auto e : h->pipe_events) cudaEventDestroy(e);
     for (auto p : h->d_fft_tw) cudaFree(p);
-    cudaFree(h->d_api_segs);
     cudaFree(h->d_S);
     cudaFree(h->d_H);
     cudaFree(h->d_Pf);
@@ -611,6 +612,7 @@ static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_
 static int aggregate_plain(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride, int64_t n_in, int64_t n_frames,
                            const uint32_t *P_prev, int64_t P_prev_stride, int32_t in_state, int64_t *sumD, uint32_t *P_first,
                            uint32_t *P_last, void *cuda_stream);
+static int launch_segments(pv_handle *h, PvProcessArgs &a, int64_t n_streams, int32_t flags, cudaStream_t st);
 
 int pv_corrected_aggregate(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride, int64_t n_in,
                            int64_t n_frames, const uint32_t *P_prev, int64_t *sumD, uint32_t *P_first,
@@ -629,7 +631,7 @@ int pv_corrected_aggregate(pv_handle *h, const float *in, int64_t n_streams, int
             h->agg_valid_for = nullptr;          // the shared per-part sums are about to be overwritten
             const int nb = h->p.window / 2 + 1;
             PvAggArgs ag{in, in_stride, n_in, pl->d_agg_segs, pl->n_segs, P_prev, (int64_t)nb, h->d_S, nullptr, h->d_Pf, h->d_Pl, 0};
-            if (h->fused && !getenv("PV_FORCE_GENERIC")) PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, ag, (cudaStream_t)cuda_stream));
+            if (h->fused && !h->env_force_generic) PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, ag, (cudaStream_t)cuda_stream));
             else PV_CUDA(pv_launch_aggregate_generic(h->dev, ag, (cudaStream_t)cuda_stream));
             PV_CUDA(pv_launch_reduce_parts(nb, n_streams, (int32_t)parts, h->d_S, h->d_Pf, h->d_Pl, sumD, P_first, P_last,
                                            (cudaStream_t)cuda_stream));
@@ -647,27 +649,28 @@ static int aggregate_plain(pv_handle *h, const float *in, int64_t n_streams, int
                            const uint32_t *P_prev, int64_t P_prev_stride, int32_t in_state, int64_t *sumD, uint32_t *P_first,
                            uint32_t *P_last, void *cuda_stream)
 {
-    std::vector<PvSegment> segs((size_t)n_streams);
-    for (int64_t s = 0; s < n_streams; s++) {
-        PvSegment g{};
-        g.stream = (int32_t)s;
-        g.state_idx = (int32_t)s;
-        g.carry_in = P_prev != nullptr;
-        g.k_begin = 0;
-        g.k_emit = 0;
-        g.k_end = n_frames;
-        segs[(size_t)s] = g;
+    // one table per (streams, frames, carry) shape in the plan cache: a queued launch never sees its table rewritten
+    bool hit = false;
+    pv_handle::Plan *pl = find_plan(h, 2, n_streams, n_frames, 0, P_prev != nullptr ? 1 : 0, 0, &hit);
+    if (!hit) {
+        std::vector<PvSegment> segs((size_t)n_streams);
+        for (int64_t s = 0; s < n_streams; s++) {
+            PvSegment g{};
+            g.stream = (int32_t)s;
+            g.state_idx = (int32_t)s;
+            g.carry_in = P_prev != nullptr;
+            g.k_begin = 0;
+            g.k_emit = 0;
+            g.k_end = n_frames;
+            segs[(size_t)s] = g;
+        }
+        int rc = upload_segments(&pl->d_segs, &pl->cap, segs);
+        if (rc != PV_OK) return rc;
+        pl->n_segs = (int32_t)n_streams;
+        pl->kind = 2;
     }
-    if (segs.size() > h->api_cap) {
-        cudaFree(h->d_api_segs);
-        h->d_api_segs = nullptr;
-        h->api_cap = 0;
-        PV_CUDA(cudaMalloc((void **)&h->d_api_segs, sizeof(PvSegment) * segs.size()));
-        h->api_cap = segs.size();
-    }
-    PV_CUDA(cudaMemcpy(h->d_api_segs, segs.data(), sizeof(PvSegment) * segs.size(), cudaMemcpyHostToDevice));
-    PvAggArgs a{in, in_stride, n_in, h->d_api_segs, (int32_t)n_streams, P_prev, P_prev_stride, sumD, nullptr, P_first, P_last, in_state};
-    if (h->fused && !getenv("PV_FORCE_GENERIC")) PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, a, (cudaStream_t)cuda_stream));
+    PvAggArgs a{in, in_stride, n_in, pl->d_segs, (int32_t)n_streams, P_prev, P_prev_stride, sumD, nullptr, P_first, P_last, in_state};
+    if (h->fused && !h->env_force_generic) PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, a, (cudaStream_t)cuda_stream));
     else PV_CUDA(pv_launch_aggregate_generic(h->dev, a, (cudaStream_t)cuda_stream));
     h->launches++;
     return PV_OK;
@@ -707,6 +710,47 @@ int pv_process_device_ex(pv_handle *h, const float *in, int64_t n_streams, int64
                         out_stream_stride, out_voice_stride, state, flags, cuda_stream);
 }
 
+// Launches the stream kernel of the handle's mode over the segment table in `a` (timing events, launch count).
+// Shared by pv_process_* (tables from the plan cache) and the real-time server (a table it owns).
+static int launch_segments(pv_handle *h, PvProcessArgs &a, int64_t n_streams, int32_t flags, cudaStream_t st)
+{
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->timing) {
+        PV_CUDA(cudaEventCreate(&e0));
+        PV_CUDA(cudaEventCreate(&e1));
+        PV_CUDA(cudaEventRecord(e0, st));
+    }
+    const bool force_generic = h->env_force_generic;
+    if (h->p.mode == PV_MODE_CORRECTED && (!h->fused || force_generic)) {
+        // shape-generic kernels work on the per-stream state in global memory and always update it.  Without a
+        // caller state, or with a state that is carried IN only (the contract: written only under CARRY_OUT), they
+        // run on a library-owned scratch copy, so a caller can re-run from a saved state
+        const bool in_only = a.state && (flags & PV_PROCESS_CARRY_IN) && !(flags & PV_PROCESS_CARRY_OUT);
+        if (!a.state || in_only) {
+            const size_t need = (size_t)n_streams * pv_state_bytes(h);
+            if (need > h->scratch_cap) {
+                if (h->scratch_cap) cudaDeviceSynchronize();     // queued launches may still use the old scratch
+                cudaFree(h->d_scratch_state);
+                h->d_scratch_state = nullptr;
+                h->scratch_cap = 0;
+                PV_CUDA(cudaMalloc(&h->d_scratch_state, need));
+                h->scratch_cap = need;
+            }
+            if (in_only) PV_CUDA(cudaMemcpyAsync(h->d_scratch_state, a.state, need, cudaMemcpyDeviceToDevice, st));
+            a.state = (unsigned char *)h->d_scratch_state;
+        }
+        PV_CUDA(pv_launch_corrected_generic(h->dev, a, st));
+    } else if (h->p.mode == PV_MODE_CORRECTED) PV_CUDA(pv_launch_corrected_fused(h->dev, h->ft, a, st));
+    else if (h->fused && !force_generic) PV_CUDA(pv_launch_compat_fused(h->dev, h->ft, a, st));
+    else PV_CUDA(pv_launch_compat_generic(h->dev, a, st));
+    h->launches++;
+    if (h->timing) {
+        PV_CUDA(cudaEventRecord(e1, st));
+        h->events.emplace_back(e0, e1);
+    }
+    return PV_OK;
+}
+
 // `plan_streams` >= n_streams: the segment table is planned (and cached) for plan_streams streams; a call
 // with fewer streams uses its stream-major prefix.  Lets the pipelined host path reuse one plan for all chunks.
 static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_t plan_streams, int64_t in_stride,
@@ -728,7 +772,7 @@ static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     // ---- corrected mode, few streams: split into frame-range parts with an on-device phase-carry scan ----
-    const bool force_generic0 = getenv("PV_FORCE_GENERIC") != nullptr;
+    const bool force_generic0 = h->env_force_generic;
     if (h->p.mode == PV_MODE_CORRECTED && plan_streams == n_streams) {
         const bool user_carry = (flags & PV_PROCESS_CARRY_IN) != 0;
         const int64_t parts = corrected_parts(h, n_streams, n_frames);
@@ -819,36 +863,7 @@ static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_
     a.state_stride = (int64_t)pv_state_bytes(h);
     a.segs = pl->d_segs;
     a.n_segs = (int32_t)((int64_t)pl->n_segs / plan_streams * n_streams);      // stream-major table
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (h->timing) {
-        PV_CUDA(cudaEventCreate(&e0));
-        PV_CUDA(cudaEventCreate(&e1));
-        PV_CUDA(cudaEventRecord(e0, st));
-    }
-    const bool force_generic = getenv("PV_FORCE_GENERIC") != nullptr;
-    if (h->p.mode == PV_MODE_CORRECTED && (!h->fused || force_generic)) {
-        // shape-generic kernel: works on the per-stream state in global memory; without a caller state a
-        // library-owned scratch state is used
-        if (!a.state) {
-            const size_t need = (size_t)n_streams * pv_state_bytes(h);
-            if (need > h->scratch_cap) {
-                cudaFree(h->d_scratch_state);
-                h->d_scratch_state = nullptr;
-                PV_CUDA(cudaMalloc(&h->d_scratch_state, need));
-                h->scratch_cap = need;
-            }
-            a.state = (unsigned char *)h->d_scratch_state;
-        }
-        PV_CUDA(pv_launch_corrected_generic(h->dev, a, st));
-    } else if (h->p.mode == PV_MODE_CORRECTED) PV_CUDA(pv_launch_corrected_fused(h->dev, h->ft, a, st));
-    else if (h->fused && !force_generic) PV_CUDA(pv_launch_compat_fused(h->dev, h->ft, a, st));
-    else PV_CUDA(pv_launch_compat_generic(h->dev, a, st));
-    h->launches++;
-    if (h->timing) {
-        PV_CUDA(cudaEventRecord(e1, st));
-        h->events.emplace_back(e0, e1);
-    }
-    return PV_OK;
+    return launch_segments(h, a, n_streams, flags, st);
 }
 
 }  // extern "C"
@@ -863,6 +878,16 @@ static int process_host_impl(pv_handle *h, const void *in_v, int64_t n_streams, 
 {
     if (!h || !in_v || !out_v) return fail(PV_ERR_PARAM, "pv_process_host: null argument");
     if (n_streams <= 0 || n_frames <= 0) return PV_OK;
+    {   // validate the layout before any copy is queued
+        const int64_t need_out = n_frames * h->p.hop_out;
+        if (n_in < 0 || in_stride < n_in)
+            return fail(PV_ERR_PARAM, "pv_process_host: bad input layout (n_in=%lld in_stride=%lld)", (long long)n_in, (long long)in_stride);
+        if (h->p.n_voices > 1 && out_voice_stride < need_out)
+            return fail(PV_ERR_PARAM, "pv_process_host: out_voice_stride %lld < n_frames*hop_out = %lld", (long long)out_voice_stride,
+                        (long long)need_out);
+        if (n_streams > 1 && out_stream_stride < need_out + (int64_t)(h->p.n_voices - 1) * out_voice_stride)
+            return fail(PV_ERR_PARAM, "pv_process_host: out_stream_stride %lld too small", (long long)out_stream_stride);
+    }
     if ((flags & (PV_PROCESS_CARRY_IN | PV_PROCESS_CARRY_OUT)) && !state)
         return fail(PV_ERR_PARAM, "pv_process_host: carry requested without a state buffer");
     DeviceGuard guard(h->device);
@@ -870,7 +895,7 @@ static int process_host_impl(pv_handle *h, const void *in_v, int64_t n_streams, 
     const size_t esz = PCM16 ? 2 : 4;
     // device rows are padded to 4 samples so that the kernels keep their 16-byte aligned fast paths
     const int64_t n_in_p = (n_in + 3) & ~int64_t(3);
-    int rc = ensure(&h->d_in, &h->in_cap, (size_t)(n_streams * n_in_p));
+    int rc = ensure(&h->d_in, &h->in_cap, std::max<size_t>(4, (size_t)(n_streams * n_in_p)));   // n_in == 0: all-zero input, not a null pointer
     if (rc == PV_OK) rc = ensure(&h->d_out, &h->out_cap, (size_t)(n_streams * V * n_out));
     if (rc == PV_OK && PCM16) rc = ensure(&h->d_in16, &h->in16_cap, (size_t)(n_streams * n_in_p) / 2);
     if (rc == PV_OK && PCM16) rc = ensure(&h->d_out16, &h->out16_cap, (size_t)(n_streams * V * n_out + 1) / 2);
@@ -1011,6 +1036,11 @@ struct pv_rt {
     float *d_buf[2] = {nullptr, nullptr};     // [S][row]: ring history (N-Ha) followed by the new block
     float *d_out = nullptr;
     void *d_state = nullptr;
+    // The server's OWN segment table (one segment per stream: frames [0, B), state carried in and out).  The
+    // recorded graphs bake device pointers in, so nothing they reference may live in the handle's shared caches
+    // (plan LRU, frame-range-split scratch): other shapes run on the same handle between two blocks would evict
+    // or reallocate those and the next replay would read a foreign table or freed memory.
+    PvSegment *d_segs = nullptr;
     float *h_in = nullptr, *h_out = nullptr;  // page-locked staging
     cudaStream_t st = nullptr;
     cudaGraphExec_t exec[2] = {nullptr, nullptr};
@@ -1027,8 +1057,20 @@ int rt_enqueue(pv_rt *rt, int p)
     const int64_t V = h->p.n_voices;
     PV_CUDA(cudaMemcpy2DAsync(rt->d_buf[p] + rt->hist, sizeof(float) * rt->row, rt->h_in, sizeof(float) * rt->in_w,
                               sizeof(float) * rt->in_w, (size_t)rt->S, cudaMemcpyHostToDevice, rt->st));
-    int rc = pv_process_device_ex(h, rt->d_buf[p], rt->S, rt->row, rt->hist + rt->in_w, rt->B, rt->B, 0, rt->d_out, V * rt->out_w,
-                                  rt->out_w, rt->d_state, PV_PROCESS_CARRY_IN | PV_PROCESS_CARRY_OUT, rt->st);
+    PvProcessArgs a{};
+    a.in = rt->d_buf[p];
+    a.in_stride = rt->row;
+    a.n_in = rt->hist + rt->in_w;
+    a.n_analysed = rt->B;
+    a.n_frames = rt->B;
+    a.out = rt->d_out;
+    a.out_stream_stride = V * rt->out_w;
+    a.out_voice_stride = rt->out_w;
+    a.state = (unsigned char *)rt->d_state;
+    a.state_stride = (int64_t)pv_state_bytes(h);
+    a.segs = rt->d_segs;
+    a.n_segs = (int32_t)rt->S;
+    int rc = launch_segments(h, a, rt->S, PV_PROCESS_CARRY_IN | PV_PROCESS_CARRY_OUT, rt->st);
     if (rc != PV_OK) return rc;
     if (rt->hist > 0)       // ring advance: the last N-Ha samples become the next block's history
         PV_CUDA(cudaMemcpy2DAsync(rt->d_buf[1 - p], sizeof(float) * rt->row, rt->d_buf[p] + rt->in_w, sizeof(float) * rt->row,
@@ -1062,6 +1104,7 @@ void pv_rt_close(pv_rt *rt)
     cudaFree(rt->d_buf[1]);
     cudaFree(rt->d_out);
     cudaFree(rt->d_state);
+    cudaFree(rt->d_segs);
     cudaFreeHost(rt->h_in);
     cudaFreeHost(rt->h_out);
     if (rt->st) cudaStreamDestroy(rt->st);
@@ -1070,7 +1113,8 @@ void pv_rt_close(pv_rt *rt)
 
 int pv_rt_open(pv_handle *h, int64_t n_streams, int32_t block_frames, pv_rt **out)
 {
-    if (!h || !out || n_streams <= 0 || block_frames <= 0) return fail(PV_ERR_PARAM, "pv_rt_open: bad argument");
+    if (!h || !out || n_streams <= 0 || n_streams > 0x7fffffffLL || block_frames <= 0)
+        return fail(PV_ERR_PARAM, "pv_rt_open: bad argument");
     *out = nullptr;
     DeviceGuard guard(h->device);
     pv_rt *rt = new pv_rt;
@@ -1091,13 +1135,29 @@ int pv_rt_open(pv_handle *h, int64_t n_streams, int32_t block_frames, pv_rt **ou
     ck(cudaMalloc((void **)&rt->d_buf[1], sizeof(float) * (size_t)(rt->S * rt->row)), "ring");
     ck(cudaMalloc((void **)&rt->d_out, sizeof(float) * (size_t)(rt->S * V * rt->out_w)), "output");
     ck(cudaMalloc(&rt->d_state, (size_t)rt->S * pv_state_bytes(h)), "state");
+    {
+        std::vector<PvSegment> segs((size_t)rt->S);
+        for (int64_t s = 0; s < rt->S; s++) {
+            PvSegment g{};
+            g.stream = (int32_t)s;
+            g.state_idx = (int32_t)s;
+            g.k_begin = 0;
+            g.k_emit = 0;
+            g.k_end = block_frames;
+            g.carry_in = 1;
+            g.carry_out = 1;
+            segs[(size_t)s] = g;
+        }
+        ck(cudaMalloc((void **)&rt->d_segs, sizeof(PvSegment) * segs.size()), "segment table");
+        if (rc == PV_OK) ck(cudaMemcpy(rt->d_segs, segs.data(), sizeof(PvSegment) * segs.size(), cudaMemcpyHostToDevice), "segment table");
+    }
     ck(cudaHostAlloc((void **)&rt->h_in, sizeof(float) * (size_t)(rt->S * rt->in_w), cudaHostAllocDefault), "pinned input");
     ck(cudaHostAlloc((void **)&rt->h_out, sizeof(float) * (size_t)(rt->S * V * rt->out_w), cudaHostAllocDefault), "pinned output");
     if (rc == PV_OK) {
         memset(rt->h_in, 0, sizeof(float) * (size_t)(rt->S * rt->in_w));
         rc = rt_clear(rt);
     }
-    // one eager block: builds the segment plan and sets the kernel attributes, neither of which can be recorded
+    // one eager block: sets the kernel attributes (cudaFuncSetAttribute cannot be recorded)
     const int64_t l0 = h->launches;
     if (rc == PV_OK) rc = rt_enqueue(rt, 0);
     if (rc == PV_OK) ck(cudaStreamSynchronize(rt->st), "first block");

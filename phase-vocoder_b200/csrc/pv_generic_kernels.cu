@@ -1049,9 +1049,12 @@ cudaError_t pv_launch_pcm16_to_float(const int16_t *in, float *out, int64_t rows
                                      int64_t n_valid, cudaStream_t st)
 {
     if (rows <= 0 || c1 <= c0) return cudaSuccess;
-    if (rows > 65535 || (pitch & 3) || (c0 & 3)) return cudaErrorInvalidValue;
-    const dim3 grid((unsigned)(((c1 - c0 + 3) / 4 + 255) / 256), (unsigned)rows);
-    pcm16_to_float_kernel<<<grid, 256, 0, st>>>(in, out, pitch, c0, c1, n_valid);
+    if ((pitch & 3) || (c0 & 3)) return cudaErrorInvalidValue;
+    for (int64_t r0 = 0; r0 < rows; r0 += 65535) {          // rows ride in gridDim.y: slabs of at most 65535
+        const int64_t nr = std::min<int64_t>(65535, rows - r0);
+        const dim3 grid((unsigned)(((c1 - c0 + 3) / 4 + 255) / 256), (unsigned)nr);
+        pcm16_to_float_kernel<<<grid, 256, 0, st>>>(in + r0 * pitch, out + r0 * pitch, pitch, c0, c1, n_valid);
+    }
     return cudaGetLastError();
 }
 

@@ -248,3 +248,40 @@ def test_host_pipeline_chunks_over_frames_bit_exact(monkeypatch, S, nf):
     a = pv.process_host(x, k, state=st, flags=pvb200.CARRY_OUT)
     b = pv.process_host(np.ascontiguousarray(x[:, k * Ha:]), nf - k, state=st, flags=pvb200.CARRY_IN | pvb200.CARRY_OUT)
     assert np.array_equal(np.concatenate([a, b], axis=2), d)
+
+
+@pytest.mark.parametrize("N,Ha,betas,force", [(128, 32, [1.5], False), (4096, 1024, [SEMI7], False),
+                                              (4096, 1024, [1.0, 1.26, 1.5], False), (1024, 256, [1.5], True),
+                                              (1024, 256, [1.5], False)])
+def test_carry_in_only_leaves_the_state_untouched(monkeypatch, N, Ha, betas, force):
+    """include/pv_b200.h: the state is written only under PV_PROCESS_CARRY_OUT.  ADVICE r01: the generic kernels
+    (windows 64/128/4096, PV_FORCE_GENERIC) used to update a carried-in state in place; now every kernel family
+    lets a caller re-run from a saved state and get the same samples."""
+    if force:
+        monkeypatch.setenv("PV_FORCE_GENERIC", "1")
+    monkeypatch.setenv("PV_NO_SPLIT", "1")
+    nf, k = 30, 11
+    betas = [f32(b) for b in betas]
+    x = dev(np.stack([multitone(N + nf * Ha, seed=77 + s, noise=1e-3) for s in range(2)]))
+    pv = make(N, Ha, Ha, betas)
+    st = torch.zeros((2, pv.state_bytes()), dtype=torch.uint8, device="cuda")
+    pv.process(x, k, state=st, flags=pvb200.CARRY_OUT)
+    saved = st.clone()
+    a = pv.process(x[:, k * Ha:], nf - k, state=st, flags=pvb200.CARRY_IN).cpu().numpy()
+    assert torch.equal(st, saved)
+    b = pv.process(x[:, k * Ha:], nf - k, state=st, flags=pvb200.CARRY_IN).cpu().numpy()
+    assert np.array_equal(a, b)
+    full = pv.process(x, nf).cpu().numpy()
+    assert np.array_equal(a, full[:, :, k * Ha:])
+
+
+def test_pcm16_host_path_takes_more_than_65535_streams():
+    """rows ride in gridDim.y of the conversion kernels; both directions now loop over slabs."""
+    N, H, nf, S = 64, 16, 6, 70000
+    rng = np.random.default_rng(5)
+    xi = rng.integers(-20000, 20000, size=(S, N + nf * H), dtype=np.int16)
+    pv = make(N, H, H, [1.0])
+    got = pv.process_host_pcm16(xi, nf)
+    assert got.shape == (S, 1, nf * H)
+    ref = pv.process_host_pcm16(np.ascontiguousarray(xi[65530:65540]), nf)
+    assert np.array_equal(got[65530:65540], ref)

@@ -57,3 +57,32 @@ def test_blocks_equal_offline_delayed_input(mode, N, Ha, Hs, B, S):
     rt.step()
     assert pv.launch_count() == n0 + 1           # one fused kernel per block
     rt.close()
+
+
+@pytest.mark.parametrize("mode", ["compat", "corrected"])
+def test_server_survives_other_shapes_on_the_same_handle(mode):
+    """the recorded graphs bake device pointers in, so the server must own everything they reference.
+    Between two blocks the SAME handle runs 40 other shapes (more than the plan cache holds, incl. few-stream
+    corrected runs that take the frame-range split and reallocate its scratch); the blocks must still equal the
+    offline output bit for bit."""
+    N, Ha, Hs, B, S, blocks = 512, 128, 128, 2, 3, 6
+    if mode == "compat":
+        pv = pvb200.PhaseVocoder(N, hop_in=Ha, hop_out=Hs, mode=pvb200.MODE_COMPAT)
+    else:
+        pv = pvb200.PhaseVocoder(N, hop_in=Ha, hop_out=Hs, mode=pvb200.MODE_CORRECTED,
+                                 window_type=pvb200.WIN_HANN_PERIODIC, pitch=(f32(1.26),))
+    x = np.stack([multitone(blocks * B * Ha, seed=90 + s) for s in range(S)])
+    rt = pvb200.RealtimeServer(pv, S, B)
+    want = offline(pv, x, rt.latency, blocks * B)
+    noise = torch.randn((5, N + 4000 * Ha), device="cuda") * 0.1
+    got, shape = [], 0
+    for b in range(blocks):
+        rt.input[:] = x[:, b * B * Ha:(b + 1) * B * Ha]
+        got.append(rt.step().copy())
+        for _ in range(8):                                   # 8 new shapes per block: 48 in all, cache holds 32
+            shape += 1
+            pv.process(noise[:1 + shape % 5], 20 + 3 * shape)
+        pv.process(noise[:1], 1500 + 100 * b)                # one long stream: frame-range split in corrected mode
+    torch.cuda.synchronize()
+    assert np.array_equal(np.concatenate(got, axis=2), want)
+    rt.close()
