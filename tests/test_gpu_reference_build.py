@@ -19,6 +19,9 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "oracle", "_ref", "pv_ref_harness")
+# windows > 512: the same sources with ONLY the launch geometry of karnel/kernel.cu:301,314,337,354,380,393,406,419
+# rewritten to blocks of <= 256 threads (oracle/ref_harness/Makefile: a generated, git-ignored copy)
+EXE_PATCHED = os.path.join(ROOT, "oracle", "_ref", "pv_ref_harness_patched")
 
 
 @pytest.fixture(scope="module")
@@ -28,11 +31,19 @@ def harness():
     return EXE
 
 
-@pytest.mark.parametrize("N,hopdiv", [(256, 2), (256, 4), (512, 4), (128, 2)])
+@pytest.mark.parametrize("N,hopdiv", [(256, 2), (256, 4), (512, 4), (128, 2),
+                                      (256, -4), (1024, -4), (2048, -4), (2048, -2), (4096, -4)])
 def test_reference_build_matches_oracle_and_cuda_path(harness, tmp_path, N, hopdiv):
+    """hopdiv < 0: the launch-patched build (the only one that can run windows > 512; window 256 runs on both
+    builds to show that the patch changes nothing).  (2048, 4) is BASELINE.json's headline shape / C2."""
     import pvb200
+    if hopdiv < 0:
+        hopdiv = -hopdiv
+        harness = EXE_PATCHED
+        if not os.path.exists(harness):
+            pytest.skip("oracle/_ref/pv_ref_harness_patched not built (needs /root/reference at build time)")
     H = N // hopdiv
-    nf = 120
+    nf = 120 if N <= 512 else 40
     n = nf * H + 17                                    # ragged end: last frames read past the input
     x = multitone(n, seed=N + hopdiv)
     fin, fout, fspec = tmp_path / "in.f32", tmp_path / "out.f32", tmp_path / "spec.f32"
