@@ -122,19 +122,28 @@ uint32_t pvo_phase_turns32(double re, double im)
 
 void pvo_fft_f64(double *re, double *im, int n, int dir) { fft_f64(re, im, n, dir); }
 
-int pvo_process_corrected(const float *x, long n_in, int N, int Ha, int Hs, const float *win,
-                          int n_voices, const double *beta, long n_frames,
-                          pvo_corrected_state *state, int precision,
-                          double *out, long out_stride)
+int pvo_process_corrected_traced(const float *x, long n_in, int N, int Ha, int Hs, const float *win,
+                                 int n_voices, const double *beta, long n_frames,
+                                 pvo_corrected_state *state, int precision,
+                                 double *out, long out_stride, const pvo_corrected_trace *trace)
 {
     if (N < 4 || (N & (N - 1)) || Ha < 1 || Hs < 1 || Hs > N || n_voices < 1 ||
         n_voices > PVO_MAX_VOICES)
         return -1;
     if (precision == 32)
         return corrected_process_f32(x, n_in, N, Ha, Hs, win, n_voices, beta, n_frames, state, out,
-                                     out_stride);
+                                     out_stride, trace);
     return corrected_process_f64(x, n_in, N, Ha, Hs, win, n_voices, beta, n_frames, state, out,
-                                 out_stride);
+                                 out_stride, trace);
+}
+
+int pvo_process_corrected(const float *x, long n_in, int N, int Ha, int Hs, const float *win,
+                          int n_voices, const double *beta, long n_frames,
+                          pvo_corrected_state *state, int precision,
+                          double *out, long out_stride)
+{
+    return pvo_process_corrected_traced(x, n_in, N, Ha, Hs, win, n_voices, beta, n_frames, state, precision, out,
+                                        out_stride, NULL);
 }
 
 int pvo_corrected_aggregate(const float *x, long n_in, int N, int Ha, const float *win,

@@ -124,6 +124,24 @@ int pvo_process_corrected(const float *x, long n_in, int N, int Ha, int Hs, cons
                           pvo_corrected_state *state, int precision,
                           double *out, long out_stride);
 
+/* Decision trace of the corrected mode, for DECISION-ALIGNED parity checks (DESIGN.md "conditioning of the
+ * phase unwrap").  The unwrap D = (int32)(P_k - P_{k-1} - nomA) is discontinuous at +-1/2 turn, so two correct
+ * implementations with different rounding may pick neighbouring aliases for a bin whose phase difference lies
+ * within their phase error of the boundary.  A checker records the oracle's own decisions (D_out, with mag_out to
+ * judge the bin's phase uncertainty), compares them with the implementation's, verifies that every disagreement is
+ * such a boundary case, and re-runs the oracle with those few decisions moved (unwrap_adjust = +-1 turn):
+ * everything else must then agree to the full tolerance.  All arrays are [n_frames][N/2+1]; any may be NULL. */
+typedef struct pvo_corrected_trace {
+    int32_t *D_out;               /* the oracle's unwrapped phase difference, turns*2^32 (0 for a first frame) */
+    double *mag_out;              /* |X| per bin */
+    const int8_t *unwrap_adjust;  /* added to D in whole turns before the accumulation */
+} pvo_corrected_trace;
+
+int pvo_process_corrected_traced(const float *x, long n_in, int N, int Ha, int Hs, const float *win,
+                                 int n_voices, const double *beta, long n_frames,
+                                 pvo_corrected_state *state, int precision,
+                                 double *out, long out_stride, const pvo_corrected_trace *trace);
+
 /* Analysis only: per-bin sum of D_k = (int32)(P_k - P_{k-1} - nomA) over frames [0,n_frames) as
  * int64, plus P of the last frame -- the "segment aggregate" of the frame-range scan. */
 int pvo_corrected_aggregate(const float *x, long n_in, int N, int Ha, const float *win,

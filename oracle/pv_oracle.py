@@ -59,6 +59,9 @@ def lib():
         L.pvo_process_corrected.argtypes = [fp, C.c_long, ip, ip, ip, fp, ip, dp, C.c_long,
                                             C.POINTER(_State), ip, dp, C.c_long]
         L.pvo_process_corrected.restype = ip
+        L.pvo_process_corrected_traced.argtypes = [fp, C.c_long, ip, ip, ip, fp, ip, dp, C.c_long,
+                                                   C.POINTER(_State), ip, dp, C.c_long, C.POINTER(_Trace)]
+        L.pvo_process_corrected_traced.restype = ip
         L.pvo_corrected_aggregate.argtypes = [fp, C.c_long, ip, ip, fp, C.c_long, ip, C.POINTER(C.c_uint32), ip,
                                               C.POINTER(C.c_int64), C.POINTER(C.c_uint32)]
         L.pvo_corrected_aggregate.restype = ip
@@ -69,6 +72,11 @@ def lib():
 class _State(C.Structure):
     _fields_ = [("have_prev", C.c_int32), ("P_prev", C.POINTER(C.c_uint32)),
                 ("psi", C.POINTER(C.c_uint64)), ("tail", C.POINTER(C.c_double))]
+
+
+class _Trace(C.Structure):
+    _fields_ = [("D_out", C.POINTER(C.c_int32)), ("mag_out", C.POINTER(C.c_double)),
+                ("unwrap_adjust", C.POINTER(C.c_int8))]
 
 
 def _f(a):
@@ -171,6 +179,29 @@ def process_corrected(x: np.ndarray, N: int, Ha: int, Hs: int, win: np.ndarray, 
         raise ValueError("pvo_process_corrected: bad parameters")
     st.have_prev = cs.have_prev
     return out, st
+
+
+def process_corrected_traced(x, N, Ha, Hs, win, betas, n_frames, unwrap_adjust=None, precision=64):
+    """Corrected mode with the decision trace (pv_oracle.h, pvo_corrected_trace).
+    Returns (out[V, n_frames*Hs], D[n_frames, N/2+1] int32, mag[n_frames, N/2+1]); unwrap_adjust (int8, same
+    shape as D) moves individual unwrap decisions by whole turns."""
+    x = np.ascontiguousarray(x, np.float32)
+    betas = np.ascontiguousarray(betas, np.float64)
+    V, nb = len(betas), N // 2 + 1
+    st = CorrectedState(N, V)
+    out = np.zeros((V, n_frames * Hs), np.float64)
+    D = np.zeros((n_frames, nb), np.int32)
+    mag = np.zeros((n_frames, nb), np.float64)
+    adj = None if unwrap_adjust is None else np.ascontiguousarray(unwrap_adjust, np.int8)
+    assert adj is None or adj.shape == D.shape
+    tr = _Trace(D.ctypes.data_as(C.POINTER(C.c_int32)), _d(mag),
+                None if adj is None else adj.ctypes.data_as(C.POINTER(C.c_int8)))
+    cs = _State(0, st.P_prev.ctypes.data_as(C.POINTER(C.c_uint32)), st.psi.ctypes.data_as(C.POINTER(C.c_uint64)), _d(st.tail))
+    rc = lib().pvo_process_corrected_traced(_f(x), len(x), N, Ha, Hs, _f(win), V, _d(betas), n_frames,
+                                            C.byref(cs), precision, _d(out), n_frames * Hs, C.byref(tr))
+    if rc != 0:
+        raise ValueError("pvo_process_corrected_traced: bad parameters")
+    return out, D, mag
 
 
 def corrected_tables(N: int, Ha: int, Hs: int, beta: float):

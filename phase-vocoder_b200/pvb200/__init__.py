@@ -219,6 +219,23 @@ class PhaseVocoder:
                                              _ptr(P_first), _ptr(P_last), _cuda_stream()))
         return sumD, P_first, P_last
 
+    def unwrap_decisions(self, x, n_frames):
+        """Diagnostic: the unwrapped phase difference D_k[b] (turns * 2^32, int32) the device computes for every frame
+        of ONE stream x [n] -- through the public aggregate entry point, applied to the n_frames-1 overlapping two-frame
+        windows of the stream (rows of stride hop_in; the aggregate of frames {k-1, k} is D_k).  D_0 = 0.  The
+        aggregate shares the processing kernels' forward transform, so these are the decisions process() takes
+        (tests/aligned.py uses them for the decision-aligned parity check)."""
+        import torch
+        N, Ha = self.nSamps, self.hopSize
+        need = (n_frames - 1) * Ha + N + Ha
+        xp = torch.zeros(need + 8, dtype=torch.float32, device=x.device)
+        xp[:min(need, x.numel())] = x.reshape(-1)[:need]
+        rows = torch.as_strided(xp, (n_frames - 1, N + Ha), (Ha, 1))
+        sumD, _, _ = self.aggregate(rows, 2)
+        D = torch.zeros((n_frames, N // 2 + 1), dtype=torch.int32, device=x.device)
+        D[1:] = sumD.to(torch.int32)
+        return D
+
     def split_aggregate(self, x, n_frames, state=None, skip=0, n_in=None):
         """The analysis pass of process(x, n_frames, state=state, flags=CARRY_IN if state is not None, skip=skip) on
         its own: sumD int64 [S, nb] over all frames of that call.  Follow it with that process call and

@@ -13,6 +13,11 @@
 
 using namespace pvfused;
 
+// Race-check self test (tsan_main.cpp): every thread skips its g_drop_barrier-th barrier (all threads skip the same
+// one, so the barrier phases stay aligned).  -1 = run normally.  ThreadSanitizer must then report a race.
+static int g_drop_barrier = -1;
+extern "C" void emul_drop_barrier(int k) { g_drop_barrier = k; }
+
 template <int LOG2N>
 static int run(const float *x, long n_in, int Ha, int Hs, const float *win, long n_analysed, long n_frames,
                int nan_compat, float *out)
@@ -28,7 +33,8 @@ static int run(const float *x, long n_in, int Ha, int Hs, const float *win, long
     const bool use_ring = (Ha % (2 * S::S1)) == 0;
     float *ring = use_ring ? ringbuf.data() : nullptr;
     auto body = [&](int tid) {
-        auto sync = [&]() { bar.arrive_and_wait(); };
+        int nbar = 0;
+        auto sync = [&]() { if (nbar++ != g_drop_barrier) bar.arrive_and_wait(); };
         int pos0 = 0;
         if (use_ring && n_analysed > 0) {
             FrameIO io0{x, n_in, 0, true, (Ha % 2) == 0};
@@ -117,7 +123,8 @@ static int run_corrected(const float *x, long n_in, int Ha, int Hs, const float 
     const bool use_ring = (Ha % 2) == 0 && Ha <= N;
     float *ring = use_ring ? ringbuf.data() : nullptr;
     auto body = [&](int tid) {
-        auto sync = [&]() { bar.arrive_and_wait(); };
+        int nbar = 0;
+        auto sync = [&]() { if (nbar++ != g_drop_barrier) bar.arrive_and_wait(); };
         CState st{};
         const CThreadTw tt = load_cthread_tw<LOG2N>(tid, tb);
         int pos0 = 0;

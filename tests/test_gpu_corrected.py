@@ -3,21 +3,21 @@ scaling -> fixed-point phase accumulation -> WOLA), through the C ABI, against t
 
 The reference does not implement this stage (PARITY UNPINNED): the oracle is the
 specification and is itself checked by analytic properties in tests/test_oracle_props.py.
-Tolerance: output SNR >= 100 dB against the fp64 oracle.  The integer phase path is exact, so the
-only differences are the fp32 FFTs, atan2 and sincos -- with ONE inherent exception (DESIGN.md
-"conditioning of the phase unwrap"): the unwrap princarg(P_k - P_{k-1} - nomA) is discontinuous
-at +-1/2 turn.  A bin far below the spectral peak has an fp32 phase error of ~1e-7 * peak/|X|; when its
-phase difference lands within that error of the boundary (probability ~1e-4..1e-3 per frame for bins
-60-80 dB down) the two implementations unwrap to opposite sides and the bin's accumulator differs
-by R = beta*Hs/Ha turns from then on.  For integer R that is a whole number of turns (no effect).
-Hence: integer R (identity, octave, x2 stretch) is checked at 100 dB on tonal AND noisy inputs;
-fractional R is checked at 60 dB plus the exact structure of the disagreement (accumulators differ by
-whole multiples of R turns on < 1 % of the bins, nothing else).  The f32 and f64 variants of the
-oracle disagree with each other in exactly the same way (tests/test_oracle_props.py)."""
+Tolerance: output SNR >= 100 dB against the fp64 oracle in EVERY case.  The integer phase path is exact, so the
+only differences are the fp32 FFTs, atan2 and sincos -- with one inherent exception (DESIGN.md
+"conditioning of the phase unwrap"): the unwrap princarg(P_k - P_{k-1} - nomA) is discontinuous at +-1/2 turn, so
+for a bin whose phase difference lies within its fp32 phase error of that boundary the two implementations may
+pick neighbouring aliases, and for a fractional R = beta*Hs/Ha that bin's accumulator differs by R turns from then
+on.  For integer R the direct comparison is held to 100 dB.  For fractional R the comparison is DECISION-ALIGNED
+(tests/aligned.py): (1) every per-frame, per-bin phase difference of the device equals the oracle's modulo one turn
+within the bin's fp32 uncertainty, (2) alias disagreements are rare among the bins that carry energy, (3) with
+exactly those decisions moved in the oracle the output agrees to >= 100 dB.  tools/spec_conditioning.py shows why the
+spec keeps the per-bin unwrap: peak-picking / phase locking has MORE discontinuous decisions, not fewer."""
 import numpy as np
 import pytest
 
 import pv_oracle as po
+from aligned import aligned_parity
 from signals import multitone, snr_db
 
 torch = pytest.importorskip("torch")
@@ -67,14 +67,21 @@ def test_corrected_parity_vs_oracle(N, Ha, Hs, betas, nf, noise):
     pv = make(N, Ha, Hs, betas)
     win = po.window(po.WIN_HANN_PERIODIC, N)
     assert np.array_equal(pv.imp, win)
-    got = pv.process(dev(x), nf).cpu().numpy()
+    xd = dev(x)
+    got = pv.process(xd, nf).cpu().numpy()
     assert got.shape == (S, len(betas), nf * Hs)
+    integer_R = all(abs(b * Hs / Ha - round(b * Hs / Ha)) < 1e-9 for b in betas)
     for s in range(S):
-        want, _ = po.process_corrected(x[s], N, Ha, Hs, win, betas, nf)
-        for v in range(len(betas)):
-            R = betas[v] * Hs / Ha
-            thr = 100 if abs(R - round(R)) < 1e-9 else 60      # fractional R: see the module docstring
-            assert snr_db(want[v], got[s, v]) > thr, (s, v, snr_db(want[v], got[s, v]))
+        if integer_R:                                          # no alias can matter: direct comparison
+            want, _ = po.process_corrected(x[s], N, Ha, Hs, win, betas, nf)
+            for v in range(len(betas)):
+                assert snr_db(want[v], got[s, v]) > 100, (s, v, snr_db(want[v], got[s, v]))
+            continue
+        D = pv.unwrap_decisions(xd[s], nf).cpu().numpy()
+        r = aligned_parity(x[s], N, Ha, Hs, win, betas, nf, D, got[s])
+        assert r["phase_ratio"] < 1.0, r                       # per-bin phase parity modulo one turn
+        assert r["frac"] < 1e-3, r                             # flips are rare among the bins that carry energy
+        assert min(r["aligned"]) > 100, (s, r)                 # and nothing else differs
 
 
 @pytest.mark.parametrize("noise", [1e-3])
@@ -161,20 +168,20 @@ def test_corrected_many_streams_host_path():
     win = po.window(po.WIN_HANN_PERIODIC, N)
     for s in (0, 151, 299):
         want, _ = po.process_corrected(x[s], N, H, H, win, [1.0, 1.5], nf)
-        assert snr_db(want[0], d[s, 0]) > 100 and snr_db(want[1], d[s, 1]) > 60
+        assert snr_db(want[0], d[s, 0]) > 100 and snr_db(want[1], d[s, 1]) > 100      # white noise: no bin near the floor
 
 
 def test_generic_corrected_kernel_matches_fused(monkeypatch):
     """The shape-generic corrected kernel (windows outside 256..2048) against the tuned one, incl. state carry."""
     N, Ha, Hs, nf = 1024, 256, 256, 50
     betas = [1.0, f32(1.5)]
-    x = multitone(N + nf * Ha, seed=12, noise=0.0)
+    x = multitone(N + nf * Ha, seed=12, noise=1e-3)      # a noise floor: the two kernels use different atan2 / sincos
     xd = dev(x)[None, :]
     fused = make(N, Ha, Hs, betas).process(xd, nf).cpu().numpy()
     monkeypatch.setenv("PV_FORCE_GENERIC", "1")
     pv = make(N, Ha, Hs, betas)
     gen = pv.process(xd, nf).cpu().numpy()
-    assert snr_db(fused[0, 0], gen[0, 0]) > 100 and snr_db(fused[0, 1], gen[0, 1]) > 60
+    assert snr_db(fused[0, 0], gen[0, 0]) > 100 and snr_db(fused[0, 1], gen[0, 1]) > 100
     st = torch.zeros(pv.state_bytes(), dtype=torch.uint8, device="cuda")
     a = pv.process(xd, 21, state=st, flags=pvb200.CARRY_OUT).cpu().numpy()
     b = pv.process(xd[:, 21 * Ha:], nf - 21, state=st, flags=pvb200.CARRY_IN | pvb200.CARRY_OUT).cpu().numpy()

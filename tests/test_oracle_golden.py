@@ -87,3 +87,17 @@ def test_wav_roundtrip_rules():
     assert rate == 44100 and bits == 16
     want = np.array([0, 16383, -16383, 32767, -32767, 32766, 0, 0], np.float32) / np.float32(32768)
     assert np.array_equal(y[0], want) and np.array_equal(y[1], want)
+
+
+def test_wav_slices_equal_the_reference_files(golden_wav, reference_dir):
+    """tests/golden/golden_wav.npz (C1 / C2 inputs) against the files themselves, decoded by the numpy restatement
+    of AudioFile's rules (which tests/test_wav_and_cli.py checks against src/AudioFile.h itself)."""
+    for name, key, off, h in (("testtones/440sine.wav", "c1", 0, golden_wav["sha256"][0]),
+                              ("testtones/MAT_ZO_24_bit.wav", "c2", golden_wav["c2_offset"], golden_wav["sha256"][1])):
+        blob = open(os.path.join(reference_dir, name), "rb").read()
+        assert hashlib.sha256(blob).hexdigest() == h
+        x, rate, bits = wo.decode_wav(blob)
+        assert rate == 44100 and x.shape == (2, golden_wav[key + "_num_samples"])
+        sl = golden_wav[key]
+        assert np.array_equal(x[:, off:off + sl.shape[1]], sl)
+    assert bits == 24
