@@ -310,15 +310,39 @@ int plan_corrected_split(pv_handle *h, int64_t n_streams, int64_t n_frames, int3
     return PV_OK;
 }
 
-// number of frame-range parts per stream for a corrected run of few streams (1 = do not split)
+// Cost model of a corrected run of n streams x F frames cut into p frame-range parts per stream, in units of the time
+// one resident group needs for one full frame.  Segments run in waves of `capacity` resident groups; a split adds the
+// analysis-only aggregate pass (measured ~0.45 of a full frame per frame), the recomputed overlap-add halo of every part
+// and two more launches.  p = 1 is the plain one-segment-per-stream launch.
+double split_cost(const pv_handle *h, int64_t n, int64_t F, int64_t p)
+{
+    const int64_t cap = std::max(1, h->capacity), halo = (h->p.window - 1) / h->p.hop_out;
+    const int64_t L = (F + p - 1) / p;
+    const double waves = (double)((n * p + cap - 1) / cap);
+    if (p <= 1) return waves * (double)F;
+    return waves * ((double)(L + halo) + 0.45 * (double)(L + 1)) + 3.0;
+}
+
+// number of frame-range parts per stream for a corrected run (1 = do not split): the cheapest under split_cost.
+// (Round 1 split whenever fewer than two waves of streams were given, which made 300..1180 streams SLOWER than not
+// splitting: profiles/r02_stream_sweep.md.)
 int64_t corrected_parts(const pv_handle *h, int64_t n_streams, int64_t n_frames)
 {
     if (h->env_no_split) return 1;
     const int64_t halo = (h->p.window - 1) / h->p.hop_out;
     const int64_t min_len = std::max<int64_t>(16 * (halo + 1), 32);     // keep the extra analysis + halo small
-    int64_t parts = std::min<int64_t>(n_frames / min_len, (h->capacity * 2 + n_streams - 1) / n_streams);
-    if (parts < 2 || n_streams * parts > (1 << 20)) return 1;
-    const int64_t L = (n_frames + parts - 1) / parts;
+    const int64_t pmax = std::min<int64_t>(n_frames / min_len, (1 << 20) / std::max<int64_t>(1, n_streams));
+    int64_t best = 1;
+    double best_cost = split_cost(h, n_streams, n_frames, 1);
+    for (int64_t p = 2; p <= pmax; p++) {
+        const double c = split_cost(h, n_streams, n_frames, p);
+        if (c < 0.92 * best_cost) {            // a split must pay clearly: it costs scratch memory and launches
+            best = p;
+            best_cost = c;
+        }
+    }
+    if (best < 2) return 1;
+    const int64_t L = (n_frames + best - 1) / best;
     return (n_frames + L - 1) / L;                                       // no empty trailing part
 }
 
@@ -771,6 +795,23 @@ static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_
     if (n_streams == 0 || n_frames == skip_frames) return PV_OK;
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    // ---- corrected mode, more streams than fit at once and a ragged last wave: run the full waves as they are and
+    // the remaining streams as a second call, which is free to cut them into frame-range parts.  1300 streams on 592
+    // resident groups used to take three waves for 2.2 waves of work. ----
+    if (h->p.mode == PV_MODE_CORRECTED && plan_streams == n_streams && !agg_only && !h->env_no_split && h->capacity > 0 &&
+        n_streams > h->capacity && n_streams % h->capacity != 0) {
+        const int64_t full = n_streams / h->capacity * h->capacity, rest = n_streams - full;
+        const int64_t p = corrected_parts(h, rest, n_frames);
+        if (p >= 2 && split_cost(h, rest, n_frames, p) < 0.85 * (double)n_frames) {
+            const int64_t sb = (int64_t)pv_state_bytes(h);
+            int rc1 = process_impl(h, in, full, full, in_stride, n_in, n_analysed, n_frames, skip_frames, out, out_stream_stride,
+                                   out_voice_stride, state, flags, cuda_stream, nullptr);
+            if (rc1 != PV_OK) return rc1;
+            return process_impl(h, in + full * in_stride, rest, rest, in_stride, n_in, n_analysed, n_frames, skip_frames,
+                                out + full * out_stream_stride, out_stream_stride, out_voice_stride,
+                                state ? (unsigned char *)state + full * sb : nullptr, flags, cuda_stream, nullptr);
+        }
+    }
     // ---- corrected mode, few streams: split into frame-range parts with an on-device phase-carry scan ----
     const bool force_generic0 = h->env_force_generic;
     if (h->p.mode == PV_MODE_CORRECTED && plan_streams == n_streams) {

@@ -24,9 +24,28 @@ static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 
 namespace pvfft {
 
-PV_DEV float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-PV_DEV float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-PV_DEV float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// ---- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 work on a 64-bit register pair, one issue slot for two
+// lanes; each lane rounds like the scalar instruction).  A complex number IS such a pair.  The swapped / negated
+// operands written with make_float2 below cost nothing: SASS takes per-operand lane swap (.LO_HI), whole-pair and
+// per-lane negation (.NP / .PN) and scalar broadcast (.F32) as modifiers.  The fused kernels are bound by
+// instruction issue, so every butterfly is written on pairs.
+#if defined(PV_HOST_EMUL) || defined(PV_NO_PACKED)
+PV_DEV float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+PV_DEV float2 f2mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+PV_DEV float2 f2fma(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#else
+PV_DEV float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+PV_DEV float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+PV_DEV float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#endif
+PV_DEV float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }
+PV_DEV float2 f2swap(float2 a) { return make_float2(a.y, a.x); }
+PV_DEV float2 f2bc(float s) { return make_float2(s, s); }
+
+PV_DEV float2 cadd(float2 a, float2 b) { return f2add(a, b); }
+PV_DEV float2 csub(float2 a, float2 b) { return f2add(a, f2neg(b)); }
+// (a.x b.x - a.y b.y, a.y b.x + a.x b.y): two packed instructions
+PV_DEV float2 cmul(float2 a, float2 b) { return f2fma(a, f2bc(b.x), f2mul(f2swap(a), make_float2(-b.y, b.y))); }
 PV_DEV float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 // a * (+j) and a * (-j)
 PV_DEV float2 mul_pj(float2 a) { return make_float2(-a.y, a.x); }
@@ -49,7 +68,7 @@ PV_DEV float2 twid16(float2 a)
         constexpr float sa = (k == 1 || k == 7) ? S1 : (k == 2 || k == 6) ? H : (k == 3 || k == 5) ? C1
                            : (k == 9 || k == 15) ? -S1 : (k == 10 || k == 14) ? -H : -C1;  // k == 11, 13
         constexpr float s = DIR > 0 ? sa : -sa;
-        return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
+        return f2fma(a, f2bc(c), f2mul(f2swap(a), make_float2(-s, s)));
     }
 }
 
@@ -121,6 +140,70 @@ PV_DEV void dft16_half(const float2 (&a)[16], float2 (&o)[8])
         o[7] = twid16<7, DIR>(o[7]);
     }
     dft8<DIR>(o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+}
+
+// ---- radix-32 pieces for window 4096 (pv_fused_core.cuh, Shape<12>: R2 = 32) ----
+// cos(2 pi k / 32) for any integer k, compile time
+constexpr float pv_cos32(int k)
+{
+    constexpr float C[9] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f,
+                            0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f, 0.0f};
+    k = ((k % 32) + 32) % 32;
+    if (k > 16) k = 32 - k;
+    return k > 8 ? -C[16 - k] : C[k];
+}
+
+// a * exp(DIR * j * 2*pi * K / 32)
+template <int K, int DIR>
+PV_DEV float2 twid32(float2 a)
+{
+    constexpr int k = ((K % 32) + 32) % 32;
+    if constexpr (k % 2 == 0) return twid16<k / 2, DIR>(a);
+    else {
+        constexpr float c = pv_cos32(k), s = (DIR > 0 ? 1.f : -1.f) * pv_cos32(k - 8);      // sin(x) = cos(x - pi/2)
+        return f2fma(a, f2bc(c), f2mul(f2swap(a), make_float2(-s, s)));
+    }
+}
+
+// One half of a 32-point DFT: outputs k = 2q + ODD, q = 0..15 (two threads share a butterfly).
+template <int DIR, bool ODD>
+PV_DEV void dft32_half(const float2 (&a)[32], float2 (&o)[16])
+{
+#pragma unroll
+    for (int n = 0; n < 16; n++) o[n] = ODD ? csub(a[n], a[n + 16]) : cadd(a[n], a[n + 16]);
+    if constexpr (ODD) {
+        o[1] = twid32<1, DIR>(o[1]); o[2] = twid32<2, DIR>(o[2]); o[3] = twid32<3, DIR>(o[3]);
+        o[4] = twid32<4, DIR>(o[4]); o[5] = twid32<5, DIR>(o[5]); o[6] = twid32<6, DIR>(o[6]);
+        o[7] = twid32<7, DIR>(o[7]); o[8] = twid32<8, DIR>(o[8]); o[9] = twid32<9, DIR>(o[9]);
+        o[10] = twid32<10, DIR>(o[10]); o[11] = twid32<11, DIR>(o[11]); o[12] = twid32<12, DIR>(o[12]);
+        o[13] = twid32<13, DIR>(o[13]); o[14] = twid32<14, DIR>(o[14]); o[15] = twid32<15, DIR>(o[15]);
+    }
+    dft<16, DIR>(o);
+}
+
+// One quarter of a 32-point DFT: outputs k = Q + 4j, j = 0..7 (four threads share a butterfly).
+// n = n0 + 8 n1:  X[Q + 4j] = sum_{n0} W8^{n0 j} * [ W32^{n0 Q} * sum_{n1} a[n0 + 8 n1] W4^{n1 Q} ]
+template <int DIR, int Q>
+PV_DEV void dft32_quarter(const float2 (&a)[32], float2 (&o)[8])
+{
+    static_assert(Q >= 0 && Q < 4, "quarter");
+#pragma unroll
+    for (int n0 = 0; n0 < 8; n0++) {
+        const float2 a0 = a[n0], a1 = a[n0 + 8], a2 = a[n0 + 16], a3 = a[n0 + 24];
+        if constexpr (Q == 0) o[n0] = cadd(cadd(a0, a2), cadd(a1, a3));
+        else if constexpr (Q == 2) o[n0] = csub(cadd(a0, a2), cadd(a1, a3));
+        else {
+            const float2 d = csub(a1, a3);
+            const float2 jd = DIR > 0 ? mul_pj(d) : mul_mj(d);             // (DIR*j) * (a1 - a3)
+            o[n0] = (Q == 1) ? cadd(csub(a0, a2), jd) : csub(csub(a0, a2), jd);
+        }
+    }
+    if constexpr (Q != 0) {
+        o[1] = twid32<1 * Q, DIR>(o[1]); o[2] = twid32<2 * Q, DIR>(o[2]); o[3] = twid32<3 * Q, DIR>(o[3]);
+        o[4] = twid32<4 * Q, DIR>(o[4]); o[5] = twid32<5 * Q, DIR>(o[5]); o[6] = twid32<6 * Q, DIR>(o[6]);
+        o[7] = twid32<7 * Q, DIR>(o[7]);
+    }
+    dft<8, DIR>(o);
 }
 
 // Forward R-point DFT of a sequence whose middle half is zero (only v[0..R/4) and v[3R/4..R) are

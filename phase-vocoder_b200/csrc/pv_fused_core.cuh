@@ -116,7 +116,7 @@ PV_DEV float2 load_pair(const FrameIO &io, const float *win, int i)
         x1 = (g + 1 < io.n_in) ? PV_LDG(io.in + g + 1) : 0.f;
     }
     const float2 w = PV_LDG(reinterpret_cast<const float2 *>(win + i));
-    return make_float2(x0 * w.x, x1 * w.y);
+    return f2mul(make_float2(x0, x1), w);
 }
 
 // ---- private input ring ----------------------------------------------------------------------
@@ -219,7 +219,7 @@ PV_DEV void forward_12(int tid, const FrameIO &io, const Tables &tb, const Threa
                 const int i = src_index(n1, t1);
                 const float2 x = *reinterpret_cast<const float2 *>(ring + ((rbase + i) & (N - 1)));
                 const float2 w = PV_LDG(reinterpret_cast<const float2 *>(tb.win + i));
-                v[n1] = make_float2(x.x * w.x, x.y * w.y);
+                v[n1] = f2mul(x, w);
             }
         } else {
 #pragma unroll
@@ -284,8 +284,8 @@ PV_DEV void forward_3(int u, const float2 *bufA, float2 (&P)[8], float2 (&Q)[8])
 // pre-scaled synthesis window w/(2N): exact, power of two.
 PV_DEV float2 split(float2 a, float2 b, float2 w)
 {
-    const float2 e = make_float2(a.x + b.x, a.y - b.y);
-    const float2 o = make_float2(a.y + b.y, b.x - a.x);          // (a - conj b)/j
+    const float2 e = f2add(a, cconj(b));
+    const float2 o = f2add(mul_mj(a), f2swap(b));                 // (a - conj b)/j = (a.y + b.y, b.x - a.x)
     return cadd(e, cmul(w, o));
 }
 
@@ -310,10 +310,10 @@ PV_DEV float2 compat_map(float2 X, bool nan_compat)
 // Z[k] = (Yk + conj(Ym)) + j*w*(Yk - conj(Ym)), w = exp(+2 pi i k/N), Ym = Y[N/2 - k]
 PV_DEV float2 herm_pack(float2 yk, float2 ym, float2 w)
 {
-    const float2 s = make_float2(yk.x + ym.x, yk.y - ym.y);
-    const float2 d = make_float2(yk.x - ym.x, yk.y + ym.y);
+    const float2 s = f2add(yk, cconj(ym));
+    const float2 d = f2add(yk, make_float2(-ym.x, ym.y));
     const float2 t = cmul(w, d);
-    return make_float2(s.x - t.y, s.y + t.x);
+    return f2add(s, mul_pj(t));                                   // (s.x - t.y, s.y + t.x)
 }
 
 // ---- middle: P,Q (16 transform outputs) -> Zp[4], Zq[4] = packed inverse inputs at
@@ -420,20 +420,9 @@ PV_DEV void inverse_23_ola(int tid, const Tables &tb, float2 *bufA, float2 *bufB
         // cudaDivVec kernel.cu:130-138 (x/N == x*(1/N) exactly, N a power of two) and cudaWindow :75-81.
         // One window table serves analysis and synthesis: with 4 CTAs x 51 KB of shared memory only ~24 KB
         // of L1 remain per SM, and a second (pre-scaled) 8 KB table measurably thrashes it.
-        float2 w = PV_LDG(reinterpret_cast<const float2 *>(tb.win + i));
-        w.x *= scale;
-        w.y *= scale;
+        const float2 w = f2mul(PV_LDG(reinterpret_cast<const float2 *>(tb.win + i)), f2bc(scale));
         float2 *slot = reinterpret_cast<float2 *>(acc + ((pos0 + i) & (N - 1)));
-        float2 a = *slot;
-#ifdef PV_EXP_SELECT_OLA
-        const int keep = N - Hs;
-        a.x = (i < keep ? a.x : 0.f) + v.x * w.x;
-        a.y = (i + 1 < keep ? a.y : 0.f) + v.y * w.y;
-#else
-        a.x += v.x * w.x;                              // cudaOverlapAdd kernel.cu:111-119
-        a.y += v.y * w.y;
-#endif
-        *slot = a;
+        *slot = f2fma(v, w, *slot);                    // cudaOverlapAdd kernel.cu:111-119
     };
     (void)Hs;
     if (!zero_frame) {

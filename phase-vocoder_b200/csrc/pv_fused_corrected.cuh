@@ -149,11 +149,11 @@ PV_DEV float2 cis_turns64(unsigned long long psi)
 // X[k] and X[M-k] of the N-point real spectrum (M = N/2) from a = C[k], b = C[M-k], w = W_N^k
 PV_DEV void split_both(float2 a, float2 b, float2 w, float2 &xk, float2 &xm)
 {
-    const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
-    const float2 o = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));
+    const float2 e = f2mul(f2add(a, cconj(b)), f2bc(0.5f));
+    const float2 o = f2mul(f2add(mul_mj(a), f2swap(b)), f2bc(0.5f));       // (a.y + b.y, b.x - a.x) / 2
     const float2 t = cmul(w, o);
-    xk = make_float2(e.x + t.x, e.y + t.y);
-    xm = make_float2(e.x - t.x, -(e.y - t.y));
+    xk = f2add(e, t);
+    xm = f2add(cconj(e), make_float2(-t.x, t.y));                          // conj(e - t)
 }
 
 // Loop-invariant per-thread twiddle bases (N = 2048 layout: both forward passes and inverse pass 2 use
@@ -174,7 +174,8 @@ PV_DEV void tw_expand(const TwBase4 &b, float2 (&e)[8])
 }
 
 struct CThreadTw {
-    TwBase4 p1, p2, ip2;     // forward pass 1, forward pass 2, inverse pass 2
+    TwBase4 p1, p2;          // forward pass 1, forward pass 2 (the inverse pass-2 twiddles come from the L1-resident table:
+                             // with packed arithmetic eight more live registers cost more in spills than four loads per frame)
     float2 wN, w2, w4;       // W_N^u, W_N^2u, W_N^4u  (split / pack / inverse pass 1), p side: u = tid
     float2 q1, q2, q4;       // same for the q side: u_q = tid ? tid : B3/2 (thread 0 owns columns 0 and B3/2, see
                              // ThreadTw in pv_fused_core.cuh: one code path for all threads)
@@ -204,15 +205,8 @@ PV_DEV CThreadTw load_cthread_tw(int tid, const CTables &tb)
             t.p2.g2 = PV_LDG(tb.ctw2 + 3 * 4 + n3);
             t.p2.g4 = PV_LDG(tb.ctw2 + 7 * 4 + n3);
         }
-        {   // inverse pass 2: exp(+2 pi i m2 n3 / B3), m2 = 2q + half, n3 = (tid % 64) % R2
-            const int n3 = (tid % (4 * R2)) % R2;
-            t.ip2.o = half ? PV_LDG(tb.itw2 + 0 * R2 + n3) : one;
-            t.ip2.g1 = PV_LDG(tb.itw2 + 1 * R2 + n3);
-            t.ip2.g2 = PV_LDG(tb.itw2 + 3 * R2 + n3);
-            t.ip2.g4 = PV_LDG(tb.itw2 + 7 * R2 + n3);
-        }
     } else {
-        t.p1 = t.p2 = t.ip2 = TwBase4{one, one, one, one};
+        t.p1 = t.p2 = TwBase4{one, one, one, one};
     }
     t.wN = PV_LDG(tb.tw2n + 2 * tid);
     t.w2 = PV_LDG(tb.tw2n + 4 * tid);
@@ -223,11 +217,6 @@ PV_DEV CThreadTw load_cthread_tw(int tid, const CTables &tb)
     t.q4 = cmul(t.q2, t.q2);
     return t;
 }
-
-struct RegTw2 {            // inverse pass-2 twiddles from registers
-    const float2 *e;
-    PV_DEV float2 operator()(int q, int /*m2*/, int /*n3*/) const { return e[q]; }
-};
 
 struct CState {             // per-thread registers carried across the frames of a stream
     uint32_t Pprev[9];
@@ -280,8 +269,7 @@ PV_DEV void cforward(int tid, const FrameIO &io, const CTables &tb, const CThrea
 #pragma unroll
         for (int n1 = 0; n1 < R; n1++) {
             const int i = (N / 2 + 2 * (n1 * S1 + t1)) & (N - 1);
-            const float2 w = PV_LDG(reinterpret_cast<const float2 *>(tb.win + i));
-            v[n1] = make_float2(v[n1].x * w.x, v[n1].y * w.y);
+            v[n1] = f2mul(v[n1], PV_LDG(reinterpret_cast<const float2 *>(tb.win + i)));
         }
     };
 
@@ -464,7 +452,7 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
             else p = mad_s32_u64(d, Rq, mad_u32_u64(hi, bqs, ps[s]));
             if (lo != (uint32_t)NB) ps[s] = p;           // an empty range leaves the accumulator untouched
             const float2 cs = cis_turns64(p);
-            Y[sl] = make_float2(m * cs.x, m * cs.y);
+            Y[sl] = f2mul(cs, f2bc(m));
         }
         // Hermitian pack (same register pattern as the compat kernel); exp(+2 pi i k/N) = conj(W_N^k)
         float2 Zp[4], Zq[4];
@@ -492,15 +480,8 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
             inverse_1_tw<LOG2N>(tP, cconj(tt.w2), cconj(tt.w4), cconj(w6), Zp, bufA);
             inverse_1_tw<LOG2N>(tQ, mul_pj(tt.q2), make_float2(-tt.q4.x, -tt.q4.y), mul_mj(q6), Zq, bufA);
         }
-        if constexpr (TWREG) {
-            float2 e[8];
-            tw_expand(tt.ip2, e);
-            inverse_23_ola<LOG2N>(tid, itb, bufA, bufB, acc + (size_t)v * N, pos0, Hs, false, tb.scale, sync,
-                                  [&]() { if (v + 1 == tb.V) pre_last_sync(); }, RegTw2{e});
-        } else {
-            inverse_23_ola<LOG2N>(tid, itb, bufA, bufB, acc + (size_t)v * N, pos0, Hs, false, tb.scale, sync,
-                                  [&]() { if (v + 1 == tb.V) pre_last_sync(); });
-        }
+        inverse_23_ola<LOG2N>(tid, itb, bufA, bufB, acc + (size_t)v * N, pos0, Hs, false, tb.scale, sync,
+                              [&]() { if (v + 1 == tb.V) pre_last_sync(); });
         (void)S::T;
     }
     (void)M;
