@@ -28,7 +28,7 @@ struct pv_handle {
     uint32_t *d_nomA = nullptr;
     int32_t *d_alo = nullptr, *d_ahi = nullptr;
     uint64_t *d_nomS = nullptr;
-    uint32_t *d_gather = nullptr;
+    uint32_t *d_gather = nullptr, *d_gather_nat = nullptr;
     std::vector<float> h_win;
     // fused-kernel tables
     bool fused = false;
@@ -443,14 +443,15 @@ int pv_create(const pv_params *params, pv_handle **out)
         if (rc == PV_OK) rc = upload(&h->d_alo, alo);
         if (rc == PV_OK) rc = upload(&h->d_ahi, ahi);
         if (rc == PV_OK) rc = upload(&h->d_nomS, nomS);
-        if (rc == PV_OK && N >= 256 && N <= 2048) {
+        if (rc == PV_OK && N >= 256 && N <= 4096) {       // per-thread slot order of the fused kernels
             std::vector<uint32_t> gath;
             build_gather_table(N, V, alo.data(), ahi.data(), gath, d.multi);
             rc = upload(&h->d_gather, gath);
-        } else if (rc == PV_OK && N == 4096) {           // natural bin order for the in-place large-window kernel
+        }
+        if (rc == PV_OK && N == 4096) {                   // natural bin order for the in-place large-window kernel (fallback path)
             std::vector<uint32_t> gath;
             build_gather_natural(N, V, alo.data(), ahi.data(), gath, d.multi);
-            rc = upload(&h->d_gather, gath);
+            rc = upload(&h->d_gather_nat, gath);
         }
     }
     h->capacity = h->sm_count * 8;
@@ -484,6 +485,7 @@ int pv_create(const pv_params *params, pv_handle **out)
     d.a_hi = h->d_ahi;
     d.nomS = h->d_nomS;
     d.gather = h->d_gather;
+    d.gather_nat = h->d_gather_nat;
     *out = h;
     return PV_OK;
 }
@@ -499,6 +501,7 @@ void pv_destroy(pv_handle *h)
     cudaFree(h->d_ahi);
     cudaFree(h->d_nomS);
     cudaFree(h->d_gather);
+    cudaFree(h->d_gather_nat);
     for (auto p : h->d_ft) cudaFree(p);
     for (auto &pl : h->plans) {
         cudaFree(pl.d_segs);

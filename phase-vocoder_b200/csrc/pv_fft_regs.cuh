@@ -14,11 +14,13 @@ struct float4 { float x, y, z, w; };
 struct uint4 { unsigned x, y, z, w; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 #define PV_DEV inline
+#define PV_HD
 #define PV_LDG(p) (*(p))
 #else
 #include <cuda_runtime.h>
 #include <stdint.h>
 #define PV_DEV __device__ __forceinline__
+#define PV_HD __host__ __device__
 #define PV_LDG(p) __ldg(p)
 #endif
 
@@ -144,7 +146,7 @@ PV_DEV void dft16_half(const float2 (&a)[16], float2 (&o)[8])
 
 // ---- radix-32 pieces for window 4096 (pv_fused_core.cuh, Shape<12>: R2 = 32) ----
 // cos(2 pi k / 32) for any integer k, compile time
-constexpr float pv_cos32(int k)
+PV_HD constexpr float pv_cos32(int k)
 {
     constexpr float C[9] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f,
                             0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f, 0.0f};
@@ -165,12 +167,16 @@ PV_DEV float2 twid32(float2 a)
     }
 }
 
-// One half of a 32-point DFT: outputs k = 2q + ODD, q = 0..15 (two threads share a butterfly).
+// One half of a 32-point DFT: outputs k = 2q + ODD, q = 0..15 (two threads share a butterfly).  Two steps, so that a
+// caller working in place can put a barrier between its loads and its stores with only 16 values live:
+//   o[n] = a[n] +- a[n + 16]                      (dft32_fold, while loading)
+//   dft32_half_finish: twiddle W32^n (odd half), 16-point DFT
+template <bool ODD>
+PV_DEV float2 dft32_fold(float2 lo, float2 hi) { return ODD ? csub(lo, hi) : cadd(lo, hi); }
+
 template <int DIR, bool ODD>
-PV_DEV void dft32_half(const float2 (&a)[32], float2 (&o)[16])
+PV_DEV void dft32_half_finish(float2 (&o)[16])
 {
-#pragma unroll
-    for (int n = 0; n < 16; n++) o[n] = ODD ? csub(a[n], a[n + 16]) : cadd(a[n], a[n + 16]);
     if constexpr (ODD) {
         o[1] = twid32<1, DIR>(o[1]); o[2] = twid32<2, DIR>(o[2]); o[3] = twid32<3, DIR>(o[3]);
         o[4] = twid32<4, DIR>(o[4]); o[5] = twid32<5, DIR>(o[5]); o[6] = twid32<6, DIR>(o[6]);
@@ -179,6 +185,14 @@ PV_DEV void dft32_half(const float2 (&a)[32], float2 (&o)[16])
         o[13] = twid32<13, DIR>(o[13]); o[14] = twid32<14, DIR>(o[14]); o[15] = twid32<15, DIR>(o[15]);
     }
     dft<16, DIR>(o);
+}
+
+template <int DIR, bool ODD>
+PV_DEV void dft32_half(const float2 (&a)[32], float2 (&o)[16])
+{
+#pragma unroll
+    for (int n = 0; n < 16; n++) o[n] = dft32_fold<ODD>(a[n], a[n + 16]);
+    dft32_half_finish<DIR, ODD>(o);
 }
 
 // One quarter of a 32-point DFT: outputs k = Q + 4j, j = 0..7 (four threads share a butterfly).

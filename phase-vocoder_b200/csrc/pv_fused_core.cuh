@@ -248,17 +248,44 @@ PV_DEV void forward_12(int tid, const FrameIO &io, const Tables &tb, const Threa
     sync();
     after_exchange1();
     // pass 2: butterflies (k1, n3), k1 fastest across threads
-#pragma unroll
-    for (int b = tid; b < R1 * 8; b += T) {
+    if constexpr (R2 == 32) {
+        // window 4096: 128 radix-32 butterflies for 256 threads -> two threads per butterfly (even / odd outputs, the
+        // half is warp-uniform).  Still in place: both threads read all 32 inputs, folded to 16 values while loading,
+        // and a barrier separates the loads from the stores
+        static_assert(2 * R1 * 8 == T, "pass 2 cover");
+        const int b = tid % (R1 * 8), half = tid / (R1 * 8);
         const int k1 = b % R1, n3 = b / R1;
-        float2 v[R2];
+        float2 o[16];
+        if (half == 0) {
 #pragma unroll
-        for (int n2 = 0; n2 < R2; n2++) v[n2] = bufA[k1 * S::LD1 + n2 * 8 + n3];
-        dft<R2, -1>(v);
-        bufA[k1 * S::LD1 + n3] = v[0];
+            for (int n2 = 0; n2 < 16; n2++) o[n2] = dft32_fold<false>(bufA[k1 * S::LD1 + n2 * 8 + n3], bufA[k1 * S::LD1 + (n2 + 16) * 8 + n3]);
+        } else {
 #pragma unroll
-        for (int k2 = 1; k2 < R2; k2++)
-            bufA[k1 * S::LD1 + k2 * 8 + n3] = cmul(v[k2], PV_LDG(tb.tw2 + (k2 - 1) * 8 + n3));
+            for (int n2 = 0; n2 < 16; n2++) o[n2] = dft32_fold<true>(bufA[k1 * S::LD1 + n2 * 8 + n3], bufA[k1 * S::LD1 + (n2 + 16) * 8 + n3]);
+        }
+        sync();
+        if (half == 0) dft32_half_finish<-1, false>(o);
+        else dft32_half_finish<-1, true>(o);
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int k2 = 2 * q + half;
+            float2 r = o[q];
+            if (k2 != 0) r = cmul(r, PV_LDG(tb.tw2 + (k2 - 1) * 8 + n3));
+            bufA[k1 * S::LD1 + k2 * 8 + n3] = r;
+        }
+    } else {
+#pragma unroll
+        for (int b = tid; b < R1 * 8; b += T) {
+            const int k1 = b % R1, n3 = b / R1;
+            float2 v[R2];
+#pragma unroll
+            for (int n2 = 0; n2 < R2; n2++) v[n2] = bufA[k1 * S::LD1 + n2 * 8 + n3];
+            dft<R2, -1>(v);
+            bufA[k1 * S::LD1 + n3] = v[0];
+#pragma unroll
+            for (int k2 = 1; k2 < R2; k2++)
+                bufA[k1 * S::LD1 + k2 * 8 + n3] = cmul(v[k2], PV_LDG(tb.tw2 + (k2 - 1) * 8 + n3));
+        }
     }
     sync();
 }
@@ -410,7 +437,8 @@ PV_DEV void inverse_23_ola(int tid, const Tables &tb, float2 *bufA, float2 *bufB
     constexpr int C2 = 4 * R2;       // pass-2 butterflies (m1, n3), radix R1
     constexpr int C3 = 4 * R1;       // pass-3 butterflies (m1, m2), radix R2
     static_assert(C2 >= T || 2 * C2 == T, "pass 2 cover");
-    static_assert(C3 >= T || 2 * C3 == T, "pass 3 cover");
+    constexpr bool QUAD3 = (4 * C3 == T) && (R2 == 32);    // window 4096: four threads per radix-32 butterfly
+    static_assert(C3 >= T || 2 * C3 == T || QUAD3, "pass 3 cover");
     constexpr bool SPLIT2 = (2 * C2 == T) && (R1 == 16);   // two threads per radix-16 butterfly
     constexpr bool SPLIT3 = (2 * C3 == T) && (R2 == 16);
     // steps G+H for complex output n (samples 2n, 2n+1).  The last Hs slots of the frame are "fresh": the
@@ -464,7 +492,24 @@ PV_DEV void inverse_23_ola(int tid, const Tables &tb, float2 *bufA, float2 *bufB
         sync();
     }
     // pass 3 -> time samples
-    if constexpr (SPLIT3) {
+    if constexpr (QUAD3) {
+        const int b = tid % C3, quarter = tid / C3;         // warp-uniform quarter: outputs m3 = quarter + 4 j
+        float2 o[8];
+        if (!zero_frame) {
+            float2 v[32];
+#pragma unroll
+            for (int n3 = 0; n3 < 32; n3++) v[n3] = bufB[b * S::ILD2 + n3];
+            if (quarter == 0) dft32_quarter<+1, 0>(v, o);
+            else if (quarter == 1) dft32_quarter<+1, 1>(v, o);
+            else if (quarter == 2) dft32_quarter<+1, 2>(v, o);
+            else dft32_quarter<+1, 3>(v, o);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) o[j] = make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) ola(b + C3 * (quarter + 4 * j), o[j]);
+    } else if constexpr (SPLIT3) {
         const int b = tid % C3, half = tid / C3;
         float2 v[16], o[8];
         if (!zero_frame) {
@@ -478,7 +523,7 @@ PV_DEV void inverse_23_ola(int tid, const Tables &tb, float2 *bufA, float2 *bufB
         }
 #pragma unroll
         for (int q = 0; q < 8; q++) ola(b + C3 * (2 * q + half), o[q]);
-    } else {
+    } else if constexpr (R2 <= 16) {
 #pragma unroll
         for (int b = tid; b < C3; b += T) {
             float2 v[R2];

@@ -35,7 +35,7 @@ struct CShape {
     static constexpr int C1 = S1;                   // pass-1 butterflies (radix R1)
     static constexpr int C2 = R1 * 4;               // pass-2 butterflies (radix R2)
     static_assert(C1 >= T || (2 * C1 == T && R1 == 16), "pass 1 cover");
-    static_assert(C2 >= T || (2 * C2 == T && R2 == 16), "pass 2 cover");
+    static_assert(C2 >= T || (2 * C2 == T && R2 == 16) || (4 * C2 == T && R2 == 32), "pass 2 cover");
 };
 
 struct CTables {
@@ -320,7 +320,25 @@ PV_DEV void cforward(int tid, const FrameIO &io, const CTables &tb, const CThrea
             if (k2 != 0) r = cmul(r, TWREG ? e[q] : PV_LDG(tb.ctw2 + (k2 - 1) * 4 + n3));
             bufB[(k1 + R1 * k2) * C::LD2 + n3] = r;
         }
-    } else {
+    } else if constexpr (4 * C::C2 == T && R2 == 32) {
+        // window 4096: 64 radix-32 butterflies for 256 threads -> four threads per butterfly (outputs k2 = quarter + 4 j)
+        const int b = tid % C::C2, quarter = tid / C::C2;       // warp-uniform
+        const int k1 = b % R1, n3 = b / R1;
+        float2 v[32], o[8];
+#pragma unroll
+        for (int n2 = 0; n2 < 32; n2++) v[n2] = bufA[k1 * C::LD1 + n2 * 4 + n3];
+        if (quarter == 0) dft32_quarter<-1, 0>(v, o);
+        else if (quarter == 1) dft32_quarter<-1, 1>(v, o);
+        else if (quarter == 2) dft32_quarter<-1, 2>(v, o);
+        else dft32_quarter<-1, 3>(v, o);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int k2 = quarter + 4 * j;
+            float2 r = o[j];
+            if (k2 != 0) r = cmul(r, PV_LDG(tb.ctw2 + (k2 - 1) * 4 + n3));
+            bufB[(k1 + R1 * k2) * C::LD2 + n3] = r;
+        }
+    } else if constexpr (R2 <= 16) {
 #pragma unroll
         for (int b = tid; b < C::C2; b += T) {
             const int k1 = b % R1, n3 = b / R1;

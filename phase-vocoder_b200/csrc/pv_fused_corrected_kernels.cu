@@ -1,4 +1,4 @@
-// pv_fused_corrected_kernels.cu -- fused CORRECTED-mode stream kernel (windows 256..2048).
+// pv_fused_corrected_kernels.cu -- fused CORRECTED-mode stream kernel (windows 256..4096).
 //
 // Same work decomposition as the compat kernel: a group of T = N/16 threads walks the frames of
 // one stream segment; the stream state (previous analysis phase in registers, 64-bit phase
@@ -264,7 +264,7 @@ int ccapacity(int V, int sm_count)
 bool pv_fused_corrected_supported(int N, int Ha, int Hs)
 {
     (void)Ha;
-    return (N == 256 || N == 512 || N == 1024 || N == 2048) && (Hs % 2) == 0;
+    return (N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096) && (Hs % 2) == 0;
 }
 
 int pv_fused_corrected_capacity(int N, int V, int sm_count)
@@ -274,6 +274,7 @@ int pv_fused_corrected_capacity(int N, int V, int sm_count)
         case 512: return ccapacity<9, 4>(V, sm_count);
         case 1024: return ccapacity<10, 4>(V, sm_count);
         case 2048: return ccapacity<11, 4>(V, sm_count);
+        case 4096: return ccapacity<12, 2>(V, sm_count);
         default: return sm_count;
     }
 }
@@ -328,6 +329,7 @@ cudaError_t pv_launch_corrected_aggregate(const PvDev &d, const PvFusedTables &t
         case 512: return agg_launch<9, 4>(d, tb, a, st);
         case 1024: return agg_launch<10, 4>(d, tb, a, st);
         case 2048: return agg_launch<11, 4>(d, tb, a, st);
+        case 4096: return agg_launch<12, 2>(d, tb, a, st);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -441,6 +443,7 @@ cudaError_t pv_launch_corrected_fused(const PvDev &d, const PvFusedTables &t, co
         case 512: return claunch<9, 4>(d, tb, a, st);
         case 1024: return claunch<10, 4>(d, tb, a, st);
         case 2048: return claunch<11, 4>(d, tb, a, st);
+        case 4096: return claunch<12, 2>(d, tb, a, st);
         default: return cudaErrorInvalidValue;
     }
 }

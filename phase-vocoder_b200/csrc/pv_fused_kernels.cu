@@ -1,4 +1,4 @@
-// pv_fused_kernels.cu -- the tuned fused stream kernels (compat mode) for windows 256..2048.
+// pv_fused_kernels.cu -- the tuned fused stream kernels (compat mode) for windows 256..4096.
 //
 // Work unit: a frame-range segment of one stream (PvSegment).  A group of T = N/16 threads owns
 // a segment and walks its frames sequentially, keeping the overlap-add accumulator in shared
@@ -30,6 +30,9 @@ struct Launch {
     static constexpr int G = (T >= 128) ? 1 : 128 / T;       // groups per CTA
     static constexpr int THREADS = T * G;
     static constexpr int GROUP_F2 = S::BUF_A + S::BUF_B;     // float2 per group
+    // resident CTAs per SM with the 16-byte ring: 40.7 KB and 96 registers at window 2048 -> 5; window 4096 (256 threads,
+    // 81 KB) -> 2
+    static constexpr int MINB_RING = LOG2N >= 12 ? 2 : 5;
     // exchange buffers + OLA accumulator (+ private input ring)
     static constexpr size_t smem(bool ring) { return (size_t)G * (GROUP_F2 * sizeof(float2) + (ring ? 2 : 1) * S::N * sizeof(float)); }
 };
@@ -166,20 +169,20 @@ cudaError_t launch(const PvDev &d, const Tables &tb, const PvProcessArgs &a, int
     const bool al16 = vec_in_ok && d.Ha <= d.N && (d.Ha % 4 == 0) && (a.in_stride % 4 == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0);
     // 5 CTAs/SM: with exchange 2 in place a group needs 40.7 KB of shared memory at N = 2048 and 96 registers
-    if (al16) return launch2<LOG2N, 5, 2>(d, tb, a, vec_in_ok, vec_out_ok, st);
+    if (al16) return launch2<LOG2N, Launch<LOG2N>::MINB_RING, 2>(d, tb, a, vec_in_ok, vec_out_ok, st);
     if (ring_ok<LOG2N>(d, vec_in_ok != 0)) return launch2<LOG2N, MINB, 1>(d, tb, a, vec_in_ok, vec_out_ok, st);
     return launch2<LOG2N, MINB, 0>(d, tb, a, vec_in_ok, vec_out_ok, st);
 }
 
 }  // namespace
 
-bool pv_fused_compat_supported(int N, int Hs) { return (N == 256 || N == 512 || N == 1024 || N == 2048) && (Hs % 2) == 0; }
+bool pv_fused_compat_supported(int N, int Hs) { return (N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096) && (Hs % 2) == 0; }
 
 template <int LOG2N, int MINB>
 static int capacity(int sm_count)
 {
     using L = Launch<LOG2N>;
-    auto kern = compat_fused_kernel<LOG2N, 5, 2>;
+    auto kern = compat_fused_kernel<LOG2N, L::MINB_RING, 2>;
     const size_t smem = L::smem(true);
     int nb = 0;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
@@ -195,6 +198,7 @@ int pv_fused_compat_capacity(int N, int sm_count)
         case 512: return capacity<9, 4>(sm_count);
         case 1024: return capacity<10, 4>(sm_count);
         case 2048: return capacity<11, 4>(sm_count);
+        case 4096: return capacity<12, 2>(sm_count);
         default: return sm_count * 8;
     }
 }
@@ -210,6 +214,7 @@ cudaError_t pv_launch_compat_fused(const PvDev &d, const PvFusedTables &t, const
         case 512: return launch<9, 4>(d, tb, a, in_ok, out_ok, st);
         case 1024: return launch<10, 4>(d, tb, a, in_ok, out_ok, st);
         case 2048: return launch<11, 4>(d, tb, a, in_ok, out_ok, st);
+        case 4096: return launch<12, 2>(d, tb, a, in_ok, out_ok, st);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -655,7 +655,7 @@ corrected_inplace_kernel(PvDev d, PvProcessArgs a)
             unsigned long long *ps = psi + (size_t)v * NBP;
             const unsigned long long Rq = d.Rq[v];
             const unsigned long long bqs = (d.beta_q[v] * (unsigned long long)Hs) << lsh;    // nomS[s] = a_hi * bqs mod 2^64
-            const uint32_t *gt = d.gather + (size_t)v * NB;                                 // a_lo | a_hi << 16, NB = no source bin
+            const uint32_t *gt = d.gather_nat + (size_t)v * NB;                                 // a_lo | a_hi << 16, NB = no source bin
             auto synth = [&](int s) -> float2 {
                 const uint32_t ge = __ldg(gt + s);
                 const uint32_t lo = ge & 0xffffu, hi = ge >> 16;

@@ -23,6 +23,7 @@ struct PvDev {
     const int32_t *a_hi;  // V*nb
     const uint64_t *nomS; // V*nb
     const uint32_t *gather; // V*T*9: per-thread packed a_lo | a_hi << 16 (pv_fused_tables.h)
+    const uint32_t *gather_nat; // V*nb: the same in natural bin order (window 4096 in-place kernel)
     uint64_t beta_q[PV_MAX_VOICES];
     uint64_t Rq[PV_MAX_VOICES];
     int32_t multi[PV_MAX_VOICES];   // voice sums several analysis bins into some synthesis bin (pitch ratio < 1)

@@ -80,6 +80,7 @@ extern "C" int emul_compat(int log2n, const float *x, long n_in, int Ha, int Hs,
         case 9: return run<9>(x, n_in, Ha, Hs, win, n_analysed, n_frames, nan_compat, out);
         case 10: return run<10>(x, n_in, Ha, Hs, win, n_analysed, n_frames, nan_compat, out);
         case 11: return run<11>(x, n_in, Ha, Hs, win, n_analysed, n_frames, nan_compat, out);
+        case 12: return run<12>(x, n_in, Ha, Hs, win, n_analysed, n_frames, nan_compat, out);
         default: return -1;
     }
 }
@@ -173,7 +174,7 @@ extern "C" int emul_corrected(int log2n, const float *x, long n_in, int Ha, int 
 {
 #define RC(L) case L: return run_corrected<L>(x, n_in, Ha, Hs, win, V, nomA, a_lo, a_hi, nomS, Rq, beta_q, gain, n_frames, out, out_stride)
     switch (log2n) {
-        RC(8); RC(9); RC(10); RC(11);
+        RC(8); RC(9); RC(10); RC(11); RC(12);
         default: return -1;
     }
 #undef RC

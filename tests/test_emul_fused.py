@@ -30,7 +30,8 @@ def emul():
 
 
 @pytest.mark.parametrize("N,Ha,Hs,nf", [(256, 64, 64, 24), (256, 128, 128, 12), (512, 128, 128, 10),
-                                        (1024, 102, 512, 8), (2048, 512, 512, 7), (256, 1, 128, 6)])
+                                        (1024, 102, 512, 8), (2048, 512, 512, 7), (256, 1, 128, 6),
+                                        (4096, 1024, 1024, 6), (4096, 1000, 2048, 4)])
 def test_fused_body_matches_oracle(emul, N, Ha, Hs, nf):
     n_in = N + (nf - 1) * Ha - 3
     x = multitone(n_in, seed=N + Ha)
@@ -47,7 +48,7 @@ def test_fused_body_matches_oracle(emul, N, Ha, Hs, nf):
 @pytest.mark.parametrize("N,Ha,Hs,betas,nf", [
     (256, 64, 64, [1.0], 30), (256, 64, 64, [1.0, 2 ** (4 / 12), 2 ** (7 / 12), 2.0], 30),
     (512, 128, 128, [1.5], 16), (1024, 102, 512, [1.0], 12), (2048, 512, 512, [2 ** (7 / 12)], 9),
-    (2048, 512, 512, [0.75, 1.0], 7),
+    (2048, 512, 512, [0.75, 1.0], 7), (4096, 1024, 1024, [2 ** (7 / 12)], 7), (4096, 1024, 512, [0.8, 1.0, 1.5], 5),
 ])
 def test_corrected_body_matches_oracle(emul, N, Ha, Hs, betas, nf):
     emul.emul_corrected.argtypes = [C.c_int, C.POINTER(C.c_float), C.c_long, C.c_int, C.c_int, C.POINTER(C.c_float),

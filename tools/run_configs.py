@@ -15,6 +15,7 @@ import torch
 
 import pv_oracle as po
 import pvb200
+from aligned import aligned_parity
 from signals import c3_multitone, multitone, snr_db
 
 f32 = lambda b: float(np.float32(b))
@@ -33,9 +34,24 @@ def timed(fn, n=5):
     return e0.elapsed_time(e1) / n
 
 
-def run(name, N, Ha, Hs, mode, betas, streams, frames, fs, gen, check_streams=2, check_frames=None):
+def golden_wav():
+    """Committed raw-integer slices of the reference's C1 / C2 input WAVs (tests/golden/golden_wav.npz), decoded with
+    AudioFile's rules."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_wav.npz"))
+    return (g["c1_440sine"].astype(np.float32) / np.float32(32768.0), g["c2_matzo"].astype(np.float32) / np.float32(8388608.0))
+
+
+def tiled(x):
+    """Generator that repeats a real slice to the requested length (timing rows; parity uses the slice itself)."""
+    return lambda n, s: np.tile(x[s % len(x)], n // x.shape[1] + 1)[:n]
+
+
+def run(name, N, Ha, Hs, mode, betas, streams, frames, fs, gen, check_streams=2, check_frames=None, wt=None):
+    """Parity column: compat = worst direct SNR against the fp64 oracle; corrected = "direct / decision-aligned" SNR
+    (tests/aligned.py: the unwrap is discontinuous, a few boundary decisions may differ between fp32 and fp64)."""
     corrected = mode == "corrected"
-    wt = pvb200.WIN_HANN_PERIODIC if corrected else pvb200.WIN_HAMMING
+    if wt is None:
+        wt = pvb200.WIN_HANN_PERIODIC if corrected else pvb200.WIN_HAMMING
     pv = pvb200.PhaseVocoder(N, hop_in=Ha, hop_out=Hs, mode=pvb200.MODE_CORRECTED if corrected else pvb200.MODE_COMPAT,
                              window_type=wt, pitch=tuple(betas))
     n_in = N + (frames - 1) * Ha
@@ -43,23 +59,27 @@ def run(name, N, Ha, Hs, mode, betas, streams, frames, fs, gen, check_streams=2,
     x = torch.from_numpy(np.tile(xs, ((streams + len(xs) - 1) // len(xs), 1))[:streams]).cuda()
     out = torch.empty((streams, len(betas) if corrected else 1, frames * Hs), device="cuda")
     ms = timed(lambda: pv.process(x, frames, out=out))
-    got = out[:check_streams].cpu().numpy()
     cf = frames if check_frames is None else min(frames, check_frames)
-    worst = 1e9
-    win = po.window(po.WIN_HANN_PERIODIC if corrected else po.WIN_HAMMING, N)
+    # parity on the first cf frames of the checked streams (a separate short run: same kernels, same arithmetic)
+    got = pv.process(x[:check_streams, :N + (cf - 1) * Ha].contiguous(), cf).cpu().numpy()
+    worst, worst_al, flips = 1e9, 1e9, 0
+    win = pv.imp
     for s in range(check_streams):
+        xc = xs[s][:N + (cf - 1) * Ha]
         if corrected:
-            want, _ = po.process_corrected(xs[s], N, Ha, Hs, win, betas, cf)
+            D = pv.unwrap_decisions(torch.from_numpy(xc).cuda(), cf).cpu().numpy()
+            r = aligned_parity(xc, N, Ha, Hs, win, betas, cf, D, got[s])
+            assert r["phase_ratio"] < 1.0, r
+            worst, worst_al, flips = min(worst, min(r["direct"])), min(worst_al, min(r["aligned"])), flips + r["flips"]
         else:
-            w, _ = po.process_compat(xs[s], N, Ha, Hs, win, cf, cf)
-            want = w[None]
-        for v in range(want.shape[0]):
-            worst = min(worst, snr_db(want[v], got[s, v, :cf * Hs]))
+            w, _ = po.process_compat(xc, N, Ha, Hs, win, cf, cf)
+            worst = min(worst, snr_db(w, got[s, 0]))
     fps = streams * frames / (ms * 1e-3)
     V = len(betas) if corrected else 1
     gbs = fps * (4 * Ha + 4 * V * Hs) / 1e9
+    par = f"{worst:.1f} / {worst_al:.1f} ({flips} flips)" if corrected else f"{worst:.1f}"
     print(f"| {name} | {N} | {Ha}/{Hs} | {mode} | {V} | {streams} x {frames} | {ms:.3f} | {fps/1e6:.2f} M | "
-          f"{fps*Ha/fs:,.0f} | {gbs:.0f} | {worst:.1f} |", flush=True)
+          f"{fps*Ha/fs:,.0f} | {gbs:.0f} | {par} |", flush=True)
 
 
 def realtime_step(streams=4096, N=256, H=64, betas=(1.0, 2 ** (4 / 12), 2 ** (7 / 12), 2.0), calls=300):
@@ -118,17 +138,22 @@ def main():
     if "--sweep" in sys.argv:
         return sweep()
     print("| config | window | Ha/Hs | mode | voices | streams x frames | ms/launch | frames/s | audio-s/s (input) | "
-          "algorithmic GB/s | worst SNR vs fp64 oracle (dB) |")
+          "algorithmic GB/s | worst SNR vs fp64 oracle (dB): compat direct; corrected direct / decision-aligned |")
     print("|---|---|---|---|---|---|---|---|---|---|---|")
     tone = lambda n, s: multitone(n, seed=s, noise=0.0)
     noisy = lambda n, s: multitone(n, seed=s, noise=1e-3)
     semi = lambda k: f32(2 ** (k / 12))
-    # C1: 440sine-like, window 256 hop 64: compat plumbing + pitch x1.5 corrected (10 s = 6890 frames)
-    sine = lambda n, s: (0.25 * np.sin(2 * np.pi * 440 * np.arange(n) / 44100)).astype(np.float32)
-    run("C1 compat", 256, 64, 64, "compat", [1.0], 2, 6890, 44100, sine)
-    run("C1 pitch x1.5", 256, 64, 64, "corrected", [1.5], 2, 6890, 44100, sine, check_frames=2000)
-    # C2: window 2048 hop 512, +7 semitones (5.58 s stereo = 2 x 480 frames; and the headline batch)
-    run("C2 file-sized", 2048, 512, 512, "corrected", [semi(7)], 2, 480, 44100, tone)
+    # C1: testtones/440sine.wav (committed slice, tiled to the file's 10 s = 6890 frames for the timing), window 256 hop 64:
+    # compat plumbing + pitch x1.5; window table of the reference's constructor (Hamming) and the periodic Hann
+    c1, c2 = golden_wav()
+    run("C1 compat (440sine.wav)", 256, 64, 64, "compat", [1.0], 2, 6890, 44100, tiled(c1), check_frames=512)
+    run("C1 pitch x1.5 (440sine.wav, Hamming)", 256, 64, 64, "corrected", [1.5], 2, 6890, 44100, tiled(c1), check_frames=512, wt=pvb200.WIN_HAMMING)
+    run("C1 pitch x1.5 (440sine.wav, Hann)", 256, 64, 64, "corrected", [1.5], 2, 6890, 44100, tiled(c1), check_frames=512)
+    # C2: testtones/MAT_ZO_24_bit.wav (committed 24-bit slice; the file is 5.58 s stereo = 2 x 480 frames), window 2048 hop 512,
+    # +7 semitones; and the headline batch
+    run("C2 compat (MAT_ZO_24_bit.wav)", 2048, 512, 512, "compat", [1.0], 2, 480, 44100, tiled(c2), check_frames=64)
+    run("C2 +7 st (MAT_ZO_24_bit.wav, Hamming)", 2048, 512, 512, "corrected", [semi(7)], 2, 480, 44100, tiled(c2), check_frames=64, wt=pvb200.WIN_HAMMING)
+    run("C2 +7 st (MAT_ZO_24_bit.wav, Hann)", 2048, 512, 512, "corrected", [semi(7)], 2, 480, 44100, tiled(c2), check_frames=64)
     run("C2 headline batch", 2048, 512, 512, "corrected", [semi(7)], 1184, 860, 44100, noisy, check_frames=120)
     run("C2 headline batch", 2048, 512, 512, "compat", [1.0], 1184, 860, 44100, noisy, check_frames=120)
     # C3: window 1024, time stretch "in-hop 10 / out-hop 2": hop divisors (102/512) and literal samples (10/2)
@@ -140,7 +165,7 @@ def main():
     run("C4 harmoniser", 256, 64, 64, "corrected", [1.0, semi(4), semi(7), 2.0], 4096, 6890, 44100, noisy, check_frames=400)
     # C5: 1 h, 48 kHz, stereo, window 4096 hop 1024 (168 750 frames per channel)
     run("C5 long file", 4096, 1024, 1024, "compat", [1.0], 2, 168750, 48000, noisy, check_frames=300)
-    run("C5 long file", 4096, 1024, 1024, "corrected", [semi(7)], 2, 20000, 48000, tone, check_frames=100)
+    run("C5 long file", 4096, 1024, 1024, "corrected", [semi(7)], 2, 168750, 48000, noisy, check_frames=100)
     realtime_step()
 
 
