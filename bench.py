@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=FRAMES_PER_STREAM)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the frame-range-sharded long file (config 5) at --gpus > 1")
     return ap.parse_args()
 
 
@@ -287,6 +288,85 @@ def bind_to_gpu_numa_node(index):
         return None
 
 
+def c5_sharded(torch, dist, pvb200, world, rank, local, seconds=3600.0):
+    """BASELINE.json config 5: a synthetic 1-hour 48 kHz stereo file, window 4096 / hop 1024 (2 x 168 750 frames), frame-range
+    sharded over the ranks behind the C ABI (pv_shard_begin -> ONE NCCL all-gather of the carry records -> pv_shard_finish).
+    Every rank hands the library only its own view (range + overlap-add halo + one frame).  Timing: CUDA events, max over
+    ranks; rank 0 also runs the whole file alone for the speed-up and checks the gathered result bit for bit."""
+    from pvb200 import sharding
+    N, H, fs = 4096, 1024, 48000.0
+    nf = int(seconds * fs) // H
+    n = N + (nf - 1) * H
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0)                                  # the same file on every rank
+    t = torch.arange(n, device="cuda", dtype=torch.float64)
+    x = torch.empty((2, n), device="cuda", dtype=torch.float32)
+    for c in range(2):
+        f = torch.rand(3, generator=g, device="cuda", dtype=torch.float64) * (8000.0 - 80.0) + 80.0
+        a = torch.rand(3, generator=g, device="cuda", dtype=torch.float64) * 0.2 + 0.1
+        acc = torch.zeros(n, device="cuda", dtype=torch.float32)
+        for i in range(3):
+            acc += (a[i] * torch.sin(6.283185307179586 * f[i] / fs * t)).float()
+        x[c] = acc + torch.randn(n, generator=g, device="cuda") * 1e-3
+    del t
+    comm = sharding.TorchComm()
+    rec = {"workload": f"synthetic {seconds / 3600:g} h 48 kHz stereo file, window {N}, hop {H}: 2 x {nf} frames, frame ranges over "
+                       f"{world} GPUs", "exchange": "one all_gather of pv_shard_carry_elems() int64 per channel and rank (corrected); "
+                                                    "none (compat: input halo recomputed)"}
+    for mode in ("corrected", "compat"):
+        corr = mode == "corrected"
+        mk = lambda: pvb200.PhaseVocoder(N, hop_in=H, hop_out=H, device=local, mode=pvb200.MODE_CORRECTED if corr else pvb200.MODE_COMPAT,
+                                         window_type=pvb200.WIN_HANN_PERIODIC if corr else pvb200.WIN_HAMMING, pitch=(SEMITONES_7,))
+        pv = mk()
+        p = pv.shard_plan(nf, world, rank)
+        first = max(0, p.ks - 1) if p.k1 > p.k0 else 0
+        xr = x[:, first * H:min(n, (max(p.k1, 1) - 1) * H + N)].contiguous() if p.k1 > p.k0 else x[:, :N].contiguous()
+        run = lambda: sharding.process_sharded_capi(pv, xr, first, nf, comm)[0]
+        for _ in range(2):
+            out = run()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            out = run()
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        per = (nf + world - 1) // world
+        pad = torch.zeros((2, 1, per * H), device="cuda")
+        pad[:, :, :out.shape[2]] = out
+        parts = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, parts, dst=0)
+        r = {"ms": float(ms.item()), "frames_per_s": 2 * nf / (float(ms.item()) * 1e-3), "carry_bytes_per_rank": 2 * 8 * pv.shard_carry_elems() if corr else 0}
+        if rank == 0:
+            got = torch.cat(parts, 2)[:, :, :nf * H]
+            del parts, pad
+            one = mk()
+            ref = one.process(x, nf)
+            torch.cuda.synchronize()
+            r["bit_identical_to_single_gpu"] = bool(torch.equal(got, ref))
+            del got
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(reps):
+                one.process(x, nf, out=ref)
+            t1.record()
+            torch.cuda.synchronize()
+            r["single_gpu_ms"] = t0.elapsed_time(t1) / reps
+            r["speedup_vs_single_gpu"] = r["single_gpu_ms"] / r["ms"]
+            one.close()
+            del ref
+        pv.close()
+        del out, xr
+        torch.cuda.empty_cache()
+        rec[mode] = r
+    return rec
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -415,31 +495,46 @@ def run_ours(args):
                  "corrected = phase-unwrap/pitch pipeline the north star names (+7 semitones)"}
         pv2.close()
 
+    # ---- BASELINE config 5 when several GPUs are given: ONE long stereo file, frame-range sharded over the ranks ----
+    c5 = None
+    if world > 1 and not args.no_c5:
+        del x, out
+        torch.cuda.empty_cache()
+        c5 = c5_sharded(torch, dist, pvb200, world, rank, local)
+
     if rank == 0:
         peak, peak_src, sm_max = peaks()
         bytes_per_frame = 4 * HOP + 4 * V * HOP
-        kern_s = (kern_ms * 1e-3 / kern_n) if kern_n else (ms_total * 1e-3 / args.steps)
+        # fused stream-kernel time per step (a step may issue several launches: ragged last wave, frame-range split)
+        kern_s = (kern_ms * 1e-3 / args.steps) if kern_n else (ms_total * 1e-3 / args.steps)
         achieved = S * F * bytes_per_frame / kern_s / 1e9
         traffic = None          # dram__bytes_read + dram__bytes_write of one ncu --set full capture of this launch shape
-        issue = None            # the limit that actually binds: warp-instruction issue slots (4 per SM and cycle)
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[args.mode]
-            if tr["frames_per_launch"] == S * F:
-                traffic = tr["bytes_per_launch"]
-                wpf = tr.get("warp_instructions_per_frame")
-                if wpf:
-                    sms = torch.cuda.get_device_properties(local).multi_processor_count
-                    peak_issue = sms * 4 * (sm_max or 1965.0) * 1e6
-                    issue = {"warp_instructions_per_frame": wpf, "achieved": S * F * wpf / kern_s / 1e9,
-                             "peak": peak_issue / 1e9, "unit": "G warp-instructions/s",
-                             "frac": S * F * wpf / kern_s / peak_issue,
-                             "note": "instruction count from the ncu capture in profiles/, time measured live"}
-        except Exception:
-            pass
+        traffic_source = None
+        issue = None            # warp-instruction issue slots (4 per SM and cycle): what bound the round-1 kernels
+        for tf in ("r02_traffic.json", "r01_traffic.json"):
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", tf)))[args.mode]
+            except Exception:
+                continue
+            if tr["frames_per_launch"] != S * F:
+                continue
+            traffic = tr["bytes_per_launch"]
+            traffic_source = (f"profiles/{tf}: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this "
+                              "launch shape (a constant from that capture, NOT measured in this run)")
+            wpf = tr.get("warp_instructions_per_frame")
+            if wpf:
+                sms = torch.cuda.get_device_properties(local).multi_processor_count
+                peak_issue = sms * 4 * (sm_max or 1965.0) * 1e6
+                issue = {"warp_instructions_per_frame": wpf, "achieved": S * F * wpf / kern_s / 1e9,
+                         "peak": peak_issue / 1e9, "unit": "G warp-instructions/s",
+                         "frac": S * F * wpf / kern_s / peak_issue,
+                         "note": "instruction count from the ncu capture in profiles/, time measured live"}
+            break
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "algorithmic_bytes_per_launch": S * F * bytes_per_frame, "peak_source": peak_src, "kernel": "fused stream kernel",
+                    "traffic": traffic, "traffic_source": traffic_source, "algorithmic_bytes_per_launch": S * F * bytes_per_frame, "peak_source": peak_src, "kernel": "fused stream kernel",
                     "kernel_ms": kern_s * 1e3, "algorithmic_bytes_per_frame": bytes_per_frame,
-                    "note": "fully fused, the path is instruction-issue bound, not HBM bound (SURVEY fact 5): see `issue`",
+                    "note": "fully fused, the path is bound by instruction issue / latency at 16-20 resident warps per SM, not by HBM "
+                            "(SURVEY fact 5; DESIGN.md 4.4): see `issue`",
                     "issue": issue}
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s",
@@ -453,6 +548,8 @@ def run_ours(args):
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         line["other_mode"] = other
+        if c5 is not None:
+            line["c5_sharded"] = c5
         if world == 1:
             line["reference_gpu_build"] = reference_gpu_build()
         if world == 1 and not args.no_cpu_baseline:

@@ -195,6 +195,45 @@ int pv_corrected_split_aggregate(pv_handle *h, const float *in, int64_t n_stream
                                  int64_t n_in, int64_t n_frames, int64_t skip_frames, const void *state,
                                  int32_t flags, int64_t *sumD, void *cuda_stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Frame-range sharding of long streams over the GPUs of a box (BASELINE.json config 5): rank r of
+ * `world` (one handle per rank / GPU) produces frames [k0, k1) of every stream.  The reference has no such path
+ * (one host loop over all frames, src/main.cpp:228-297); this replaces that loop for a sharded file.
+ *
+ * What crosses ranks:  compat -- nothing (frames are independent; the (N-1)/Hs frames in front of a range are
+ * recomputed from the input halo).  corrected -- the per-bin phase carry: ONE all-gather of
+ * pv_shard_carry_elems() int64 per stream and rank (the rank's sum of unwrapped phase differences per bin, plus
+ * rank 0's phase of frame 0).  Integer sums are associative, so the sharded output is bit-identical to the
+ * single-GPU one.  The library does everything except the collective itself, which the caller issues between the
+ * two calls with whatever it has (ncclAllGather, MPI_Allgather, torch.distributed, cudaMemcpyPeerAsync):
+ *
+ *     pv_shard_begin (h, in, ..., world, rank, carry_send, stream);          // analysis of the rank's range
+ *     ncclAllGather(carry_send, carry_all, n_streams * pv_shard_carry_elems(h), ncclInt64, comm, stream);
+ *     pv_shard_finish(h, in, ..., world, rank, carry_all, out, ..., stream); // state from the carry + processing
+ *
+ * `in` points at sample in_first_frame*Ha of stream 0 (in_first_frame <= max(0, ks-1), so a rank only needs its
+ * own range plus the halo resident; rank 0 needs frame 0), n_in counts the valid samples from there (zero beyond).
+ * carry_send: device, [n_streams][elems]; carry_all: device, [world][n_streams][elems].  The range is analysed
+ * once: pv_shard_finish reuses the per-part sums pv_shard_begin left in the handle (PV_PROCESS_REUSE_AGGREGATE),
+ * provided nothing else ran on the handle in between (otherwise it recomputes them; the result is the same).
+ * out receives frames [k0, k1): out[stream][voice][(k - k0)*Hs ..].
+ * ---------------------------------------------------------------------------------------- */
+typedef struct pv_shard_plan {
+    int64_t k0, k1;   /* frames this rank writes */
+    int64_t ks;       /* first frame it computes: k0 - halo, clipped at 0 */
+    int64_t halo;     /* (N-1)/Hs */
+} pv_shard_plan;
+
+int pv_shard_plan_frames(const pv_handle *h, int64_t n_frames, int32_t world, int32_t rank, pv_shard_plan *out);
+size_t pv_shard_carry_elems(const pv_handle *h);
+int pv_shard_begin(pv_handle *h, const float *in, int64_t in_first_frame, int64_t n_streams, int64_t in_stride,
+                   int64_t n_in, int64_t n_frames, int32_t world, int32_t rank, int64_t *carry_send,
+                   void *cuda_stream);
+int pv_shard_finish(pv_handle *h, const float *in, int64_t in_first_frame, int64_t n_streams, int64_t in_stride,
+                    int64_t n_in, int64_t n_analysed, int64_t n_frames, int32_t world, int32_t rank,
+                    const int64_t *carry_all, float *out, int64_t out_stream_stride, int64_t out_voice_stride,
+                    void *cuda_stream);
+
 /* Same with HOST buffers (pinned or pageable): H2D, kernel, D2H, synchronise.  This is the
  * call the C++ PhaseVocoder shim and the CLI make, and what bench.py times as `e2e`.         */
 int pv_process_host(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride,

@@ -69,6 +69,11 @@ struct pv_handle {
     size_t state_cap = 0;
     void *d_scratch_state = nullptr;
     size_t scratch_cap = 0;
+    // frame-range sharding across ranks (pv_shard_begin / pv_shard_finish): per-stream scratch of the rank
+    int64_t *d_sh_total = nullptr, *d_sh_minus = nullptr;
+    uint32_t *d_sh_Pm1 = nullptr, *d_sh_P0 = nullptr;
+    unsigned char *d_sh_state = nullptr;
+    size_t sh_cap = 0;
     cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};        // host path: H2D, kernels, D2H
     std::vector<cudaEvent_t> pipe_events;
     // accounting
@@ -520,6 +525,11 @@ void pv_destroy(pv_handle *h)
     cudaFree(h->d_out);
     cudaFree(h->d_state);
     cudaFree(h->d_scratch_state);
+    cudaFree(h->d_sh_total);
+    cudaFree(h->d_sh_minus);
+    cudaFree(h->d_sh_Pm1);
+    cudaFree(h->d_sh_P0);
+    cudaFree(h->d_sh_state);
     for (auto ps : h->pipe)
         if (ps) cudaStreamDestroy(ps);
     for (auto &e : h->events) {
@@ -908,6 +918,140 @@ static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_
     a.segs = pl->d_segs;
     a.n_segs = (int32_t)((int64_t)pl->n_segs / plan_streams * n_streams);      // stream-major table
     return launch_segments(h, a, n_streams, flags, st);
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Frame-range sharding across ranks (include/pv_b200.h, "Frame-range sharding of long streams")
+// ---------------------------------------------------------------------------------------------------
+int pv_shard_plan_frames(const pv_handle *h, int64_t n_frames, int32_t world, int32_t rank, pv_shard_plan *out)
+{
+    if (!h || !out || n_frames < 0 || world < 1 || rank < 0 || rank >= world) return fail(PV_ERR_PARAM, "pv_shard_plan_frames: bad argument");
+    const int64_t per = (n_frames + world - 1) / world;
+    out->k0 = std::min<int64_t>(n_frames, (int64_t)rank * per);
+    out->k1 = std::min<int64_t>(n_frames, out->k0 + per);
+    out->halo = (h->p.window - 1) / h->p.hop_out;
+    out->ks = std::max<int64_t>(0, out->k0 - out->halo);
+    return PV_OK;
+}
+
+size_t pv_shard_carry_elems(const pv_handle *h)
+{
+    if (!h) return 0;
+    const size_t nb = (size_t)h->p.window / 2 + 1;
+    return nb + (nb + 1) / 2;
+}
+
+static int shard_scratch(pv_handle *h, int64_t n_streams)
+{
+    const size_t nb = (size_t)h->p.window / 2 + 1, need = (size_t)n_streams * nb;
+    if (need <= h->sh_cap) return PV_OK;
+    if (h->sh_cap) cudaDeviceSynchronize();
+    cudaFree(h->d_sh_total); cudaFree(h->d_sh_minus); cudaFree(h->d_sh_Pm1); cudaFree(h->d_sh_P0); cudaFree(h->d_sh_state);
+    h->d_sh_total = h->d_sh_minus = nullptr; h->d_sh_Pm1 = h->d_sh_P0 = nullptr; h->d_sh_state = nullptr; h->sh_cap = 0;
+    PV_CUDA(cudaMalloc((void **)&h->d_sh_total, sizeof(int64_t) * need));
+    PV_CUDA(cudaMalloc((void **)&h->d_sh_minus, sizeof(int64_t) * need));
+    PV_CUDA(cudaMalloc((void **)&h->d_sh_Pm1, sizeof(uint32_t) * need));
+    PV_CUDA(cudaMalloc((void **)&h->d_sh_P0, sizeof(uint32_t) * need));
+    PV_CUDA(cudaMalloc((void **)&h->d_sh_state, (size_t)n_streams * pv_state_bytes(h)));
+    h->sh_cap = need;
+    return PV_OK;
+}
+
+int pv_shard_begin(pv_handle *h, const float *in, int64_t in_first_frame, int64_t n_streams, int64_t in_stride,
+                   int64_t n_in, int64_t n_frames, int32_t world, int32_t rank, int64_t *carry_send, void *cuda_stream)
+{
+    if (!h || !in || !carry_send || n_streams < 0 || in_first_frame < 0) return fail(PV_ERR_PARAM, "pv_shard_begin: bad argument");
+    pv_shard_plan p;
+    int rc = pv_shard_plan_frames(h, n_frames, world, rank, &p);
+    if (rc != PV_OK) return rc;
+    if (n_streams == 0) return PV_OK;
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int nb = h->p.window / 2 + 1, elems = (int)pv_shard_carry_elems(h);
+    const int64_t Ha = h->p.hop_in;
+    if (h->p.mode != PV_MODE_CORRECTED || p.k1 <= p.k0) {        // nothing to contribute: compat mode, or an empty range
+        PV_CUDA(cudaMemsetAsync(carry_send, 0, sizeof(int64_t) * (size_t)n_streams * (size_t)elems, st));
+        return PV_OK;
+    }
+    if (in_first_frame > std::max<int64_t>(0, p.ks - 1))
+        return fail(PV_ERR_PARAM, "pv_shard_begin: rank %d needs the input from frame %lld on, got it from frame %lld", rank,
+                    (long long)std::max<int64_t>(0, p.ks - 1), (long long)in_first_frame);
+    rc = shard_scratch(h, n_streams);
+    if (rc != PV_OK) return rc;
+    auto at = [&](int64_t frame) { return in + (frame - in_first_frame) * Ha; };
+    auto left = [&](int64_t frame) { return std::max<int64_t>(0, n_in - (frame - in_first_frame) * Ha); };
+    if (p.ks == 0) {
+        // the range reaches frame 0: fresh start.  D over [1, k1) from the analysis pass of the processing call itself,
+        // minus what lies before k0 (another rank reports that)
+        rc = process_impl(h, at(0), n_streams, n_streams, in_stride, left(0), p.k1, p.k1, p.k0, nullptr, 0, 0, nullptr, 0,
+                          cuda_stream, h->d_sh_total);
+        if (rc != PV_OK) return rc;
+        const pv_handle::Plan *keep = h->agg_valid_for;
+        const bool before = p.k0 > 1;
+        if (before) rc = pv_corrected_aggregate(h, at(0), n_streams, in_stride, left(0), p.k0, nullptr, h->d_sh_minus, nullptr, nullptr, cuda_stream);
+        if (rc == PV_OK && p.k0 == 0)
+            rc = pv_corrected_aggregate(h, at(0), n_streams, in_stride, left(0), 1, nullptr, h->d_sh_minus, h->d_sh_P0, nullptr, cuda_stream);
+        if (rc != PV_OK) return rc;
+        h->agg_valid_for = keep;       // the small aggregates above ran unsplit: the per-part sums of the range are still there
+        PV_CUDA(pv_launch_shard_pack(nb, elems, n_streams, h->d_sh_total, before ? h->d_sh_minus : nullptr,
+                                     p.k0 == 0 ? h->d_sh_P0 : nullptr, carry_send, st));
+        h->launches++;
+        return PV_OK;
+    }
+    // D over the halo [ks, k0) and the phase of frame ks-1, from a handful of frames
+    rc = pv_corrected_aggregate(h, at(p.ks - 1), n_streams, in_stride, left(p.ks - 1), p.k0 - p.ks + 1, nullptr, h->d_sh_minus,
+                                h->d_sh_Pm1, nullptr, cuda_stream);
+    if (rc != PV_OK) return rc;
+    // a state that holds only the previous phase (accumulators unknown yet), so that frame ks has a phase difference
+    PV_CUDA(cudaMemsetAsync(h->d_sh_total, 0, sizeof(int64_t) * (size_t)n_streams * nb, st));
+    PV_CUDA(cudaMemsetAsync(h->d_sh_P0, 0, sizeof(uint32_t) * (size_t)n_streams * nb, st));
+    PV_CUDA(pv_launch_state_from_carry(h->dev, h->ft, n_streams, h->d_sh_P0, h->d_sh_total, 1, h->d_sh_Pm1, h->d_sh_state,
+                                       (int64_t)pv_state_bytes(h), st));
+    h->launches++;
+    rc = process_impl(h, at(p.ks), n_streams, n_streams, in_stride, left(p.ks), p.k1 - p.ks, p.k1 - p.ks, p.k0 - p.ks, nullptr, 0, 0,
+                      h->d_sh_state, PV_PROCESS_CARRY_IN, cuda_stream, h->d_sh_total);       // D over [ks, k1)
+    if (rc != PV_OK) return rc;
+    PV_CUDA(pv_launch_shard_pack(nb, elems, n_streams, h->d_sh_total, h->d_sh_minus, nullptr, carry_send, st));
+    h->launches++;
+    return PV_OK;
+}
+
+int pv_shard_finish(pv_handle *h, const float *in, int64_t in_first_frame, int64_t n_streams, int64_t in_stride,
+                    int64_t n_in, int64_t n_analysed, int64_t n_frames, int32_t world, int32_t rank,
+                    const int64_t *carry_all, float *out, int64_t out_stream_stride, int64_t out_voice_stride,
+                    void *cuda_stream)
+{
+    if (!h || !in || !out || n_streams < 0 || in_first_frame < 0) return fail(PV_ERR_PARAM, "pv_shard_finish: bad argument");
+    pv_shard_plan p;
+    int rc = pv_shard_plan_frames(h, n_frames, world, rank, &p);
+    if (rc != PV_OK) return rc;
+    if (n_streams == 0 || p.k1 <= p.k0) return PV_OK;
+    if (in_first_frame > std::max<int64_t>(0, p.ks - (h->p.mode == PV_MODE_CORRECTED ? 1 : 0)))
+        return fail(PV_ERR_PARAM, "pv_shard_finish: the input must start at or before frame %lld", (long long)std::max<int64_t>(0, p.ks - 1));
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int64_t Ha = h->p.hop_in;
+    const float *x = in + (p.ks - in_first_frame) * Ha;
+    const int64_t n_left = std::max<int64_t>(0, n_in - (p.ks - in_first_frame) * Ha);
+    const int64_t nf = p.k1 - p.ks, skip = p.k0 - p.ks;
+    const int64_t an = std::max<int64_t>(0, std::min<int64_t>(nf, n_analysed - p.ks));
+    if (h->p.mode != PV_MODE_CORRECTED)        // compat: frames are independent, the halo is recomputed
+        return process_impl(h, x, n_streams, n_streams, in_stride, n_left, an, nf, skip, out, out_stream_stride, out_voice_stride,
+                            nullptr, 0, cuda_stream);
+    if (p.ks == 0)
+        return process_impl(h, x, n_streams, n_streams, in_stride, n_left, nf, nf, skip, out, out_stream_stride, out_voice_stride,
+                            nullptr, PV_PROCESS_REUSE_AGGREGATE, cuda_stream);
+    if (!carry_all) return fail(PV_ERR_PARAM, "pv_shard_finish: corrected mode needs the gathered carry");
+    const int nb = h->p.window / 2 + 1, elems = (int)pv_shard_carry_elems(h);
+    if ((size_t)n_streams * nb > h->sh_cap) return fail(PV_ERR_PARAM, "pv_shard_finish without a matching pv_shard_begin");
+    // prefix up to ks = everything the ranks before this one own, minus the D of the halo frames [ks, k0)
+    PV_CUDA(pv_launch_shard_prefix(nb, elems, rank, n_streams, carry_all, h->d_sh_minus, h->d_sh_total, h->d_sh_P0, st));
+    PV_CUDA(pv_launch_state_from_carry(h->dev, h->ft, n_streams, h->d_sh_P0, h->d_sh_total, p.ks, h->d_sh_Pm1, h->d_sh_state,
+                                       (int64_t)pv_state_bytes(h), st));
+    h->launches += 2;
+    return process_impl(h, x, n_streams, n_streams, in_stride, n_left, nf, nf, skip, out, out_stream_stride, out_voice_stride,
+                        h->d_sh_state, PV_PROCESS_CARRY_IN | PV_PROCESS_REUSE_AGGREGATE, cuda_stream);
 }
 
 }  // extern "C"

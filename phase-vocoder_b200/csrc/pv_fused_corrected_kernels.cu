@@ -4,6 +4,7 @@
 // one stream segment; the stream state (previous analysis phase in registers, 64-bit phase
 // accumulators and the per-voice overlap-add rings in shared memory) never leaves the SM between
 // frames.  HBM traffic per frame: 4*Ha bytes in, 4*V*Hs bytes out.
+#include <algorithm>
 #include <cstdlib>
 
 #include "pv_fused_corrected.cuh"
@@ -169,6 +170,10 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
         const AggCtx ac{agg_mode, k < seg.k_emit ? sumH : sumS, agg_pf};
         frame_corrected<LOG2N>(tid, io, tb, tt, ring, bufA, bufB, magS, dS, psi, acc, st, pos0, Hs, sync, hook,
                                [&]() { if (use_ring) cp_async_wait_all(); }, ac);
+        if (agg_mode && use_ring) {        // analysis only: no inverse passes whose last barrier would complete the refill
+            cp_async_wait_all();
+            sync();
+        }
         pos0 = (pos0 + Hs) & (N - 1);
     }
     if (agg_mode) {
@@ -304,11 +309,15 @@ static cudaError_t agg_launch(const PvDev &d, const CTables &tb, const PvAggArgs
 {
     using L = CLaunch<LOG2N>;
     auto kern = corrected_fused_kernel<LOG2N, MINB>;
-    const size_t gb = L::group_bytes(tb.V) - (size_t)d.N * 4;          // no input ring
+    const bool in_ok = (d.Ha % 2 == 0) && (ag.in_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(ag.in) & 7) == 0);
+    // the analysis pass streams its input through the same shared-memory ring as the processing pass (each hop is
+    // fetched once, one frame ahead); without it every frame re-reads its whole window from L2 with the latency exposed
+    const bool al16 = in_ok && (d.Ha % 4 == 0) && (ag.in_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(ag.in) & 15) == 0);
+    const int ring = (in_ok && d.Ha <= d.N) ? (al16 ? 2 : 1) : 0;
+    const size_t gb = L::group_bytes(tb.V) - (ring ? 0 : (size_t)d.N * 4);
     const size_t smem = gb * L::G;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(L::group_bytes(tb.V) * L::G));
     if (e != cudaSuccess) return e;
-    const bool in_ok = (d.Ha % 2 == 0) && (ag.in_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(ag.in) & 7) == 0);
     PvProcessArgs a{};
     a.in = ag.in;
     a.in_stride = ag.in_stride;
@@ -316,7 +325,7 @@ static cudaError_t agg_launch(const PvDev &d, const CTables &tb, const PvAggArgs
     a.segs = ag.segs;
     a.n_segs = ag.n_segs;
     const int grid = (ag.n_segs + L::G - 1) / L::G;
-    kern<<<grid, L::THREADS, smem, st>>>(d, tb, a, in_ok, 0, 0, (unsigned)gb, ag);
+    kern<<<grid, L::THREADS, smem, st>>>(d, tb, a, in_ok, 0, ring, (unsigned)gb, ag);
     return cudaGetLastError();
 }
 
@@ -334,17 +343,18 @@ cudaError_t pv_launch_corrected_aggregate(const PvDev &d, const PvFusedTables &t
     }
 }
 
-// One block per stream walks its parts in order: running = sum_{q<p} S_q (per bin, int64 in shared memory).
+// Per-part carried states of split streams.  grid = (stream, tile of 256 entries): thread i of a stream owns entry i of
+// every array it fills -- accumulator (voice, synthesis bin) i < V*NB with its own running sum of S at its source bin
+// a_hi, previous-phase bin i < NB, words i of the copied caller state -- and walks the parts in order.  (Round 1 used ONE
+// block per stream: 1.7 ms for the two channels of C5, 10 % of the whole call.)
 __global__ void split_states_kernel(PvDev d, CTables tb, int parts, const PvSegment *segs, const long long *S,
                                     const long long *H, const uint32_t *P_first, unsigned char *slots, long long slot_stride,
                                     const unsigned char *state_in)
 {
-    extern __shared__ long long sh[];
     const int NB = d.N / 2 + 1, V = tb.V, N = d.N;
-    long long *run = sh, *pre = sh + NB;
     const long long s = blockIdx.x;
-    for (int b = threadIdx.x; b < NB; b += blockDim.x) run[b] = 0;
-    __syncthreads();
+    const int i = blockIdx.y * blockDim.x + threadIdx.x;
+    const int stride = gridDim.y * blockDim.x;
     const uint32_t *P0 = P_first + (s * parts) * NB;
     // carried-in stream: psi continues from the caller's accumulators and frame 0 has a phase difference too
     const unsigned char *sin = state_in ? state_in + s * slot_stride : nullptr;
@@ -352,37 +362,35 @@ __global__ void split_states_kernel(PvDev d, CTables tb, int parts, const PvSegm
     const unsigned long long *psi_in = sin ? reinterpret_cast<const unsigned long long *>(sin + 8 + ((NB * 4 + 7) / 8) * 8) : nullptr;
     if (sin) {      // part 0 starts from the caller's state as it is
         unsigned char *dst = slots + (long long)segs[s * parts].state_idx * slot_stride;
-        for (long long i = threadIdx.x; i < slot_stride / 4; i += blockDim.x)
-            reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(sin)[i];
+        for (long long w = i; w < slot_stride / 4; w += stride)
+            reinterpret_cast<uint32_t *>(dst)[w] = reinterpret_cast<const uint32_t *>(sin)[w];
     }
+    const bool owns_psi = i < V * NB;
+    const int v = owns_psi ? i / NB : 0;
+    const int lo = owns_psi ? tb.a_lo[i] : 1, hi = owns_psi ? tb.a_hi[i] : 0;
+    const bool src = owns_psi && lo <= hi;
+    const unsigned long long base = src ? (cont ? psi_in[i] : ((unsigned long long)P0[hi] << 32)) : 0ull;
+    const unsigned long long nomS = src ? tb.nomS[i] : 0ull;
+    const long long Rq = (long long)tb.Rq[v];
+    long long run = 0;                       // sum_{q<p} S_q[hi]
     for (int p = 0; p < parts; p++) {
         const long long gidx = s * parts + p;
         const PvSegment seg = segs[gidx];
         if (seg.carry_in && p > 0) {
-            for (int b = threadIdx.x; b < NB; b += blockDim.x) pre[b] = run[b] - H[gidx * NB + b];
-            __syncthreads();
             unsigned char *st = slots + (long long)seg.state_idx * slot_stride;
             uint32_t *hdr = reinterpret_cast<uint32_t *>(st);
             uint32_t *stP = hdr + 2;
             unsigned long long *psi = reinterpret_cast<unsigned long long *>(st + 8 + ((NB * 4 + 7) / 8) * 8);
             float *acc = reinterpret_cast<float *>(psi + (size_t)V * NB);
-            if (threadIdx.x == 0) { hdr[0] = 1u; hdr[1] = 0u; }
-            for (int b = threadIdx.x; b < NB; b += blockDim.x) stP[b] = P_first[gidx * NB + b];
-            const unsigned long long nb4 = (unsigned long long)(cont ? seg.k_begin : seg.k_begin - 1);
-            for (int i = threadIdx.x; i < V * NB; i += blockDim.x) {
-                const int v = i / NB;
-                const int lo = tb.a_lo[i], hi = tb.a_hi[i];
-                unsigned long long ps = 0;
-                if (lo <= hi)
-                    ps = (cont ? psi_in[i] : ((unsigned long long)P0[hi] << 32)) + nb4 * tb.nomS[i] +
-                         (unsigned long long)(pre[hi] * (long long)tb.Rq[v]);
-                psi[i] = ps;
+            if (i == 0) { hdr[0] = 1u; hdr[1] = 0u; }
+            if (i < NB) stP[i] = P_first[gidx * NB + i];
+            if (owns_psi) {
+                const unsigned long long nb4 = (unsigned long long)(cont ? seg.k_begin : seg.k_begin - 1);
+                psi[i] = src ? base + nb4 * nomS + (unsigned long long)((run - H[gidx * NB + hi]) * Rq) : 0ull;
             }
-            for (int i = threadIdx.x; i < V * N; i += blockDim.x) acc[i] = 0.f;
-            __syncthreads();
+            for (int w = i; w < V * N; w += stride) acc[w] = 0.f;
         }
-        for (int b = threadIdx.x; b < NB; b += blockDim.x) run[b] += S[gidx * NB + b];
-        __syncthreads();
+        if (src) run += S[gidx * NB + hi];
     }
 }
 
@@ -415,8 +423,9 @@ cudaError_t pv_launch_split_states(const PvDev &d, int64_t n_streams, int32_t pa
     if (n_streams <= 0) return cudaSuccess;
     PvFusedTables none;
     const CTables tb = make_ctables(d, none);
-    const size_t smem = sizeof(long long) * 2 * (size_t)(d.N / 2 + 1);
-    split_states_kernel<<<(unsigned)n_streams, 256, smem, st>>>(d, tb, parts, proc_segs, reinterpret_cast<const long long *>(S),
+    const int entries = std::max(d.V * (d.N / 2 + 1), 1);
+    const dim3 grid((unsigned)n_streams, (unsigned)((entries + 255) / 256));
+    split_states_kernel<<<grid, 256, 0, st>>>(d, tb, parts, proc_segs, reinterpret_cast<const long long *>(S),
                                                                reinterpret_cast<const long long *>(H), P_first, slots, slot_stride,
                                                                state_in);
     return cudaGetLastError();
@@ -431,6 +440,55 @@ cudaError_t pv_launch_state_from_carry(const PvDev &d, const PvFusedTables &t, i
     state_from_carry_kernel<<<(unsigned)n_streams, 256, 0, st>>>(d, tb, n_streams, P_first,
                                                                 reinterpret_cast<const long long *>(sumD), n_before, P_prev,
                                                                 reinterpret_cast<unsigned char *>(state), state_stride);
+    return cudaGetLastError();
+}
+
+// ---- frame-range sharding across ranks (pv_shard_begin / pv_shard_finish): the carry record of one stream is
+// [nb int64 sums | nb uint32 phase of frame 0 (rank 0 only), packed into (nb+1)/2 int64] ----
+__global__ void shard_pack_kernel(int nb, int elems, const long long *total, const long long *minus, const uint32_t *P0,
+                                  long long *carry)
+{
+    const long long s = blockIdx.x;
+    long long *rec = carry + s * elems;
+    uint32_t *recP = reinterpret_cast<uint32_t *>(rec + nb);
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        rec[b] = (total ? total[s * nb + b] : 0) - (minus ? minus[s * nb + b] : 0);
+        recP[b] = P0 ? P0[s * nb + b] : 0u;
+    }
+    if (threadIdx.x == 0 && (nb & 1)) recP[nb] = 0u;
+}
+
+// prefix[s][b] = sum_{r < rank} carry_all[r][s].sums[b] - minus[s][b];  P0[s][b] = carry_all[0][s].P0[b]
+__global__ void shard_prefix_kernel(int nb, int elems, int rank, long long n_streams, const long long *carry_all,
+                                    const long long *minus, long long *prefix, uint32_t *P0)
+{
+    const long long s = blockIdx.x;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        long long acc = minus ? -minus[s * nb + b] : 0;
+        for (int r = 0; r < rank; r++) acc += carry_all[((long long)r * n_streams + s) * elems + b];
+        prefix[s * nb + b] = acc;
+        P0[s * nb + b] = reinterpret_cast<const uint32_t *>(carry_all + s * elems + nb)[b];
+    }
+}
+
+cudaError_t pv_launch_shard_pack(int nb, int elems, int64_t n_streams, const int64_t *total, const int64_t *minus,
+                                 const uint32_t *P0, int64_t *carry, cudaStream_t st)
+{
+    if (n_streams <= 0) return cudaSuccess;
+    shard_pack_kernel<<<(unsigned)n_streams, 256, 0, st>>>(nb, elems, reinterpret_cast<const long long *>(total),
+                                                          reinterpret_cast<const long long *>(minus), P0,
+                                                          reinterpret_cast<long long *>(carry));
+    return cudaGetLastError();
+}
+
+cudaError_t pv_launch_shard_prefix(int nb, int elems, int rank, int64_t n_streams, const int64_t *carry_all,
+                                   const int64_t *minus, int64_t *prefix, uint32_t *P0, cudaStream_t st)
+{
+    if (n_streams <= 0) return cudaSuccess;
+    shard_prefix_kernel<<<(unsigned)n_streams, 256, 0, st>>>(nb, elems, rank, (long long)n_streams,
+                                                            reinterpret_cast<const long long *>(carry_all),
+                                                            reinterpret_cast<const long long *>(minus),
+                                                            reinterpret_cast<long long *>(prefix), P0);
     return cudaGetLastError();
 }
 

@@ -105,6 +105,11 @@ cudaError_t pv_launch_split_states(const PvDev &d, int64_t n_streams, int32_t pa
 // sumD[s] = sum over the parts of stream s of S; P_first from part 0; P_last from the last part.
 cudaError_t pv_launch_reduce_parts(int nb, int64_t n_streams, int32_t parts, const int64_t *S, const uint32_t *Pf,
                                    const uint32_t *Pl, int64_t *sumD, uint32_t *P_first, uint32_t *P_last, cudaStream_t st);
+// frame-range sharding across ranks: pack / unpack of the per-stream carry record (pv_shard_begin / pv_shard_finish)
+cudaError_t pv_launch_shard_pack(int nb, int elems, int64_t n_streams, const int64_t *total, const int64_t *minus,
+                                 const uint32_t *P0, int64_t *carry, cudaStream_t st);
+cudaError_t pv_launch_shard_prefix(int nb, int elems, int rank, int64_t n_streams, const int64_t *carry_all,
+                                   const int64_t *minus, int64_t *prefix, uint32_t *P0, cudaStream_t st);
 // generic (any window) fused corrected path; a.state must be non-null (caller's or library scratch)
 cudaError_t pv_launch_corrected_generic(const PvDev &d, const PvProcessArgs &a, cudaStream_t st);
 

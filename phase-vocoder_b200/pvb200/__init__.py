@@ -29,11 +29,17 @@ EXPORTS = [
     "pv_corrected_aggregate", "pv_corrected_state_from_carry", "pv_launch_count", "pv_timing_enable", "pv_timing_read",
     "pv_rt_open", "pv_rt_close", "pv_rt_reset", "pv_rt_latency_samples", "pv_rt_input", "pv_rt_output", "pv_rt_step",
     "pv_rt_callback", "pv_fft_batch", "pv_corrected_split_aggregate",
+    "pv_shard_plan_frames", "pv_shard_carry_elems", "pv_shard_begin", "pv_shard_finish",
 ]
 
 
 class PvError(RuntimeError):
     pass
+
+
+class ShardPlanC(C.Structure):
+    """pv_shard_plan (include/pv_b200.h)."""
+    _fields_ = [("k0", C.c_int64), ("k1", C.c_int64), ("ks", C.c_int64), ("halo", C.c_int64)]
 
 
 class Params(C.Structure):
@@ -94,6 +100,11 @@ def load():
     L.pv_rt_callback.argtypes = [vp, vp, vp, C.c_uint32]
     L.pv_fft_batch.argtypes = [vp, vp, vp, i32, i64, i32, vp]
     L.pv_corrected_split_aggregate.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, i32, vp, vp]
+    L.pv_shard_plan_frames.argtypes = [vp, i64, i32, i32, C.POINTER(ShardPlanC)]
+    L.pv_shard_carry_elems.argtypes = [vp]
+    L.pv_shard_carry_elems.restype = C.c_size_t
+    L.pv_shard_begin.argtypes = [vp, vp, i64, i64, i64, i64, i64, i32, i32, vp, vp]
+    L.pv_shard_finish.argtypes = [vp, vp, i64, i64, i64, i64, i64, i64, i32, i32, vp, vp, i64, i64, vp]
     _lib = L
     return L
 
@@ -235,6 +246,39 @@ class PhaseVocoder:
         D = torch.zeros((n_frames, N // 2 + 1), dtype=torch.int32, device=x.device)
         D[1:] = sumD.to(torch.int32)
         return D
+
+    # ---- frame-range sharding across ranks, behind the C ABI (pv_shard_begin / pv_shard_finish) ----
+    def shard_plan(self, n_frames, world, rank):
+        p = ShardPlanC()
+        _check(load().pv_shard_plan_frames(self._h, n_frames, world, rank, C.byref(p)))
+        return p
+
+    def shard_carry_elems(self):
+        return load().pv_shard_carry_elems(self._h)
+
+    def shard_begin(self, x, first_frame, n_frames, world, rank, n_in=None):
+        """Phase 1 of a sharded run: x [S, n] holds the stream(s) from sample first_frame*hop_in on.  Returns this
+        rank's carry record [S, elems] int64 (device) for the all-gather."""
+        import torch
+        S = x.shape[0]
+        n_in = x.shape[1] if n_in is None else n_in
+        carry = torch.empty((S, self.shard_carry_elems()), dtype=torch.int64, device=x.device)
+        _check(load().pv_shard_begin(self._h, _ptr(x), first_frame, S, x.stride(0), n_in, n_frames, world, rank, _ptr(carry),
+                                     _cuda_stream()))
+        return carry
+
+    def shard_finish(self, x, first_frame, n_frames, world, rank, carry_all, n_analysed=None, n_in=None):
+        """Phase 2: carry_all [world, S, elems] int64 (device) as gathered.  Returns out [S, V, (k1-k0)*Hs]."""
+        import torch
+        S = x.shape[0]
+        n_in = x.shape[1] if n_in is None else n_in
+        p = self.shard_plan(n_frames, world, rank)
+        out = torch.empty((S, self.n_voices, max(0, p.k1 - p.k0) * self.outHopSize), dtype=torch.float32, device=x.device)
+        na = n_frames if n_analysed is None else n_analysed
+        _check(load().pv_shard_finish(self._h, _ptr(x), first_frame, S, x.stride(0), n_in, na, n_frames, world, rank,
+                                      _ptr(carry_all), _ptr(out), out.stride(0) if S else 0, out.stride(1) if S else 0,
+                                      _cuda_stream()))
+        return out
 
     def split_aggregate(self, x, n_frames, state=None, skip=0, n_in=None):
         """The analysis pass of process(x, n_frames, state=state, flags=CARRY_IN if state is not None, skip=skip) on

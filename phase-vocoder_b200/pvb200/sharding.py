@@ -66,6 +66,19 @@ class TorchComm:
         return out
 
 
+def process_sharded_capi(pv, x, first_frame, n_frames, comm, n_analysed=None):
+    """The same through the C ABI (pv_shard_begin / pv_shard_finish, include/pv_b200.h): the library does the
+    analysis, the carry bookkeeping, the state rebuild and the processing; this function only issues the ONE
+    collective in between -- what a C caller does with ncclAllGather.  x [S, n]: the stream(s) from sample
+    first_frame*hop_in on (a rank needs its range, the overlap-add halo and one more frame; rank 0 needs frame 0).
+    Returns (out [S, V, (k1-k0)*Hs], plan).  Both modes; compat contributes an all-zero record."""
+    import torch
+    carry = pv.shard_begin(x, first_frame, n_frames, comm.world, comm.rank)
+    gathered = torch.stack(comm.all_gather(carry)) if comm.world > 1 else carry[None]
+    out = pv.shard_finish(x, first_frame, n_frames, comm.world, comm.rank, gathered.contiguous(), n_analysed=n_analysed)
+    return out, pv.shard_plan(n_frames, comm.world, comm.rank)
+
+
 def process_compat_sharded(engine, x, n_frames, n_analysed, comm, Ha, Hs, N):
     """x: the rank's view of the stream(s) as a [S, n] tensor starting at sample ks*Ha.  Returns this
     rank's output block [S, 1, (k1-k0)*Hs] and its plan."""

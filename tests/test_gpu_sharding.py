@@ -122,3 +122,35 @@ def test_split_aggregate_matches_aggregate_and_reuse_changes_nothing():
     assert torch.equal(c, d) and torch.equal(c[:, :, halo * H:], b[:, :, (k + halo) * H:])
     # the flag alone (nothing to reuse) is harmless
     assert torch.equal(pv.process(x, nf, flags=pvb200.REUSE_AGGREGATE), b)
+
+
+@pytest.mark.parametrize("mode,N,Ha,Hs,betas,nf,world,S", [
+    ("corrected", 2048, 512, 512, [1.4983071], 203, 4, 1), ("corrected", 4096, 1024, 1024, [1.4983071], 3000, 4, 2),   # C5 shape, stereo
+    ("corrected", 256, 64, 64, [1.0, 1.5, 2.0], 1001, 8, 1), ("corrected", 1024, 256, 512, [1.0], 150, 3, 2),
+    ("corrected", 512, 128, 128, [1.26], 7, 4, 1),                                                # ranges shorter than the halo, empty ranks
+    ("compat", 2048, 512, 512, [1.0], 203, 4, 2), ("compat", 4096, 1024, 1024, [1.0], 2000, 2, 2)])
+def test_sharding_through_the_c_abi_is_bit_exact(mode, N, Ha, Hs, betas, nf, world, S):
+    """pv_shard_begin -> ONE all-gather of the carry records -> pv_shard_finish (include/pv_b200.h): the library does the
+    analysis, the bookkeeping and the state rebuild; the caller only moves pv_shard_carry_elems() int64 per stream.
+    Every rank sees only its own part of the input (range + halo + one frame), and the concatenated ranges equal the
+    single-call result bit for bit."""
+    corrected = mode == "corrected"
+    x = torch.from_numpy(np.stack([multitone(N + nf * Ha, seed=8 + s, noise=1e-3) for s in range(S)])).cuda()
+    mk = lambda: pvb200.PhaseVocoder(N, hop_in=Ha, hop_out=Hs, mode=pvb200.MODE_CORRECTED if corrected else pvb200.MODE_COMPAT,
+                                     window_type=pvb200.WIN_HANN_PERIODIC if corrected else pvb200.WIN_HAMMING, pitch=tuple(betas))
+    n_an = nf if corrected else nf - 2
+    full = mk().process(x, nf, n_analysed=n_an).cpu().numpy()
+
+    def fn(comm):
+        pvr = mk()
+        p = pvr.shard_plan(nf, comm.world, comm.rank)
+        first = max(0, p.ks - 1)                                   # the rank's own view: nothing before its halo
+        last = min(x.shape[1], (max(p.k1, 1) - 1) * Ha + N)        # ... and nothing after its last frame
+        xr = x[:, first * Ha:last].contiguous() if p.k1 > p.k0 else x[:, :N].contiguous()
+        assert pvr.shard_carry_elems() == (N // 2 + 1) + (N // 2 + 2) // 2
+        out, _ = sharding.process_sharded_capi(pvr, xr, first if p.k1 > p.k0 else 0, nf, comm, n_analysed=n_an)
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+
+    got = np.concatenate(_run_ranks(world, fn), axis=2)
+    assert np.array_equal(got, full)

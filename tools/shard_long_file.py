@@ -4,10 +4,11 @@ box with torch.distributed / NCCL.  Launch:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 tools/shard_long_file.py
 
-Every rank holds the whole input (a real deployment would hold its range + halo), processes its frame range
-of both channels with the C ABI engine and exchanges ONLY the per-bin int64 phase carry (one all-gather of
-(N/2+1) x 8 bytes per channel).  Rank 0 then checks the concatenated result bit for bit against a single-GPU
-run of the same file and prints a JSON line with the timing (max over ranks, CUDA events)."""
+Every rank generates the whole input (so that rank 0 can check the result) but hands the library only ITS view: its
+frame range, the overlap-add halo and one more frame.  The sharding itself runs behind the C ABI (pv_shard_begin ->
+ONE all-gather of pv_shard_carry_elems() int64 per channel -> pv_shard_finish; include/pv_b200.h).  Rank 0 then checks
+the concatenated result bit for bit against a single-GPU run of the same file and prints a JSON line with the timing
+(max over ranks, CUDA events)."""
 import json
 import os
 import sys
@@ -43,12 +44,14 @@ def main():
     pv = mk()
     comm = sharding.TorchComm()
 
+    p0 = pv.shard_plan(nf, world, rank)
+    first = max(0, p0.ks - 1)
+    xr = x[:, first * H:min(n, (max(p0.k1, 1) - 1) * H + N)].contiguous() if p0.k1 > p0.k0 else x[:, :N].contiguous()
+    first = first if p0.k1 > p0.k0 else 0
+
     def run_sharded():
-        # both channels in one call: they are independent streams with the same frame ranges
-        if corrected:
-            return sharding.process_corrected_sharded(pv, lambda k: x[:, k * H:], nf, comm, H, H, N)
-        p = sharding.plan(nf, world, rank, N, H)
-        return sharding.process_compat_sharded(pv, x[:, p.ks * H:], nf, nf, comm, H, H, N)
+        # both channels in one call: they are independent streams cut at the same frames
+        return sharding.process_sharded_capi(pv, xr, first, nf, comm)
 
     for _ in range(2):
         out, p = run_sharded()
@@ -72,13 +75,22 @@ def main():
     dist.gather(pad, parts, dst=0)
     if rank == 0:
         got = torch.cat(parts, 2)[:, :, :nf * H]
-        ref = mk().process(x, nf)
+        one = mk()
+        ref = one.process(x, nf)
         torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(reps):
+            one.process(x, nf, out=ref)
+        t1.record()
+        torch.cuda.synchronize()
+        single_ms = t0.elapsed_time(t1) / reps
         exact = bool(torch.equal(got, ref))
         print(json.dumps({"config": "C5 long file", "mode": mode, "window": N, "hop": H, "channels": 2, "frames_per_channel": nf,
                           "audio_seconds": nf * H / fs, "n_gpus": world, "ms": float(ms.item()),
                           "frames_per_s": 2 * nf / (float(ms.item()) * 1e-3),
-                          "exchange": "phase carry: one all_gather of (N/2+1) int64 per channel" if corrected else "none (input halo recomputed)",
+                          "exchange": f"one all_gather of {pv.shard_carry_elems()} int64 per channel and rank (C ABI: pv_shard_begin/finish)" if corrected else "none (input halo recomputed)",
+                          "single_gpu_ms": single_ms, "speedup_vs_single_gpu": single_ms / float(ms.item()),
                           "bit_identical_to_single_gpu": exact}), flush=True)
     dist.barrier()
     dist.destroy_process_group()
