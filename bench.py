@@ -454,6 +454,29 @@ def run_ours(args):
                "host_cpus_bound": (len(numa) if numa else None)}
         # keep a checksum so that the D2H result is actually consumed
         e2e["checksum"] = float(oh[0, 0, :4096].double().abs().sum())
+        # the ceiling of this number on this box: the SAME bytes copied in both directions at once (two streams, whole
+        # buffers, no kernel), on all ranks at the same time
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def copies():
+            with torch.cuda.stream(s_in):
+                x.copy_(xh, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                oh.copy_(out, non_blocking=True)
+        copies()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            copies()
+        barrier()
+        dtc = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dtc, op=dist.ReduceOp.MAX)
+        ceil_v = frames_step * n_e2e / float(dtc.item())
+        e2e["copy_ceiling"] = {"value": ceil_v, "unit": "frames/s", "frac_achieved": e2e["value"] / ceil_v,
+                               "gb_per_s_each_direction_all_gpus": S * n_in * 4 * world * n_e2e / float(dtc.item()) / 1e9,
+                               "method": "pinned host buffers of this run copied H2D and D2H concurrently (two streams, no kernel), all "
+                                         "ranks at once, same barriers; what pv_process_host could reach if compute were free"}
         del oh
         # the same call with 16-bit PCM host buffers (what a WAV file holds): AudioFile's int16<->float rules run
         # on the device, half the bytes cross PCIe
