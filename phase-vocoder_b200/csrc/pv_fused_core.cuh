@@ -156,6 +156,44 @@ PV_DEV void cp_async16(float *dst, const float *src, int src_bytes)
 }
 #endif
 
+// ---- bulk asynchronous copy of one input hop (the TMA engine's 1-D form: cp.async.bulk + mbarrier) ----
+// ONE elected thread moves the whole new hop of the next frame into the ring; completion is counted in bytes on an
+// mbarrier in shared memory that every consumer waits on (phase parity = frame parity).  Replaces T x 16-byte
+// cp.async (LDGSTS) copies and their per-thread address / bounds arithmetic.
+#if !defined(PV_HOST_EMUL)
+PV_DEV void mbar_init(unsigned long long *mbar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(mbar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+PV_DEV void bulk_load_hop(float *dst, const float *src, unsigned bytes, unsigned long long *mbar)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst), m = (unsigned)__cvta_generic_to_shared(mbar);
+    // the slots about to be overwritten were last read through the generic proxy: order those reads before the async write
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src), "r"(bytes),
+                 "r"(m) : "memory");
+}
+PV_DEV void mbar_wait(unsigned long long *mbar, unsigned parity)
+{
+    const unsigned m = (unsigned)__cvta_generic_to_shared(mbar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(m), "r"(parity) : "memory");
+}
+#else
+PV_DEV void mbar_init(unsigned long long *, unsigned) {}
+PV_DEV void bulk_load_hop(float *dst, const float *src, unsigned bytes, unsigned long long *) { for (unsigned j = 0; j < bytes / 4; j++) dst[j] = src[j]; }
+PV_DEV void mbar_wait(unsigned long long *, unsigned) {}
+#endif
+
 // Cooperative refill with 16-byte pieces: samples [lo, N) (frame coordinates, multiples of 4) of the frame at
 // io.base, spread over T threads.  Issue after a barrier that follows the last read of the replaced samples;
 // complete with cp_async_wait_all() + a barrier before the first read of the new ones.

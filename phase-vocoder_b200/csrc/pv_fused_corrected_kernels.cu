@@ -30,7 +30,7 @@ struct CLaunch {
     static size_t group_bytes(int V)
     {
         return (size_t)(C::BUF_A + C::BUF_B) * sizeof(float2) + (size_t)V * ((C::NB + 1) & ~1) * 8 +
-               (size_t)((C::NB + 3) & ~3) * 4 * 2 + (size_t)V * C::N * 4 + (size_t)C::N * 4;
+               (size_t)((C::NB + 3) & ~3) * 4 * 2 + (size_t)V * C::N * 4 + (size_t)C::N * 4 + 16;     // + the ring's mbarrier
     }
 };
 
@@ -68,6 +68,10 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
     int32_t *dS = reinterpret_cast<int32_t *>(magS + ((NB + 3) & ~3));
     float *acc = reinterpret_cast<float *>(dS + ((NB + 3) & ~3));
     float *ring = use_ring ? acc + (size_t)V * N : nullptr;
+    // ring mode 3: the new hop of every frame arrives as ONE bulk asynchronous copy (cp.async.bulk + mbarrier)
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(base + group_bytes - 16);
+    unsigned mbar_phase = 0;
+    bool bulk_pending = false;
     unsigned long long *psi_v0 = psi;      // voice stride in psi is NB (kernel body) -> keep packed
     (void)psi_v0;
 
@@ -127,9 +131,10 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
             acc[i] = (cin && ii + Hs < N) ? st_acc[i + Hs] : 0.f;
         }
     }
+    if (use_ring == 3 && tid == 0) mbar_init(mbar, 1);
     if (use_ring) {
         FrameIO io0{in, a.n_in, seg.k_begin * (long long)d.Ha, true, true};
-        if (use_ring == 2) ring_prefetch_coop16<N, T>(tid, io0, ring, 0);
+        if (use_ring >= 2) ring_prefetch_coop16<N, T>(tid, io0, ring, 0);
         else ring_prefetch_coop<N, T>(tid, io0, ring, 0);
         cp_async_wait_all();
     }
@@ -162,7 +167,11 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
         auto hook = [&]() {
             if (use_ring && k + 1 < seg.k_end) {
                 FrameIO nx{in, a.n_in, (k + 1) * (long long)d.Ha, true, true};
-                if (use_ring == 2) ring_prefetch_coop16<N, T>(tid, nx, ring, N - d.Ha);
+                const long long g0 = nx.base + (N - d.Ha);                // first new sample of the next frame
+                if (use_ring == 3 && g0 + d.Ha <= a.n_in) {              // whole hop inside the stream: one bulk copy
+                    if (tid == 0) bulk_load_hop(ring + (int)(g0 & (N - 1)), in + g0, (unsigned)d.Ha * 4u, mbar);
+                    bulk_pending = true;
+                } else if (use_ring >= 2) ring_prefetch_coop16<N, T>(tid, nx, ring, N - d.Ha);
                 else ring_prefetch_coop<N, T>(tid, nx, ring, N - d.Ha);
             }
             if (!agg_mode && k > seg.k_begin) emit(k - 1, (pos0 - Hs) & (N - 1), PV_ZERO_ON_EMIT);
@@ -173,6 +182,11 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
         if (agg_mode && use_ring) {        // analysis only: no inverse passes whose last barrier would complete the refill
             cp_async_wait_all();
             sync();
+        }
+        if (bulk_pending) {                // every consumer observes the completion itself: no barrier needed for visibility
+            mbar_wait(mbar, mbar_phase);
+            mbar_phase ^= 1u;
+            bulk_pending = false;
         }
         pos0 = (pos0 + Hs) & (N - 1);
     }
@@ -239,7 +253,10 @@ cudaError_t claunch(const PvDev &d, const CTables &tb, const PvProcessArgs &a, c
                         ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
     // 2: 16-byte cp.async.cg pieces (L1 bypass) when rows and hops are 16-byte aligned, 1: 8-byte pieces
     const bool al16 = in_ok && (d.Ha % 4 == 0) && (a.in_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0);
-    const int ring = (in_ok && d.Ha <= d.N && !no_ring) ? (al16 ? 2 : 1) : 0;
+    // 3: bulk asynchronous hop copies (needs the hop to divide the window so that a hop never wraps in the ring)
+    static const bool ldgsts = getenv("PV_RING_LDGSTS") != nullptr;       // A/B switch, read once
+    int ring = (in_ok && d.Ha <= d.N && !no_ring) ? (al16 ? 2 : 1) : 0;
+    if (ring == 2 && !ldgsts && d.N % d.Ha == 0) ring = 3;
     const size_t gb = L::group_bytes(tb.V) - (ring ? 0 : (size_t)d.N * 4);
     const size_t smem = gb * L::G;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -34,7 +34,7 @@ struct Launch {
     // 81 KB) -> 2
     static constexpr int MINB_RING = LOG2N >= 12 ? 2 : 5;
     // exchange buffers + OLA accumulator (+ private input ring)
-    static constexpr size_t smem(bool ring) { return (size_t)G * (GROUP_F2 * sizeof(float2) + (ring ? 2 : 1) * S::N * sizeof(float)); }
+    static constexpr size_t smem(bool ring) { return (size_t)G * (GROUP_F2 * sizeof(float2) + (ring ? 2 : 1) * S::N * sizeof(float) + 16); }   // + mbarrier
 };
 
 template <int T, int G>
@@ -50,7 +50,8 @@ struct GroupSync {
 };
 
 // RING: 0 = inputs straight from global memory, 1 = private 8-byte cp.async ring (each thread copies exactly
-// the samples it consumes, no barrier), 2 = cooperative 16-byte cp.async.cg ring (L1 bypass)
+// the samples it consumes, no barrier), 2 = cooperative 16-byte cp.async.cg ring (L1 bypass), 3 = the new hop of every frame
+// as ONE bulk asynchronous copy (cp.async.bulk + mbarrier, the TMA engine's 1-D form) issued by one elected thread
 template <int LOG2N, int MINB, int RING>
 __global__ void __launch_bounds__(Launch<LOG2N>::THREADS, MINB)
 compat_fused_kernel(PvDev d, Tables tb, PvProcessArgs a, int vec_in_ok, int vec_out_ok)
@@ -68,6 +69,9 @@ compat_fused_kernel(PvDev d, Tables tb, PvProcessArgs a, int vec_in_ok, int vec_
     float *fbase = reinterpret_cast<float *>(reinterpret_cast<float2 *>(smem_raw) + (size_t)G * L::GROUP_F2);
     float *acc = fbase + (size_t)g * N;
     float *ring = RING ? fbase + (size_t)(G + g) * N : nullptr;
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(fbase + (size_t)(RING ? 2 : 1) * G * N) + 2 * g;
+    unsigned mbar_phase = 0;
+    bool bulk_pending = false;
 
     GroupSync<T, G> sync{g, T >= 32 ? 0xffffffffu : (((1u << (T & 31)) - 1u) << ((threadIdx.x & 31) / T * T))};
 
@@ -103,6 +107,7 @@ compat_fused_kernel(PvDev d, Tables tb, PvProcessArgs a, int vec_in_ok, int vec_
     };
 
     const long long k_an_end = seg.k_end < a.n_analysed ? seg.k_end : a.n_analysed;   // frames >= this are zero spectra
+    if (RING == 3 && tid == 0) mbar_init(mbar, 1);
     if (RING && seg.k_begin < k_an_end) {
         FrameIO io0{in, a.n_in, seg.k_begin * (long long)d.Ha, true, true};
         if (RING == 1) ring_prefetch<LOG2N>(tid, io0, ring, 0);
@@ -123,14 +128,23 @@ compat_fused_kernel(PvDev d, Tables tb, PvProcessArgs a, int vec_in_ok, int vec_
         auto hook = [&]() {
             if (RING && k + 1 < k_an_end) {
                 FrameIO nx{in, a.n_in, (k + 1) * (long long)d.Ha, true, true};
+                const long long g0 = nx.base + (N - d.Ha);            // first new sample of the next frame
                 if (RING == 1) ring_prefetch<LOG2N>(tid, nx, ring, N - d.Ha);
-                else ring_prefetch_coop16<N, T>(tid, nx, ring, N - d.Ha);
+                else if (RING == 3 && g0 + d.Ha <= a.n_in) {           // whole hop inside the stream: one bulk copy
+                    if (tid == 0) bulk_load_hop(ring + (int)(g0 & (N - 1)), in + g0, (unsigned)d.Ha * 4u, mbar);
+                    bulk_pending = true;
+                } else ring_prefetch_coop16<N, T>(tid, nx, ring, N - d.Ha);
             }
             if (k > seg.k_begin) emit(k - 1, (pos0 - Hs) & (N - 1), PV_ZERO_ON_EMIT);
         };
         if (RING == 1) cp_async_wait_all();
         frame_compat<LOG2N, TWREG>(tid, io, tb, tt, nan_compat, ring, bufA, bufB, acc, pos0, Hs, sync, hook,
-                                   [&]() { if (RING == 2) cp_async_wait_all(); });
+                                   [&]() { if (RING >= 2) cp_async_wait_all(); });
+        if (RING == 3 && bulk_pending) {      // every consumer observes the completion itself
+            mbar_wait(mbar, mbar_phase);
+            mbar_phase ^= 1u;
+            bulk_pending = false;
+        }
         pos0 = (pos0 + Hs) & (N - 1);
     }
     sync();
@@ -169,6 +183,11 @@ cudaError_t launch(const PvDev &d, const Tables &tb, const PvProcessArgs &a, int
     const bool al16 = vec_in_ok && d.Ha <= d.N && (d.Ha % 4 == 0) && (a.in_stride % 4 == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0);
     // 5 CTAs/SM: with exchange 2 in place a group needs 40.7 KB of shared memory at N = 2048 and 96 registers
+    // Bulk asynchronous hop copies (ring mode 3) where they measured faster: window 4096 (+1.3 %).  At windows <= 2048 this
+    // kernel runs five CTAs per SM on 96 registers and the mbarrier bookkeeping spills (-3 %), so the 16-byte cp.async ring
+    // stays; PV_RING_BULK / PV_RING_LDGSTS force either for the A/B (read once).
+    static const bool ldgsts = getenv("PV_RING_LDGSTS") != nullptr, force_bulk = getenv("PV_RING_BULK") != nullptr;
+    if (al16 && !ldgsts && (LOG2N >= 12 || force_bulk) && d.N % d.Ha == 0) return launch2<LOG2N, Launch<LOG2N>::MINB_RING, 3>(d, tb, a, vec_in_ok, vec_out_ok, st);
     if (al16) return launch2<LOG2N, Launch<LOG2N>::MINB_RING, 2>(d, tb, a, vec_in_ok, vec_out_ok, st);
     if (ring_ok<LOG2N>(d, vec_in_ok != 0)) return launch2<LOG2N, MINB, 1>(d, tb, a, vec_in_ok, vec_out_ok, st);
     return launch2<LOG2N, MINB, 0>(d, tb, a, vec_in_ok, vec_out_ok, st);
