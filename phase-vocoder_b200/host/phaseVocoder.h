@@ -24,6 +24,22 @@
 struct float2 { float x, y; };
 #endif
 
+// The reference's public stream fields (src/phaseVocoder.h:4, :31-32): plain g++ callers get the opaque runtime types.
+// Compiled by nvcc (as the reference's driver is) or with -DPV_SHIM_WITH_CUDART the three streams are really created;
+// a plain g++ build that does not link the CUDA runtime keeps them null.
+#if defined(__CUDACC__) || defined(PV_SHIM_WITH_CUDART)
+#include <cuda_runtime_api.h>
+#define PV_SHIM_HAS_CUDART 1
+#elif __has_include(<driver_types.h>)
+#include <driver_types.h>
+#else
+typedef struct CUstream_st* cudaStream_t;
+#endif
+#ifndef _CUFFT_H_
+typedef int cufftHandle;                                    // cufft.h: `typedef int cufftHandle;` -- no cuFFT is linked here
+#endif
+#define NUM_STREAMS 3                                       // src/phaseVocoder.h:4
+
 enum Effect { TIME_SHIFT = 't', PITCH_SHIFT = 'p' };       // src/phaseVocoder.h:5-8
 
 class PhaseVocoder {
@@ -51,17 +67,45 @@ class PhaseVocoder {
         win_.resize(samples);
         pv_window_table(h_, win_.data());
         imp = imp1 = win_.data();
+        for (int i = 0; i < NUM_STREAMS; i++) {              // src/phaseVocoder.h:113-115
+            streams[i] = nullptr;
+#ifdef PV_SHIM_HAS_CUDART
+            cudaStreamCreate(&streams[i]);
+#endif
+        }
     }
 
 public:
     float* imp = nullptr;       // window table (host copy; the device copy is owned by the engine)
     float* imp1 = nullptr;
+    // per-frame scratch of the reference's unfinished real-time path (src/phaseVocoder.h:18-22): never allocated by the
+    // four-argument constructor there either; kept so that code naming them compiles
+    float* curr_input = nullptr;
+    float* prev_input = nullptr;
+    float* prev_output = nullptr;
+    float2* prev_mag_phase = nullptr;
+    float2* curr_mag_phase = nullptr;
+    // src/phaseVocoder.h:23-24: the reference creates two cuFFT plans here and never uses them (kernel.cu makes its own
+    // per frame, :324, :363).  This engine has no cuFFT at all; the handles stay 0.
+    cufftHandle plan = 0;
+    cufftHandle ifft = 0;
     int hopSize;
     int nSamps;
     int R = 1;
     int N = 0;
     float timeScale = 1.f;
     int outHopSize;
+    int stream = 0;                                      // src/phaseVocoder.h:31
+    cudaStream_t streams[NUM_STREAMS];                   // :32, created in the constructor like the reference's (:113-115)
+
+    // src/phaseVocoder.h:118-126: round-robin stream getters (the reference never calls them; same arithmetic)
+    cudaStream_t* getStream()
+    {
+        cudaStream_t* out = &streams[stream++];
+        stream %= NUM_STREAMS;
+        return out;
+    }
+    cudaStream_t* getPrevStream() { return &streams[(stream + NUM_STREAMS - 1) % NUM_STREAMS]; }
 
     // src/phaseVocoder.h:46-78: periodic Hann, hop = samples/2
     explicit PhaseVocoder(int samples) : hopSize(samples / 2), nSamps(samples), outHopSize(samples / 2)
@@ -82,7 +126,14 @@ public:
             create(samples, hopSize, outHopSize, PV_MODE_COMPAT, PV_WIN_HAMMING, 1.f);
         }
     }
-    ~PhaseVocoder() { pv_destroy(h_); }
+    ~PhaseVocoder()
+    {
+#ifdef PV_SHIM_HAS_CUDART
+        for (int i = 0; i < NUM_STREAMS; i++)
+            if (streams[i]) cudaStreamDestroy(streams[i]);
+#endif
+        pv_destroy(h_);
+    }
     PhaseVocoder(const PhaseVocoder&) = delete;
     PhaseVocoder& operator=(const PhaseVocoder&) = delete;
 

@@ -190,3 +190,34 @@ def test_cli_reproduces_golden_head(golden, tmp_path):
     # frames 0..127 are identical to the full-file run; frame 128 here is the un-analysed last frame
     assert np.abs(got[:len(want) - 128] - want[:len(want) - 128]).max() <= 1
     assert not got[129 * 128:].any()
+
+
+@pytest.mark.gpu
+def test_cli_with_the_reference_audiofile_writes_the_same_file(golden_wav, tmp_path):
+    """North star: "WAV in and out via AudioFile".  oracle/_ref/pv_cli_audiofile is host/pv_cli.cpp compiled against the
+    reference's OWN, unmodified src/AudioFile.h (used exactly as src/main.cpp:128-143,309 uses it); the default build uses
+    the built-in codec.  Both must write byte-identical files -- 16-bit C1 input (440sine.wav slice, window 256, hop
+    divisor 4, compat and pitch x1.5) and 24-bit C2 input with a trailing chunk (MAT_ZO slice, window 2048, +7 semitones)."""
+    exe_af = os.path.join(ROOT, "oracle", "_ref", "pv_cli_audiofile")
+    if not os.path.exists(exe_af):
+        pytest.skip("oracle/_ref/pv_cli_audiofile not built (needs the reference checkout at build time)")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-o", CLI, os.path.join(LIBDIR, "host", "pv_cli.cpp"), "-L" + LIBDIR,
+                    "-lpv_b200", "-Wl,-rpath," + LIBDIR], check=True)
+    c1 = golden_wav["c1_raw"]                                              # int16 [2, n]
+    pcm = c1.T.astype("<i2").tobytes()
+    w16 = b"RIFF" + struct.pack("<i", 36 + len(pcm)) + b"WAVE" + b"fmt " + struct.pack(
+        "<ihhiihh", 16, 1, 2, 44100, 2 * 44100 * 2, 4, 16) + b"data" + struct.pack("<i", len(pcm)) + pcm
+    open(tmp_path / "c1.wav", "wb").write(w16)
+    open(tmp_path / "c2.wav", "wb").write(_wav24(golden_wav["c2_raw"], rate=44100))
+    runs = [("c1.wav", "t", ["--window", "256", "--hop-div", "4"]), ("c1.wav", "p", ["--window", "256", "--hop-div", "4", "--scale", "1.5"]),
+            ("c2.wav", "p", ["--window", "2048", "--hop-div", "4", "--scale", "1.4983071"])]
+    for i, (wav, eff, extra) in enumerate(runs):
+        outs = []
+        for exe, tag in ((CLI, "own"), (exe_af, "af")):
+            o = tmp_path / f"out{i}_{tag}.wav"
+            r = subprocess.run([exe, str(tmp_path / wav), eff, str(o)] + extra, capture_output=True, text=True)
+            assert r.returncode == 0, (exe, r.stdout, r.stderr)
+            outs.append(open(o, "rb").read())
+        assert outs[0] == outs[1], (wav, eff)
+        y, rate, bits = wo.decode_wav(outs[0])
+        assert y.shape[0] == 2 and rate == 44100 and bits == 16 and np.abs(y).max() > 0.01
