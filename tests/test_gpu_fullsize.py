@@ -10,11 +10,13 @@ Properties, all evaluated on the GPU over EVERY sample of the full-size result:
     fp32 -- out(2x) == 2 out(x) bit for bit (phases do not move, magnitudes double)
   * batch invariance: a stream inside the big batch == the same stream processed on its own, bit for bit
   * shift invariance (compat; frames are independent): out(x delayed by one hop) == out(x) delayed by one hop
-  * a sample of streams against the fp64 oracle on the first frames (tolerance 100 dB)."""
+  * a sample of streams against the fp64 oracle on the first frames (tolerance 100 dB; the +7 semitone output of the full-size
+    run itself, decision-aligned as in tests/aligned.py, and the identity run directly)."""
 import numpy as np
 import pytest
 
 import pv_oracle as po
+from aligned import aligned_parity
 from signals import snr_db
 
 torch = pytest.importorskip("torch")
@@ -72,8 +74,14 @@ def test_corrected_full_size(S, F, N, H):
     cf = 48
     win = po.window(po.WIN_HANN_PERIODIC, N)
     for s in (0, S - 1):
-        want, _ = po.process_corrected(x[s, :N + cf * H].cpu().numpy(), N, H, H, win, [1.0], cf)
+        xs = x[s, :N + cf * H].cpu().numpy()
+        want, _ = po.process_corrected(xs, N, H, H, win, [1.0], cf)
         assert snr_db(want[0], y[s, 0, :cf * H].cpu().numpy()) > 100
+        # the pitch-shifted output of the FULL-SIZE launch (not a re-run): its first cf frames depend only on the first
+        # cf frames of the input
+        D = pv.unwrap_decisions(x[s, :N + cf * H].contiguous(), cf).cpu().numpy()
+        r = aligned_parity(xs, N, H, H, win, [SEMI7], cf, D, out[s, :, :cf * H].cpu().numpy())
+        assert r["phase_ratio"] < 1.0 and r["frac"] < 1e-3 and min(r["aligned"]) > 100, r
 
 
 @pytest.mark.parametrize("S,F,N,H", [(1184, 860, 2048, 512), (2, 168750, 4096, 1024)])
