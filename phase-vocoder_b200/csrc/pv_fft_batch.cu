@@ -120,17 +120,27 @@ cudaError_t launch_n(const float2 *in, float2 *out, int64_t batch, const float2 
     const bool pipelined = aligned && (force ? force[0] == '1' : (LG_N >= 9 && n_tiles > 4 * (int64_t)g_sms));
     if (pipelined) {
         const size_t smem = work + sizeof(float2) * (size_t)G * n;
-        e = cudaFuncSetAttribute(fft_batch_pipelined_kernel<LG_N, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_batch_pipelined_kernel<LG_N, DIR>, threads, smem);
-        if (e != cudaSuccess) return e;
+        // attribute and occupancy are properties of this instantiation and launch shape: query once, not per call
+        static int per_sm = 0, per_sm_threads = 0;
+        static size_t per_sm_smem = 0;
+        if (per_sm == 0 || per_sm_threads != threads || per_sm_smem != smem) {
+            e = cudaFuncSetAttribute(fft_batch_pipelined_kernel<LG_N, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return e;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_batch_pipelined_kernel<LG_N, DIR>, threads, smem);
+            if (e != cudaSuccess) return e;
+            per_sm_threads = threads;
+            per_sm_smem = smem;
+        }
         const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)g_sms * std::max(1, per_sm));
         fft_batch_pipelined_kernel<LG_N, DIR><<<grid, threads, smem, st>>>(in, out, G, batch, tw);
         return cudaGetLastError();
     }
-    e = cudaFuncSetAttribute(fft_batch_kernel<LG_N, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    if (e != cudaSuccess) return e;
+    static bool attr_set = false;                     // once per instantiation (single-transform calls are latency-bound)
+    if (!attr_set) {
+        e = cudaFuncSetAttribute(fft_batch_kernel<LG_N, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
     fft_batch_kernel<LG_N, DIR><<<(unsigned)n_tiles, threads, work, st>>>(in, out, G, batch, tw);
     return cudaGetLastError();
 }

@@ -12,7 +12,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-R = sys.argv[1] if len(sys.argv) > 1 else "r01"
+R = sys.argv[1] if len(sys.argv) > 1 else "r02"
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 FRAMES = 1184 * 860
 
@@ -41,9 +41,17 @@ for mode, kern in (("corrected", "corrected_fused"), ("compat", "compat_fused"))
     traffic[mode] = {"bytes_per_launch": num(m, "dram__bytes_read.sum") + num(m, "dram__bytes_write.sum"),
                      "frames_per_launch": FRAMES,
                      "warp_instructions_per_frame": num(m, "smsp__inst_executed.sum") / FRAMES,
-                     "source": f"profiles/{R}_{mode}_fused_n2048.md",
+                     "source": f"profiles/{R}_{mode}_fused_n2048.md (one `ncu --set full` capture; constants, not measured in the bench run)",
                      "workload": "1184 streams x 860 frames, window 2048, hop 512"}
 json.dump(traffic, open(os.path.join(P, f"{R}_traffic.json"), "w"), indent=1)
+
+# window 4096 (C5's shape): summaries of the two stream kernels on one batch of 592 streams x 430 frames
+F4096 = 592 * 430
+for mode in ("compat", "corrected"):
+    rep = os.path.join(G, f"{R}_{mode}4096.ncu-rep")
+    if os.path.exists(rep):
+        with open(os.path.join(P, f"{R}_{mode}_fused_n4096.md"), "w") as f:
+            subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep, str(F4096)], stdout=f, check=True)
 
 # launch list
 rows = [r for r in csv.reader(open(os.path.join(G, f"{R}_launches.csv"))) if len(r) > 10]
@@ -69,8 +77,12 @@ for n in ("bench.json", "bench_reference.json", "bench_under_profile_config.json
 # SASS of the two headline kernels
 so = os.path.join(ROOT, "phase-vocoder_b200", "libpv_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-for mode, key in (("corrected", "corrected_fused_kernelILi11ELi4"), ("compat", "compat_fused_kernelILi11ELi5ELi2")):
+for name, key in (("corrected_fused_n2048", "corrected_fused_kernelILi11ELi4"), ("compat_fused_n2048", "compat_fused_kernelILi11ELi5ELi2"),
+                  ("corrected_fused_n4096", "corrected_fused_kernelILi12ELi2"), ("compat_fused_n4096", "compat_fused_kernelILi12ELi2ELi3")):
     parts = sass.split("\t\tFunction : ")
     body = [p for p in parts if p.startswith("_Z") and key in p.split("\n")[0]]
-    open(os.path.join(P, f"{R}_sass_{mode}_fused_n2048.txt"), "w").write("Function : " + body[0] if body else "not found\n")
+    open(os.path.join(P, f"{R}_sass_{name}.txt"), "w").write("Function : " + body[0] if body else "not found\n")
+for n in ("4096_rates.txt",):
+    if os.path.exists(os.path.join(G, f"{R}_{n}")):
+        shutil.copy(os.path.join(G, f"{R}_{n}"), os.path.join(P, f"{R}_{n}"))
 print(json.dumps(traffic, indent=1))
