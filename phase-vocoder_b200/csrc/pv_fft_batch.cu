@@ -9,6 +9,8 @@
 // ceil(log16 n)-1 times, in ONE padded buffer (middle passes run in place: load, barrier, store).
 // The transform length is a template parameter: every shared-memory offset is an immediate.  Unnormalised in
 // both directions, forward kernel e^{-j...} (cuFFT's convention, which karnel/kernel.cu:324-326,363-368 rely on).
+// Scalar fp32 butterflies in this translation unit: the stand-alone transforms are HBM-bound, not issue-bound: packed FADD2/FFMA2 only add latency here (n = 256 batch: 96 us packed, 83 us scalar = 99 % of the HBM peak; one transform in a graph 1.83 vs 1.58 us).
+#define PV_NO_PACKED 1
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>

@@ -18,6 +18,8 @@
 //   G /N, half swap, win  karnel/kernel.cu:130-138, 51-59, 75-81
 //   H overlap-add         karnel/kernel.cu:111-119
 //   I emit hop            src/main.cpp:281-295
+// Scalar fp32 butterflies in this translation unit: the per-frame contract kernels move 32 KB of {mag, phase} per frame through HBM and the shape-generic stream kernels are fallbacks: scalar butterflies, as measured for the HBM-bound stand-alone FFT (pv_fft_batch.cu).
+#define PV_NO_PACKED 1
 #include <algorithm>
 #include <cstdlib>
 
