@@ -56,7 +56,10 @@ struct CTables {
     unsigned long long bqs[8];      // (beta_q * Hs) << (32 - lgN): nomS[s] = a_hi * bqs mod 2^64 is recomputed per slot
     int multi[8];                   // voice has synthesis bins that sum several analysis bins
     float scale;            // gain / N
-    int V;
+    int V;                  // voices of THIS launch (tables above start at its first voice)
+    int V_total, voice0;    // voices of the handle and first voice of this launch: the carried state holds all V_total
+    int last_group;         // this launch holds the handle's last voice: it writes the state's common part (previous phase);
+                            // earlier voice groups must leave it as carried in for the launches that follow
     int Ha;
 };
 

@@ -95,8 +95,10 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
     // state layout: [have_prev u32][pad][P_prev u32 x NB (8-byte padded)][psi u64 x V*NB][acc f32 x V*N]
     uint32_t *st_hdr = reinterpret_cast<uint32_t *>(state);
     uint32_t *st_P = st_hdr ? st_hdr + 2 : nullptr;
-    unsigned long long *st_psi = state ? reinterpret_cast<unsigned long long *>(state + 8 + ((NB * 4 + 7) / 8) * 8) : nullptr;
-    float *st_acc = st_psi ? reinterpret_cast<float *>(st_psi + (size_t)V * NB) : nullptr;
+    // psi and the OLA rings of ALL the handle's voices; this launch works on voices [voice0, voice0 + V)
+    unsigned long long *st_psi_all = state ? reinterpret_cast<unsigned long long *>(state + 8 + ((NB * 4 + 7) / 8) * 8) : nullptr;
+    unsigned long long *st_psi = st_psi_all ? st_psi_all + (size_t)tb.voice0 * NB : nullptr;
+    float *st_acc = st_psi_all ? reinterpret_cast<float *>(st_psi_all + (size_t)tb.V_total * NB) + (size_t)tb.voice0 * N : nullptr;
 
     const CThreadTw tt = load_cthread_tw<LOG2N>(tid, tb);
     CState st;
@@ -206,10 +208,12 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
     const int plast = (pos0 - Hs) & (N - 1);
     emit(seg.k_end - 1, plast, false);
     if (seg.carry_out && state) {
-        if (tid == 0) { st_hdr[0] = (uint32_t)st.have_prev; st_hdr[1] = 0; }
+        if (tb.last_group) {
+            if (tid == 0) { st_hdr[0] = (uint32_t)st.have_prev; st_hdr[1] = 0; }
 #pragma unroll
-        for (int sl = 0; sl < 9; sl++)
-            if (sl < 8 || tid == 0) st_P[slot_bin<B3>(tid, sl)] = st.Pprev[sl];
+            for (int sl = 0; sl < 9; sl++)
+                if (sl < 8 || tid == 0) st_P[slot_bin<B3>(tid, sl)] = st.Pprev[sl];
+        }
         for (int i = tid; i < V * NB; i += T) st_psi[i] = psi[i];
         for (int i = tid; i < V * N; i += T) st_acc[i] = acc[(i & ~(N - 1)) + ((plast + i) & (N - 1))];
     }
@@ -291,6 +295,7 @@ bool pv_fused_corrected_supported(int N, int Ha, int Hs)
 
 int pv_fused_corrected_capacity(int N, int V, int sm_count)
 {
+    if (V >= 3 && !getenv("PV_VOICES_ONE_LAUNCH")) V = 2;        // voices_per_launch()
     switch (N) {
         case 256: return ccapacity<8, 4>(V, sm_count);
         case 512: return ccapacity<9, 4>(V, sm_count);
@@ -301,21 +306,29 @@ int pv_fused_corrected_capacity(int N, int V, int sm_count)
     }
 }
 
-static CTables make_ctables(const PvDev &d, const PvFusedTables &t)
+// Tables for voices [v0, v0 + nv) of the handle (nv = 0: all of them).
+static CTables make_ctables(const PvDev &d, const PvFusedTables &t, int v0 = 0, int nv = 0)
 {
+    if (nv <= 0) nv = d.V - v0;
+    const size_t nb = (size_t)d.N / 2 + 1;
     CTables tb{};
     tb.ctw1 = t.ctw1; tb.ctw2 = t.ctw2; tb.tw2n = t.tw2n; tb.itw1 = t.itw1; tb.itw2 = t.itw2;
-    tb.win = d.win; tb.nomA = d.nomA; tb.a_lo = d.a_lo; tb.a_hi = d.a_hi;
-    tb.nomS = reinterpret_cast<const unsigned long long *>(d.nomS);
-    for (int v = 0; v < d.V; v++) tb.Rq[v] = d.Rq[v];
+    tb.win = d.win; tb.nomA = d.nomA;
+    tb.a_lo = d.a_lo ? d.a_lo + (size_t)v0 * nb : nullptr;
+    tb.a_hi = d.a_hi ? d.a_hi + (size_t)v0 * nb : nullptr;
+    tb.nomS = d.nomS ? reinterpret_cast<const unsigned long long *>(d.nomS) + (size_t)v0 * nb : nullptr;
     tb.scale = d.gain / (float)d.N;
-    tb.V = d.V;
+    tb.V = nv;
+    tb.V_total = d.V;
+    tb.voice0 = v0;
+    tb.last_group = (v0 + nv == d.V) ? 1 : 0;
     tb.Ha = d.Ha;
-    tb.gather = d.gather;
-    for (int v = 0; v < d.V; v++) {
-        tb.beta_q[v] = d.beta_q[v];
-        tb.bqs[v] = (d.beta_q[v] * (unsigned long long)d.Hs) << (32 - d.lgN);
-        tb.multi[v] = d.multi[v];
+    tb.gather = d.gather ? d.gather + (size_t)v0 * (size_t)(d.N / 16) * 9 : nullptr;
+    for (int v = 0; v < nv; v++) {
+        tb.Rq[v] = d.Rq[v0 + v];
+        tb.beta_q[v] = d.beta_q[v0 + v];
+        tb.bqs[v] = (d.beta_q[v0 + v] * (unsigned long long)d.Hs) << (32 - d.lgN);
+        tb.multi[v] = d.multi[v0 + v];
     }
     return tb;
 }
@@ -509,16 +522,33 @@ cudaError_t pv_launch_shard_prefix(int nb, int elems, int rank, int64_t n_stream
     return cudaGetLastError();
 }
 
-cudaError_t pv_launch_corrected_fused(const PvDev &d, const PvFusedTables &t, const PvProcessArgs &a, cudaStream_t st)
+// Voices per launch.  Every voice adds a phase-accumulator array and an overlap-add ring to the group's shared memory, and
+// at three or four voices that costs resident CTAs (window 256: 4 -> 2 per SM).  Two launches of two voices each -- the
+// forward transform is computed twice -- measured faster than one launch of four (tools/voices_probe.py).
+static int voices_per_launch(const PvDev &d)
 {
-    if (a.n_segs <= 0) return cudaSuccess;
-    const CTables tb = make_ctables(d, t);
-    switch (d.N) {
-        case 256: return claunch<8, 4>(d, tb, a, st);
-        case 512: return claunch<9, 4>(d, tb, a, st);
-        case 1024: return claunch<10, 4>(d, tb, a, st);
-        case 2048: return claunch<11, 4>(d, tb, a, st);
-        case 4096: return claunch<12, 2>(d, tb, a, st);
-        default: return cudaErrorInvalidValue;
+    static const bool no_split = getenv("PV_VOICES_ONE_LAUNCH") != nullptr;      // A/B switch, read once
+    return (d.V >= 3 && !no_split) ? 2 : d.V;
+}
+
+cudaError_t pv_launch_corrected_fused(const PvDev &d, const PvFusedTables &t, const PvProcessArgs &a0, cudaStream_t st)
+{
+    if (a0.n_segs <= 0) return cudaSuccess;
+    const int per = voices_per_launch(d);
+    for (int v0 = 0; v0 < d.V; v0 += per) {
+        const CTables tb = make_ctables(d, t, v0, std::min(per, d.V - v0));
+        PvProcessArgs a = a0;
+        a.out = a0.out + (long long)v0 * a0.out_voice_stride;
+        cudaError_t e;
+        switch (d.N) {
+            case 256: e = claunch<8, 4>(d, tb, a, st); break;
+            case 512: e = claunch<9, 4>(d, tb, a, st); break;
+            case 1024: e = claunch<10, 4>(d, tb, a, st); break;
+            case 2048: e = claunch<11, 4>(d, tb, a, st); break;
+            case 4096: e = claunch<12, 2>(d, tb, a, st); break;
+            default: return cudaErrorInvalidValue;
+        }
+        if (e != cudaSuccess) return e;
     }
+    return cudaSuccess;
 }

@@ -20,7 +20,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "phase-vocoder_b200", "csrc")
 
 @pytest.fixture(scope="module")
 def emul():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("pv_fused_core.cuh", "pv_fft_regs.cuh", "pv_fused_tables.h")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("pv_fused_core.cuh", "pv_fused_corrected.cuh", "pv_fft_regs.cuh", "pv_fused_tables.h")]
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-o", LIB, SRC], check=True)
     L = C.CDLL(LIB)
