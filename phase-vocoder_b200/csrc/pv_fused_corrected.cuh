@@ -192,24 +192,24 @@ PV_DEV CThreadTw load_cthread_tw(int tid, const CTables &tb)
     constexpr int S1 = C::S1, R2 = C::R2;
     CThreadTw t;
     auto one = make_float2(1.f, 0.f);
-    if constexpr (2 * C::C1 == C::T && 2 * C::C2 == C::T) {
+    t.p1 = t.p2 = TwBase4{one, one, one, one};
+    if constexpr (2 * C::C1 == C::T) {
+        // forward pass 1 (split radix 16): W_M^{k1 t1}, k1 = 2q + half, t1 = tid % C1; table row k1-1
         const int half = tid / C::C1;
-        {   // forward pass 1: W_M^{k1 t1}, k1 = 2q + half, t1 = tid % C1; table row k1-1
-            const int t1 = tid % C::C1;
-            t.p1.o = half ? PV_LDG(tb.ctw1 + 0 * S1 + t1) : one;
-            t.p1.g1 = PV_LDG(tb.ctw1 + 1 * S1 + t1);
-            t.p1.g2 = PV_LDG(tb.ctw1 + 3 * S1 + t1);
-            t.p1.g4 = PV_LDG(tb.ctw1 + 7 * S1 + t1);
-        }
-        {   // forward pass 2: W_S1^{k2 n3}, n3 = (tid % C2) / R1
-            const int n3 = (tid % C::C2) / C::R1;
-            t.p2.o = half ? PV_LDG(tb.ctw2 + 0 * 4 + n3) : one;
-            t.p2.g1 = PV_LDG(tb.ctw2 + 1 * 4 + n3);
-            t.p2.g2 = PV_LDG(tb.ctw2 + 3 * 4 + n3);
-            t.p2.g4 = PV_LDG(tb.ctw2 + 7 * 4 + n3);
-        }
-    } else {
-        t.p1 = t.p2 = TwBase4{one, one, one, one};
+        const int t1 = tid % C::C1;
+        t.p1.o = half ? PV_LDG(tb.ctw1 + 0 * S1 + t1) : one;
+        t.p1.g1 = PV_LDG(tb.ctw1 + 1 * S1 + t1);
+        t.p1.g2 = PV_LDG(tb.ctw1 + 3 * S1 + t1);
+        t.p1.g4 = PV_LDG(tb.ctw1 + 7 * S1 + t1);
+    }
+    if constexpr (2 * C::C2 == C::T) {
+        // forward pass 2 (split radix 16): W_S1^{k2 n3}, n3 = (tid % C2) / R1
+        const int half = tid / C::C2;
+        const int n3 = (tid % C::C2) / C::R1;
+        t.p2.o = half ? PV_LDG(tb.ctw2 + 0 * 4 + n3) : one;
+        t.p2.g1 = PV_LDG(tb.ctw2 + 1 * 4 + n3);
+        t.p2.g2 = PV_LDG(tb.ctw2 + 3 * 4 + n3);
+        t.p2.g4 = PV_LDG(tb.ctw2 + 7 * 4 + n3);
     }
     t.wN = PV_LDG(tb.tw2n + 2 * tid);
     t.w2 = PV_LDG(tb.tw2n + 4 * tid);
@@ -284,12 +284,13 @@ PV_DEV void cforward(int tid, const FrameIO &io, const CTables &tb, const CThrea
         if (half == 0) dft16_half<-1, false>(v, o);
         else dft16_half<-1, true>(v, o);
         float2 e[8];
-        if constexpr (TWREG) tw_expand(tt.p1, e);
+        constexpr bool TWREG1 = TWREG || (2 * C::C1 == T);      // window 4096: pass 1 is a split radix 16 too
+        if constexpr (TWREG1) tw_expand(tt.p1, e);
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             const int k1 = 2 * q + half;
             float2 r = o[q];
-            if (k1 != 0) r = cmul(r, TWREG ? e[q] : PV_LDG(tb.ctw1 + (k1 - 1) * S1 + t1));
+            if (k1 != 0) r = cmul(r, TWREG1 ? e[q] : PV_LDG(tb.ctw1 + (k1 - 1) * S1 + t1));
             bufA[k1 * C::LD1 + t1] = r;
         }
     } else {

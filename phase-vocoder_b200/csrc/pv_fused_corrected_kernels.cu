@@ -263,9 +263,7 @@ cudaError_t claunch(const PvDev &d, const CTables &tb, const PvProcessArgs &a, c
     if (ring == 2 && !ldgsts && d.N % d.Ha == 0) ring = 3;
     const size_t gb = L::group_bytes(tb.V) - (ring ? 0 : (size_t)d.N * 4);
     const size_t smem = gb * L::G;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaError_t e = pv_max_smem_once<corrected_fused_kernel<LOG2N, MINB>>();
     if (e != cudaSuccess) return e;
     const int grid = (a.n_segs + L::G - 1) / L::G;
     kern<<<grid, L::THREADS, smem, st>>>(d, tb, a, in_ok, out_ok, ring, (unsigned)gb, PvAggArgs{});
@@ -279,7 +277,7 @@ int ccapacity(int V, int sm_count)
     auto kern = corrected_fused_kernel<LOG2N, MINB>;
     const size_t smem = L::group_bytes(V) * L::G;
     int nb = 0;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+    if (pv_max_smem_once<corrected_fused_kernel<LOG2N, MINB>>() != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, L::THREADS, smem) != cudaSuccess || nb < 1)
         nb = 1;
     return nb * sm_count * L::G;
@@ -346,7 +344,7 @@ static cudaError_t agg_launch(const PvDev &d, const CTables &tb, const PvAggArgs
     const int ring = (in_ok && d.Ha <= d.N) ? (al16 ? 2 : 1) : 0;
     const size_t gb = L::group_bytes(tb.V) - (ring ? 0 : (size_t)d.N * 4);
     const size_t smem = gb * L::G;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(L::group_bytes(tb.V) * L::G));
+    cudaError_t e = pv_max_smem_once<corrected_fused_kernel<LOG2N, MINB>>();
     if (e != cudaSuccess) return e;
     PvProcessArgs a{};
     a.in = ag.in;

@@ -166,9 +166,7 @@ cudaError_t launch2(const PvDev &d, const Tables &tb, const PvProcessArgs &a, in
     using L = Launch<LOG2N>;
     auto kern = compat_fused_kernel<LOG2N, MINB, RING>;
     const size_t smem = L::smem(RING != 0);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaError_t e = pv_max_smem_once<compat_fused_kernel<LOG2N, MINB, RING>>();
     if (e != cudaSuccess) return e;
     const int grid = (a.n_segs + L::G - 1) / L::G;
     kern<<<grid, L::THREADS, smem, st>>>(d, tb, a, vec_in_ok, vec_out_ok);
@@ -204,7 +202,7 @@ static int capacity(int sm_count)
     auto kern = compat_fused_kernel<LOG2N, L::MINB_RING, 2>;
     const size_t smem = L::smem(true);
     int nb = 0;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+    if (pv_max_smem_once<compat_fused_kernel<LOG2N, L::MINB_RING, 2>>() != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, L::THREADS, smem) != cudaSuccess || nb < 1)
         nb = 1;
     return nb * sm_count * L::G;

@@ -989,14 +989,14 @@ cudaError_t pv_launch_aggregate_generic(const PvDev &d, const PvAggArgs &a, cuda
     if (a.n_segs <= 0) return cudaSuccess;
     if (use_inplace_corrected(d)) {         // must be the aggregate that shares analysis_inplace with the processing kernel
         const size_t smem = InplaceLayout<12>::bytes(d.V, false);
-        cudaError_t e = cudaFuncSetAttribute(aggregate_inplace_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = pv_max_smem_once<aggregate_inplace_kernel<12>, false>();
         if (e != cudaSuccess) return e;
         aggregate_inplace_kernel<12><<<a.n_segs, 256, smem, st>>>(d, a);
         return cudaGetLastError();
     }
     const size_t NB = d.N / 2 + 1;
     const size_t smem = sizeof(float2) * (NB + fft_work_elems(d.N / 2)) + sizeof(uint32_t) * NB;
-    cudaError_t e = cudaFuncSetAttribute(aggregate_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = pv_max_smem_once<aggregate_generic_kernel, false>();
     if (e != cudaSuccess) return e;
     aggregate_generic_kernel<<<(unsigned)a.n_segs, generic_threads(d.N), smem, st>>>(d, a);
     return cudaGetLastError();
@@ -1079,7 +1079,7 @@ cudaError_t pv_launch_corrected_generic(const PvDev &d, const PvProcessArgs &a, 
     if (a.n_segs <= 0) return cudaSuccess;
     if (use_inplace_corrected(d)) {
         const size_t smem = InplaceLayout<12>::bytes(d.V, true);
-        cudaError_t e = cudaFuncSetAttribute(corrected_inplace_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = pv_max_smem_once<corrected_inplace_kernel<12>, false>();
         if (e != cudaSuccess) return e;
         corrected_inplace_kernel<12><<<a.n_segs, 256, smem, st>>>(d, a);
         return cudaGetLastError();
@@ -1088,12 +1088,12 @@ cudaError_t pv_launch_corrected_generic(const PvDev &d, const PvProcessArgs &a, 
     const size_t smem = std::max(sizeof(float2) * (2 * NB + fft_work_elems(d.N / 2)) + sizeof(float) * 2 * NB, sizeof(float) * (size_t)d.N);
     const size_t with_state = smem + (size_t)d.V * NB * 8 + (size_t)d.V * d.N * 4 + NB * 4;
     if (with_state <= 113 * 1024) {         // two CTAs per SM still fit
-        cudaError_t e = cudaFuncSetAttribute(corrected_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_state);
+        cudaError_t e = pv_max_smem_once<corrected_generic_kernel<true>, false>();
         if (e != cudaSuccess) return e;
         corrected_generic_kernel<true><<<a.n_segs, generic_threads(d.N), with_state, st>>>(d, a);
         return cudaGetLastError();
     }
-    cudaError_t e = cudaFuncSetAttribute(corrected_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = pv_max_smem_once<corrected_generic_kernel<false>, false>();
     if (e != cudaSuccess) return e;
     corrected_generic_kernel<false><<<a.n_segs, generic_threads(d.N), smem, st>>>(d, a);
     return cudaGetLastError();
@@ -1104,7 +1104,7 @@ cudaError_t pv_launch_analysis_batch(const PvDev &d, const float *in, int64_t n_
 {
     if (n_frames <= 0) return cudaSuccess;
     const size_t smem = sizeof(float2) * 2 * (size_t)d.N;
-    cudaError_t e = cudaFuncSetAttribute(analysis_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = pv_max_smem_once<analysis_batch_kernel, false>();
     if (e != cudaSuccess) return e;
     analysis_batch_kernel<<<(unsigned)n_frames, generic_threads(d.N), smem, st>>>(
         d, in, n_in, reinterpret_cast<float2 *>(out_magphase));
@@ -1115,7 +1115,7 @@ static cudaError_t launch_resynth(const PvDev &d, const float *spectra, int64_t 
                                   float *back_out, float *out, float *full, cudaStream_t st)
 {
     const size_t smem = sizeof(float2) * (size_t)d.N + sizeof(float) * (size_t)d.N;
-    cudaError_t e = cudaFuncSetAttribute(resynthesis_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = pv_max_smem_once<resynthesis_batch_kernel, false>();
     if (e != cudaSuccess) return e;
     resynthesis_batch_kernel<<<1, generic_threads(d.N), smem, st>>>(d, reinterpret_cast<const float2 *>(spectra), n_frames,
                                                              back_in, back_out, out, full);
@@ -1147,13 +1147,13 @@ cudaError_t pv_launch_compat_generic(const PvDev &d, const PvProcessArgs &a, cud
     if (a.n_segs <= 0) return cudaSuccess;
     if (d.N == 4096 && !getenv("PV_NO_INPLACE")) {
         const size_t smem = sizeof(float2) * (size_t)fft_work_elems(d.N) + sizeof(float) * (size_t)d.N;
-        cudaError_t e = cudaFuncSetAttribute(compat_inplace_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = pv_max_smem_once<compat_inplace_kernel<12>, false>();
         if (e != cudaSuccess) return e;
         compat_inplace_kernel<12><<<a.n_segs, 256, smem, st>>>(d, a);
         return cudaGetLastError();
     }
     const size_t smem = sizeof(float2) * (size_t)(d.N + fft_work_elems(d.N)) + sizeof(float) * (size_t)d.N;
-    cudaError_t e = cudaFuncSetAttribute(compat_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = pv_max_smem_once<compat_generic_kernel, false>();
     if (e != cudaSuccess) return e;
     compat_generic_kernel<<<a.n_segs, generic_threads(d.N), smem, st>>>(d, a);
     return cudaGetLastError();

@@ -56,6 +56,26 @@ struct PvFusedTables {
     const float2 *ctw1 = nullptr, *ctw2 = nullptr;
 };
 
+// Opts a kernel in to the device's full dynamic shared memory ONCE per kernel and device.  The attribute is process-wide per
+// function: setting it to each launch's own size (round 1) let two host threads with different voice counts or ring modes
+// shrink it under each other's feet ("too many resources requested for launch").
+template <auto Kern, bool CARVEOUT = true>
+inline cudaError_t pv_max_smem_once()
+{
+    static bool done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+        e = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        if (CARVEOUT) e = cudaFuncSetAttribute(Kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+    return cudaSuccess;
+}
+
 // ---- launchers (defined in the .cu files) ----
 bool pv_fused_compat_supported(int N, int Hs);
 // number of segment groups that can be resident on the device at once
