@@ -1099,9 +1099,11 @@ static int process_host_impl(pv_handle *h, const void *in_v, int64_t n_streams, 
     // unchunked call.  Pinned host buffers are needed for real overlap.
     const int N = h->p.window, Ha = h->p.hop_in, Hs = h->p.hop_out;
     const int64_t bytes_in = n_streams * n_in * (int64_t)esz;
-    // ~24 MB per chunk and direction, at most 64 chunks: measured on the headline batch (tools/host_chunks_probe.py),
-    // 64 chunks of 32 MB take 44 ms where 32 chunks of 65 MB take 51 ms (copies of about 64 MB are a slow spot)
-    int64_t n_chunks = std::min<int64_t>(64, std::max<int64_t>(1, bytes_in / (24ll << 20)));
+    // ~32 MB per chunk and direction, at most 64 chunks.  Measured on the headline batch (tools/host_chunks_probe.py,
+    // tools/pcm16_probe.py): the copy engines of this box have slow spots by copy size -- float: 64 chunks of 33 MB take 45 ms
+    // where 32 chunks of 65 MB take 54 ms; 16-bit PCM: 32 chunks of 33 MB take 22.3 ms, 43 chunks of 24 MB 26.6 ms, 64 chunks of
+    // 16 MB 23.0 ms -- so both sample types aim at the ~33 MB chunk.
+    int64_t n_chunks = std::min<int64_t>(64, std::max<int64_t>(1, bytes_in / (32ll << 20)));
     if (const char *e = getenv("PV_HOST_CHUNKS")) n_chunks = std::max(1, atoi(e));      // test / tuning knob
     const int64_t min_fc = std::max<int64_t>(8, 4 * ((N + Ha - 1) / Ha));
     int64_t fc = std::max(min_fc, (n_frames + n_chunks - 1) / n_chunks);

@@ -71,6 +71,9 @@ def test_null_arguments_are_rejected_before_any_device_work():
         lambda: lib.pv_corrected_split_aggregate(None, buf, 1, 8, 8, 1, 0, None, 0, buf, None),
         lambda: lib.pv_corrected_state_from_carry(None, 1, buf, buf, 0, buf, None, None),
         lambda: lib.pv_fft_batch(None, buf, buf, 4, 1, -1, None),
+        lambda: lib.pv_shard_plan_frames(None, 10, 2, 0, C.byref(pvb200.ShardPlanC())),
+        lambda: lib.pv_shard_begin(None, buf, 0, 1, 8, 8, 4, 2, 0, buf, None),
+        lambda: lib.pv_shard_finish(None, buf, 0, 1, 8, 8, 4, 4, 2, 0, buf, buf, 8, 8, None),
         lambda: lib.pv_rt_open(None, 1, 1, C.byref(rt)),
         lambda: lib.pv_rt_step(None),
         lambda: lib.pv_rt_reset(None),
@@ -84,7 +87,7 @@ def test_null_arguments_are_rejected_before_any_device_work():
     assert lib.pv_rt_latency_samples(None) == 0 and not lib.pv_rt_input(None) and not lib.pv_rt_output(None)
     lib.pv_rt_close(None)
     lib.pv_destroy(None)
-    assert lib.pv_launch_count(None) == 0 and lib.pv_state_bytes(None) == 0
+    assert lib.pv_launch_count(None) == 0 and lib.pv_state_bytes(None) == 0 and lib.pv_shard_carry_elems(None) == 0
 
 
 def test_public_header_is_plain_c():
