@@ -548,7 +548,10 @@ def run_ours(args):
     if world > 1 and not args.no_c5:
         del x, out
         torch.cuda.empty_cache()
-        c5 = c5_sharded(torch, dist, pvb200, world, rank, local)
+        try:
+            c5 = c5_sharded(torch, dist, pvb200, world, rank, local)
+        except Exception as e:          # noqa: BLE001 -- a side record: never lose the headline line over it
+            c5 = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         peak, peak_src, sm_max = peaks()
