@@ -455,27 +455,35 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
         const unsigned long long Rq = tb.Rq[v];
         const bool multi = tb.multi[v] != 0;
         float2 Y[9];
+        // The slot loop is branch-free on the common path (pitch ratio >= 1: every synthesis bin has at most one source
+        // bin): the nine slots' chains -- gather, two 32 x 64-bit multiply-adds, int -> float, two MUFU, one packed
+        // multiply -- are independent, and only straight-line code lets the scheduler interleave them.  The multi-source
+        // loop of ratios < 1 and the first-frame initialisation used to sit inside every slot as branches.
+        auto slots = [&](auto multi_tag) {
+            constexpr bool MULTI = decltype(multi_tag)::value;
 #pragma unroll
-        for (int sl = 0; sl < 9; sl++) {
-            Y[sl] = make_float2(0.f, 0.f);
-            if (sl == 8 && u != 0) break;
-            const int s = slot_bin<B3>(u, sl);
-            const uint32_t ge = PV_LDG(gt + sl);         // a_lo | a_hi << 16; no source bin: both = NB, the dummy bin
-            const uint32_t lo = ge & 0xffffu, hi = ge >> 16;
-            float m = magS[lo];                          // 0 at the dummy bin: the slot stays zero
-            if (multi) {                                 // pitch ratio < 1 only (uniform per voice)
+            for (int sl = 0; sl < 9; sl++) {
+                Y[sl] = make_float2(0.f, 0.f);
+                if (sl == 8 && u != 0) break;
+                const int s = slot_bin<B3>(u, sl);
+                const uint32_t ge = PV_LDG(gt + sl);         // a_lo | a_hi << 16; no source bin: both = NB, the dummy bin
+                const uint32_t lo = ge & 0xffffu, hi = ge >> 16;
+                float m = magS[lo];                          // 0 at the dummy bin: the slot stays zero
+                if constexpr (MULTI) {
 #pragma unroll 1
-                for (uint32_t a = lo + 1; a <= hi; a++) m += magS[a];   // ascending, as the specification sums
+                    for (uint32_t a = lo + 1; a <= hi; a++) m += magS[a];   // ascending, as the specification sums
+                }
+                const int32_t d = dS[hi];
+                // psi[s] += nomS[s] + D * Rq (mod 2^64), nomS[s] = a_hi * bqs: 32 x 64-bit multiply-adds
+                unsigned long long p = mad_s32_u64(d, Rq, mad_u32_u64(hi, bqs, ps[s]));
+                p = first ? ((unsigned long long)(uint32_t)d << 32) : p;     // first frame: the analysis phase itself
+                if (lo != (uint32_t)NB) ps[s] = p;           // an empty range leaves the accumulator untouched
+                const float2 cs = cis_turns64(p);
+                Y[sl] = f2mul(cs, f2bc(m));
             }
-            const int32_t d = dS[hi];
-            // psi[s] += nomS[s] + D * Rq (mod 2^64), nomS[s] = a_hi * bqs: 32 x 64-bit multiply-adds
-            unsigned long long p;
-            if (first) p = (unsigned long long)(uint32_t)d << 32;
-            else p = mad_s32_u64(d, Rq, mad_u32_u64(hi, bqs, ps[s]));
-            if (lo != (uint32_t)NB) ps[s] = p;           // an empty range leaves the accumulator untouched
-            const float2 cs = cis_turns64(p);
-            Y[sl] = f2mul(cs, f2bc(m));
-        }
+        };
+        if (multi) slots(std::true_type{});                  // pitch ratio < 1 only (uniform per voice)
+        else slots(std::false_type{});
         // Hermitian pack (same register pattern as the compat kernel); exp(+2 pi i k/N) = conj(W_N^k)
         float2 Zp[4], Zq[4];
         {
