@@ -357,19 +357,21 @@ PV_DEV float2 split(float2 a, float2 b, float2 w)
 // steps D+E of the reference collapsed algebraically: re' = |Re X|, im' = Re X Im X/|X|
 PV_DEV float2 compat_map(float2 X, bool nan_compat)
 {
+    // Branch-free on purpose: a thread maps nine independent bins, and only straight-line code lets the scheduler
+    // interleave their rsqrt (MUFU) latencies.
     const float m2 = X.x * X.x + X.y * X.y;
-    if (m2 == 0.f) {
-        const float z = nan_compat ? __builtin_nanf("") : 0.f;   // atanf(0/0) of kernel.cu:108
-        return make_float2(z, z);
-    }
 #ifdef PV_HOST_EMUL
-    const float r = 1.0f / sqrtf(m2);
+    const float r = m2 > 0.f ? 1.0f / sqrtf(m2) : 0.f;
 #else
-    float r;     // single MUFU.RSQ (2 ulp); a denormal |X|^2 flushes to 0 -> r = inf, caught below
+    float r;     // single MUFU.RSQ (2 ulp); a zero or denormal |X|^2 flushes to 0 -> r = inf, replaced below
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(m2));
-    if (m2 < 1.17549435e-38f) return make_float2(fabsf(X.x), 0.f);
 #endif
-    return make_float2(fabsf(X.x), X.x * X.y * r);
+    const bool tiny = m2 < 1.17549435e-38f;                         // zero or denormal |X|^2: Im' = 0
+    const bool zero_nan = nan_compat && m2 == 0.f;                  // atanf(0/0) of kernel.cu:108 when asked for
+    const float z = __builtin_nanf("");
+    const float re = zero_nan ? z : fabsf(X.x);
+    const float im = zero_nan ? z : (tiny ? 0.f : X.x * X.y * r);
+    return make_float2(re, im);
 }
 
 // Z[k] = (Yk + conj(Ym)) + j*w*(Yk - conj(Ym)), w = exp(+2 pi i k/N), Ym = Y[N/2 - k]

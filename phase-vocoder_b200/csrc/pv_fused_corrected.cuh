@@ -426,8 +426,9 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
             const int bin = slot_bin<B3>(u, sl);
             const uint32_t Pc = phase_turns32(X[sl].x, X[sl].y);
             const uint32_t nomA = ((uint32_t)bin * (uint32_t)tb.Ha) << (32 - LOG2N);
-            if (!first) agg.sum[bin] += (long long)(int32_t)(Pc - st.Pprev[sl] - nomA);
-            else if (agg.P_first) agg.P_first[bin] = Pc;
+            // branch-free in the common case (see the synthesis slot loop): a first frame adds 0
+            agg.sum[bin] += first ? 0ll : (long long)(int32_t)(Pc - st.Pprev[sl] - nomA);
+            if (first && agg.P_first) agg.P_first[bin] = Pc;
             st.Pprev[sl] = Pc;
         }
         st.have_prev = 1;
