@@ -428,8 +428,14 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
             const uint32_t nomA = ((uint32_t)bin * (uint32_t)tb.Ha) << (32 - LOG2N);
             // branch-free in the common case (see the synthesis slot loop): a first frame adds 0
             agg.sum[bin] += first ? 0ll : (long long)(int32_t)(Pc - st.Pprev[sl] - nomA);
-            if (first && agg.P_first) agg.P_first[bin] = Pc;
             st.Pprev[sl] = Pc;
+        }
+        if (first && agg.P_first) {          // once per segment, outside the slot loop
+#pragma unroll
+            for (int sl = 0; sl < 9; sl++) {
+                if (sl == 8 && u != 0) break;
+                agg.P_first[slot_bin<B3>(u, sl)] = st.Pprev[sl];
+            }
         }
         st.have_prev = 1;
         return;          // the next frame's first barrier orders the reuse of the exchange buffers
