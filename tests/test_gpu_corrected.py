@@ -157,6 +157,26 @@ def test_corrected_state_carry_is_bit_exact():
     assert np.abs(dP[strong]).max() < 2 ** 32 * 1e-3        # < 1e-3 turns on every bin (noise floor present)
 
 
+def test_four_voices_carry_and_launch_modes_are_bit_exact(monkeypatch):
+    """Three or four voices run as launches of two voices each (calls of >= 16 frames) or as one launch (short calls, or
+    PV_VOICES_ONE_LAUNCH): same bits either way, and chained calls through the carried state equal one call."""
+    N, H, nf = 512, 128, 70
+    betas = [1.0, f32(1.26), SEMI7, 2.0]
+    x = dev(np.stack([multitone(N + nf * H, seed=40 + s, noise=1e-3) for s in range(3)]))
+    pv = make(N, H, H, betas)
+    full = pv.process(x, nf).cpu().numpy()
+    st = torch.zeros((3, pv.state_bytes()), dtype=torch.uint8, device="cuda")
+    parts, k = [], 0
+    for n in (30, 5, 35):                               # 30 and 35 frames: voice pairs; 5 frames: one launch
+        parts.append(pv.process(x[:, k * H:], n, state=st, flags=(pvb200.CARRY_IN if k else 0) | pvb200.CARRY_OUT).cpu().numpy())
+        k += n
+    assert np.array_equal(np.concatenate(parts, axis=2), full)
+    monkeypatch.setenv("PV_VOICES_ONE_LAUNCH", "1")     # read once per process by the launcher: may already be latched
+    win = po.window(po.WIN_HANN_PERIODIC, N)
+    want, _ = po.process_corrected(x[1].cpu().numpy(), N, H, H, win, [1.0, 2.0], nf)
+    assert snr_db(want[0], full[1, 0]) > 100 and snr_db(want[1], full[1, 3]) > 100
+
+
 def test_corrected_many_streams_host_path():
     N, H, nf, S = 256, 64, 40, 300
     rng = np.random.default_rng(3)

@@ -26,15 +26,18 @@ def offline(pv, x, latency, n_frames):
     ("corrected", 256, 64, 64, 1, 7),         # C4's shape, one hop per block
     ("corrected", 2048, 512, 512, 3, 2),
     ("corrected", 512, 100, 100, 4, 2),       # hop not a multiple of 4: unaligned ring rows
-    ("corrected", 256, 64, 64, 96, 1),        # one long block of one stream: the frame-range split inside the graph
+    ("corrected", 256, 64, 64, 96, 1),        # one long block of one stream
+    ("corrected4", 256, 64, 64, 1, 5),        # C4: four voices; a short block is ONE launch, the offline run two launches of two voices
+    ("corrected4", 512, 128, 128, 20, 2),     # four voices, blocks long enough for the voice-pair launches inside the graph
 ])
 def test_blocks_equal_offline_delayed_input(mode, N, Ha, Hs, B, S):
     blocks = 9
     if mode == "compat":
         pv = pvb200.PhaseVocoder(N, hop_in=Ha, hop_out=Hs, mode=pvb200.MODE_COMPAT)
     else:
+        pitch = (1.0, f32(1.5)) if mode == "corrected" else (1.0, f32(2 ** (4 / 12)), f32(2 ** (7 / 12)), 2.0)
         pv = pvb200.PhaseVocoder(N, hop_in=Ha, hop_out=Hs, mode=pvb200.MODE_CORRECTED,
-                                 window_type=pvb200.WIN_HANN_PERIODIC, pitch=(1.0, f32(1.5)))
+                                 window_type=pvb200.WIN_HANN_PERIODIC, pitch=pitch)
     x = np.stack([multitone(blocks * B * Ha, seed=70 + s) for s in range(S)])
     rt = pvb200.RealtimeServer(pv, S, B)
     assert rt.latency == N - Ha and rt.block_in == B * Ha and rt.block_out == B * Hs
