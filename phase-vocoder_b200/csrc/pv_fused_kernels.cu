@@ -13,11 +13,9 @@
 #include "pv_fused_core.cuh"
 #include "pv_internal.h"
 
-#ifdef PV_EXP_SELECT_OLA
-#define PV_ZERO_ON_EMIT false
-#else
+// every emitted hop is zeroed as it is written out: it becomes the fresh tail of the next frame, so the overlap-add is a
+// plain accumulate (pv_fused_core.cuh, inverse_23_ola)
 #define PV_ZERO_ON_EMIT true
-#endif
 
 namespace {
 
