@@ -75,30 +75,40 @@ PV_DEV void ring_prefetch_coop(int tid, const FrameIO &io, float *ring, int lo)
 // atan2(im, re) in turns, scaled by 2^32 (wraps mod 2^32).  Octant reduction + a degree-15 odd minimax
 // polynomial for atan(t)/(2 pi) on [0, 1] (max error 2.6e-8 turns in fp32, i.e. the accuracy of atan2f):
 // branch-free, no special-case handling (atan2(0,0) = 0), ~1/3 of the instructions of atan2f.
-PV_DEV uint32_t phase_turns32(float re, float im)
+// The three steps are separate functions so that TWO bins can share the polynomial as packed pairs (phase_turns32x2): each
+// lane of a packed instruction rounds like the scalar one, so a bin's phase does not depend on whether it was paired.
+PV_DEV float phase_ratio(float re, float im)            // min(|re|, |im|) / max(|re|, |im|) in [0, 1]
 {
     const float ax = fabsf(re), ay = fabsf(im);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
 #ifdef PV_HOST_EMUL
-    const float t = mx > 1e-30f ? mn / mx : 0.f;
+    return mx > 1e-30f ? mn / mx : 0.f;
 #else
     // one MUFU.RCP + one multiply: __fdividef wraps the same reciprocal in a denormal-divisor rescue (two compares, predicate
     // logic, two scalings: ~10 instructions per bin); a bin below 1e-30 (-600 dB) has no phase worth rescuing
     float rc;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(mx));
-    const float t = mx > 1e-30f ? mn * rc : 0.f;
+    return mx > 1e-30f ? mn * rc : 0.f;
 #endif
-    const float s = t * t;
-    float q = -0.0006453014793805778f;
-    q = fmaf(q, s, 0.0034795869141817093f);
-    q = fmaf(q, s, -0.00889870710670948f);
-    q = fmaf(q, s, 0.015346021391451359f);
-    q = fmaf(q, s, -0.02213626727461815f);
-    q = fmaf(q, s, 0.031745944172143936f);
-    q = fmaf(q, s, -0.05304612219333649f);
-    q = fmaf(q, s, 0.15915483236312866f);
-    float r = q * t;                       // [0, 1/8] turn
-    r = ay > ax ? 0.25f - r : r;
+}
+
+PV_DEV float2 phase_poly2(float2 t)                      // atan(t) / (2 pi) for two ratios: [0, 1/8] turn
+{
+    const float2 s = f2mul(t, t);
+    float2 q = f2bc(-0.0006453014793805778f);
+    q = f2fma(q, s, f2bc(0.0034795869141817093f));
+    q = f2fma(q, s, f2bc(-0.00889870710670948f));
+    q = f2fma(q, s, f2bc(0.015346021391451359f));
+    q = f2fma(q, s, f2bc(-0.02213626727461815f));
+    q = f2fma(q, s, f2bc(0.031745944172143936f));
+    q = f2fma(q, s, f2bc(-0.05304612219333649f));
+    q = f2fma(q, s, f2bc(0.15915483236312866f));
+    return f2mul(q, t);
+}
+
+PV_DEV uint32_t phase_finish(float r, float re, float im)
+{
+    r = fabsf(im) > fabsf(re) ? 0.25f - r : r;
     r = re < 0.f ? 0.5f - r : r;
     r = im < 0.f ? -r : r;
     // r*2^32 reaches +-2^31 (r = +-1/2 turn), outside the int32 range: convert r*2^31 (32-bit F2I instead of the slow 64-bit one)
@@ -109,6 +119,20 @@ PV_DEV uint32_t phase_turns32(float re, float im)
 #else
     return (uint32_t)__float2int_rn(r * 2147483648.0f) << 1;
 #endif
+}
+
+PV_DEV uint32_t phase_turns32(float re, float im)
+{
+    const float t = phase_ratio(re, im);
+    return phase_finish(phase_poly2(make_float2(t, t)).x, re, im);
+}
+
+// two bins at once: the polynomial (ten of the ~25 instructions of a bin) runs once on a packed pair
+PV_DEV void phase_turns32x2(float2 xa, float2 xb, uint32_t &Pa, uint32_t &Pb)
+{
+    const float2 r = phase_poly2(make_float2(phase_ratio(xa.x, xa.y), phase_ratio(xb.x, xb.y)));
+    Pa = phase_finish(r.x, xa.x, xa.y);
+    Pb = phase_finish(r.y, xb.x, xb.y);
 }
 
 // |X|: one MUFU (sqrt.approx.ftz, 1 ulp) instead of the IEEE sqrtf sequence
@@ -141,16 +165,15 @@ PV_DEV unsigned long long mad_s32_u64(int32_t d, unsigned long long b, unsigned 
 
 PV_DEV float2 cis_turns64(unsigned long long psi)
 {
-    // top 32 bits as signed turns in [-0.5, 0.5)
-    const float t = (float)(int32_t)(psi >> 32) * (1.0f / 4294967296.0f);
+    // top 32 bits as signed turns in [-0.5, 0.5), converted to radians in ONE multiply (2 pi * 2^-32)
+    const float ang = (float)(int32_t)(psi >> 32) * 1.4629180792671596e-9f;
     float s, c;
 #ifdef PV_HOST_EMUL
-    const float ang = t * 6.283185307179586f;
     s = sinf(ang); c = cosf(ang);
 #else
     // the argument is already reduced to [-pi, pi): the SFU approximations are accurate to 2^-21 absolute
     // there (4e-7 of the bin magnitude, -128 dB), and cost 2 MUFU instead of ~25 instructions
-    __sincosf(t * 6.283185307179586f, &s, &c);
+    __sincosf(ang, &s, &c);
 #endif
     return make_float2(c, s);
 }
@@ -426,11 +449,16 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
     // ---- analysis: magnitude, phase (turns*2^32), unwrapped phase difference ----
     const bool first = st.have_prev == 0;
     if (agg.on) {
+        uint32_t Pn[9];
+#pragma unroll
+        for (int sl = 0; sl < 8; sl += 2) phase_turns32x2(X[sl], X[sl + 1], Pn[sl], Pn[sl + 1]);
+        Pn[8] = 0u;
+        if (u == 0) Pn[8] = phase_turns32(X[8].x, X[8].y);
 #pragma unroll
         for (int sl = 0; sl < 9; sl++) {
             if (sl == 8 && u != 0) break;
             const int bin = slot_bin<B3>(u, sl);
-            const uint32_t Pc = phase_turns32(X[sl].x, X[sl].y);
+            const uint32_t Pc = Pn[sl];
             const uint32_t nomA = ((uint32_t)bin * (uint32_t)tb.Ha) << (32 - LOG2N);
             // branch-free in the common case (see the synthesis slot loop): a first frame adds 0
             agg.sum[bin] += first ? 0ll : (long long)(int32_t)(Pc - st.Pprev[sl] - nomA);
@@ -446,12 +474,17 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
         st.have_prev = 1;
         return;          // the next frame's first barrier orders the reuse of the exchange buffers
     }
+    uint32_t Pn[9];
+#pragma unroll
+    for (int sl = 0; sl < 8; sl += 2) phase_turns32x2(X[sl], X[sl + 1], Pn[sl], Pn[sl + 1]);
+    Pn[8] = 0u;
+    if (u == 0) Pn[8] = phase_turns32(X[8].x, X[8].y);
 #pragma unroll
     for (int sl = 0; sl < 9; sl++) {
         if (sl == 8 && u != 0) break;
         const int bin = slot_bin<B3>(u, sl);
         const float2 x = X[sl];
-        const uint32_t Pc = phase_turns32(x.x, x.y);
+        const uint32_t Pc = Pn[sl];
         magS[bin] = fast_sqrt(x.x * x.x + x.y * x.y);
         // nomA[bin] = (bin*Ha*2^32/N) mod 2^32 (see pv_capi.cu): two integer ops instead of a table load
         const uint32_t nomA = ((uint32_t)bin * (uint32_t)tb.Ha) << (32 - LOG2N);
