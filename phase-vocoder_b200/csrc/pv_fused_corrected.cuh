@@ -18,6 +18,12 @@
 #pragma once
 #include "pv_fused_core.cuh"
 
+#ifdef PV_HOST_EMUL
+#include <cstring>
+static inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+static inline int __float_as_int(float f) { int v; std::memcpy(&v, &f, 4); return v; }
+#endif
+
 namespace pvfused {
 
 template <int LOG2N>
@@ -434,7 +440,7 @@ struct AggCtx {
 
 template <int LOG2N, class Sync, class Hook, class PreLast>
 PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const CThreadTw &tt, const float *ring,
-                            float2 *bufA, float2 *bufB, float *magS, int32_t *dS, unsigned long long *psi, float *acc,
+                            float2 *bufA, float2 *bufB, float2 *mdS, unsigned long long *psi, float *acc,
                             CState &st, int pos0, int Hs, Sync sync, Hook hook, PreLast pre_last_sync,
                             const AggCtx agg = AggCtx{false, nullptr, nullptr})
 {
@@ -485,10 +491,12 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
         const int bin = slot_bin<B3>(u, sl);
         const float2 x = X[sl];
         const uint32_t Pc = Pn[sl];
-        magS[bin] = fast_sqrt(x.x * x.x + x.y * x.y);
         // nomA[bin] = (bin*Ha*2^32/N) mod 2^32 (see pv_capi.cu): two integer ops instead of a table load
         const uint32_t nomA = ((uint32_t)bin * (uint32_t)tb.Ha) << (32 - LOG2N);
-        dS[bin] = first ? (int32_t)Pc : (int32_t)(Pc - st.Pprev[sl] - nomA);
+        const int32_t dd = first ? (int32_t)Pc : (int32_t)(Pc - st.Pprev[sl] - nomA);
+        // {|X|, D} of a bin side by side: one 8-byte store here, and ONE 8-byte load per synthesis bin in the common case of a
+        // single source bin (pitch ratio >= 1)
+        mdS[bin] = make_float2(fast_sqrt(x.x * x.x + x.y * x.y), __int_as_float(dd));
         st.Pprev[sl] = Pc;
     }
     st.have_prev = 1;
@@ -514,12 +522,13 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
                 const int s = slot_bin<B3>(u, sl);
                 const uint32_t ge = PV_LDG(gt + sl);         // a_lo | a_hi << 16; no source bin: both = NB, the dummy bin
                 const uint32_t lo = ge & 0xffffu, hi = ge >> 16;
-                float m = magS[lo];                          // 0 at the dummy bin: the slot stays zero
+                float2 md = mdS[lo];                         // {0, 0} at the dummy bin: the slot stays zero
+                float m = md.x;
                 if constexpr (MULTI) {
 #pragma unroll 1
-                    for (uint32_t a = lo + 1; a <= hi; a++) m += magS[a];   // ascending, as the specification sums
+                    for (uint32_t a = lo + 1; a <= hi; a++) { md = mdS[a]; m += md.x; }   // ascending, as the specification sums
                 }
-                const int32_t d = dS[hi];
+                const int32_t d = __float_as_int(md.y);      // D of the LAST source bin (a_hi); a_lo == a_hi unless MULTI
                 // psi[s] += nomS[s] + D * Rq (mod 2^64), nomS[s] = a_hi * bqs: 32 x 64-bit multiply-adds
                 unsigned long long p = mad_s32_u64(d, Rq, mad_u32_u64(hi, bqs, ps[s]));
                 p = first ? ((unsigned long long)(uint32_t)d << 32) : p;     // first frame: the analysis phase itself

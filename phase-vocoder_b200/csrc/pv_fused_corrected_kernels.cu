@@ -63,8 +63,8 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
     float2 *bufB = bufA + C::BUF_A;
     unsigned long long *psi = reinterpret_cast<unsigned long long *>(bufB + C::BUF_B);
     float *magS = reinterpret_cast<float *>(psi + (size_t)V * ((NB + 1) & ~1));
-    int32_t *dS = reinterpret_cast<int32_t *>(magS + ((NB + 3) & ~3));
-    float *acc = reinterpret_cast<float *>(dS + ((NB + 3) & ~3));
+    float2 *mdS = reinterpret_cast<float2 *>(magS);            // {|X|, D} per bin, NB + 1 entries (the last one: the dummy bin)
+    float *acc = magS + 2 * ((NB + 3) & ~3);
     float *ring = use_ring ? acc + (size_t)V * N : nullptr;
     // ring mode 3: the new hop of every frame arrives as ONE bulk asynchronous copy (cp.async.bulk + mbarrier)
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(base + group_bytes - 16);
@@ -124,7 +124,7 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
             if (agg_pf) agg_pf[bin] = 0u;
         }
     } else {
-        if (tid == 0) { magS[NB] = 0.f; dS[NB] = 0; }      // the dummy bin behind empty gather entries (pv_fused_tables.h)
+        if (tid == 0) mdS[NB] = make_float2(0.f, 0.f);     // the dummy bin behind empty gather entries (pv_fused_tables.h)
         for (int i = tid; i < V * NB; i += T) psi[i] = cin ? st_psi[i] : 0ull;
         for (int i = tid; i < V * N; i += T) {
             const int ii = i & (N - 1);
@@ -177,7 +177,7 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
             if (!agg_mode && k > seg.k_begin) emit(k - 1, (pos0 - Hs) & (N - 1), PV_ZERO_ON_EMIT);
         };
         const AggCtx ac{agg_mode, k < seg.k_emit ? sumH : sumS, agg_pf};
-        frame_corrected<LOG2N>(tid, io, tb, tt, ring, bufA, bufB, magS, dS, psi, acc, st, pos0, Hs, sync, hook,
+        frame_corrected<LOG2N>(tid, io, tb, tt, ring, bufA, bufB, mdS, psi, acc, st, pos0, Hs, sync, hook,
                                [&]() { if (use_ring) cp_async_wait_all(); }, ac);
         if (agg_mode && use_ring) {        // analysis only: no inverse passes whose last barrier would complete the refill
             cp_async_wait_all();

@@ -117,8 +117,8 @@ static int run_corrected(const float *x, long n_in, int Ha, int Hs, const float 
         tb.multi[v] = multi[v];
     }
     std::vector<float2> bufA(C::BUF_A), bufB(C::BUF_B);
-    std::vector<float> acc((size_t)V * N, 0.f), ringbuf(N, 0.f), magS(NB + 3, 0.f);
-    std::vector<int32_t> dS(NB + 3, 0);
+    std::vector<float> acc((size_t)V * N, 0.f), ringbuf(N, 0.f);
+    std::vector<float2> mdS(NB + 3, make_float2(0.f, 0.f));
     std::vector<unsigned long long> psi((size_t)V * NB, 0ull);
     std::barrier bar(T);
     const bool use_ring = (Ha % 2) == 0 && Ha <= N;
@@ -151,7 +151,7 @@ static int run_corrected(const float *x, long n_in, int Ha, int Hs, const float 
                         }
                 }
             };
-            frame_corrected<LOG2N>(tid, io, tb, tt, ring, bufA.data(), bufB.data(), magS.data(), dS.data(), psi.data(),
+            frame_corrected<LOG2N>(tid, io, tb, tt, ring, bufA.data(), bufB.data(), mdS.data(), psi.data(),
                                    acc.data(), st, pos0, Hs, sync, hook, [&]() { cp_async_wait_all(); });
             pos0 = (pos0 + Hs) & (N - 1);
         }
