@@ -55,7 +55,7 @@ struct CTables {
     const int32_t *a_lo;    // [V][NB]
     const int32_t *a_hi;    // [V][NB]
     const unsigned long long *nomS;   // [V][NB]
-    const uint32_t *gather; // [V][T][9] per-thread packed a_lo | a_hi << 16 in slot order (4.6 KB per voice at N = 2048:
+    const uint32_t *gather; // [V][T][9] per-thread source bins in slot order, pv_fused_tables.h (4.6 KB per voice at N = 2048:
                             // small on purpose -- only ~24 KB of L1 remain next to the shared-memory carve-out)
     unsigned long long Rq[8];
     unsigned long long beta_q[8];   // pitch ratio, Q32.32
@@ -167,6 +167,35 @@ PV_DEV unsigned long long mad_s32_u64(int32_t d, unsigned long long b, unsigned 
     // (uint32)d = d + 2^32 for negative d: take b << 32 back out
     const uint32_t hi = (uint32_t)(r >> 32) + (uint32_t)(d >> 31) * (uint32_t)b;
     return ((unsigned long long)hi << 32) | (uint32_t)r;
+}
+
+// The accumulator update of one synthesis bin, psi += a_hi * bqs + D * Rq (mod 2^64), in four multiply-adds.
+//   e8 = 8 * a_hi (the byte offset of the source bin's {|X|, D} slot, which the slot loop has anyway) times bq = bqs / 8;
+//   Rq = rq_hi * 2^32 + rq_lo with rq_lo SIGNED: D * rq_lo is then one signed 32 x 32 -> 64-bit multiply-add, and only the low
+//   word of D * rq_hi matters -- no sign fix-up for negative D.
+// A stream's first frame sets psi = D << 32 (D = the analysis phase itself then): the same update with the multipliers
+// (bq, Rq) = (0, 2^32) on the zero-initialised accumulator, chosen once per frame instead of two selects per bin.
+struct PsiMul { uint32_t bq_lo, bq_hi; int32_t rq_lo; uint32_t rq_hi; };
+
+PV_DEV PsiMul psi_mul(unsigned long long bqs, unsigned long long Rq, bool first)
+{
+    const unsigned long long bq = bqs >> 3;          // bqs = x << (32 - lgN): a multiple of 2^20
+    PsiMul m;
+    m.bq_lo = first ? 0u : (uint32_t)bq;
+    m.bq_hi = first ? 0u : (uint32_t)(bq >> 32);
+    m.rq_lo = first ? 0 : (int32_t)(uint32_t)Rq;
+    m.rq_hi = first ? 1u : (uint32_t)(Rq >> 32) + ((uint32_t)Rq >> 31);
+    return m;
+}
+
+PV_DEV unsigned long long psi_step(unsigned long long ps, uint32_t e8, int32_t d, const PsiMul &m)
+{
+    unsigned long long t = (unsigned long long)e8 * m.bq_lo + ps;
+    t = (unsigned long long)((long long)d * (long long)m.rq_lo + (long long)t);
+    uint32_t hi = (uint32_t)(t >> 32);
+    hi += e8 * m.bq_hi;
+    hi += (uint32_t)d * m.rq_hi;
+    return ((unsigned long long)hi << 32) | (uint32_t)t;
 }
 
 PV_DEV float2 cis_turns64(unsigned long long psi)
@@ -504,15 +533,14 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
     // ---- synthesis, one voice at a time ----
     for (int v = 0; v < tb.V; v++) {
         const uint32_t *gt = tb.gather + ((size_t)v * C::T + u) * 9;
-        const unsigned long long bqs = tb.bqs[v];
         unsigned long long *ps = psi + (size_t)v * NB;
-        const unsigned long long Rq = tb.Rq[v];
+        const PsiMul pm = psi_mul(tb.bqs[v], tb.Rq[v], first);
         const bool multi = tb.multi[v] != 0;
         float2 Y[9];
         // The slot loop is branch-free on the common path (pitch ratio >= 1: every synthesis bin has at most one source
-        // bin): the nine slots' chains -- gather, two 32 x 64-bit multiply-adds, int -> float, two MUFU, one packed
-        // multiply -- are independent, and only straight-line code lets the scheduler interleave them.  The multi-source
-        // loop of ratios < 1 and the first-frame initialisation used to sit inside every slot as branches.
+        // bin): the nine slots' chains -- gather, four multiply-adds, int -> float, two MUFU, one packed multiply -- are
+        // independent, and only straight-line code lets the scheduler interleave them.  The multi-source loop of ratios < 1
+        // and the first-frame initialisation used to sit inside every slot as branches.
         auto slots = [&](auto multi_tag) {
             constexpr bool MULTI = decltype(multi_tag)::value;
 #pragma unroll
@@ -520,19 +548,25 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
                 Y[sl] = make_float2(0.f, 0.f);
                 if (sl == 8 && u != 0) break;
                 const int s = slot_bin<B3>(u, sl);
-                const uint32_t ge = PV_LDG(gt + sl);         // a_lo | a_hi << 16; no source bin: both = NB, the dummy bin
-                const uint32_t lo = ge & 0xffffu, hi = ge >> 16;
-                float2 md = mdS[lo];                         // {0, 0} at the dummy bin: the slot stays zero
-                float m = md.x;
-                if constexpr (MULTI) {
+                const uint32_t ge = PV_LDG(gt + sl);         // no source bin: the dummy bin NB ({0, 0}: the slot stays zero)
+                uint32_t e8;                                 // 8 * a_hi
+                float2 md;
+                float m;
+                if constexpr (MULTI) {                       // entry = a_lo | a_hi << 16
+                    const uint32_t lo = ge & 0xffffu, hi = ge >> 16;
+                    md = mdS[lo];
+                    m = md.x;
 #pragma unroll 1
                     for (uint32_t a = lo + 1; a <= hi; a++) { md = mdS[a]; m += md.x; }   // ascending, as the specification sums
+                    e8 = hi << 3;
+                } else {                                     // entry = 8 * a_hi: the load address and the multiplier as they are
+                    e8 = ge;
+                    md = *reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(mdS) + e8);
+                    m = md.x;
                 }
-                const int32_t d = __float_as_int(md.y);      // D of the LAST source bin (a_hi); a_lo == a_hi unless MULTI
-                // psi[s] += nomS[s] + D * Rq (mod 2^64), nomS[s] = a_hi * bqs: 32 x 64-bit multiply-adds
-                unsigned long long p = mad_s32_u64(d, Rq, mad_u32_u64(hi, bqs, ps[s]));
-                p = first ? ((unsigned long long)(uint32_t)d << 32) : p;     // first frame: the analysis phase itself
-                if (lo != (uint32_t)NB) ps[s] = p;           // an empty range leaves the accumulator untouched
+                const int32_t d = __float_as_int(md.y);      // D of the LAST source bin (a_hi)
+                const unsigned long long p = psi_step(ps[s], e8, d, pm);
+                if (e8 != (uint32_t)(8 * NB)) ps[s] = p;     // an empty range leaves the accumulator untouched
                 const float2 cs = cis_turns64(p);
                 Y[sl] = f2mul(cs, f2bc(m));
             }

@@ -125,7 +125,8 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
         }
     } else {
         if (tid == 0) mdS[NB] = make_float2(0.f, 0.f);     // the dummy bin behind empty gather entries (pv_fused_tables.h)
-        for (int i = tid; i < V * NB; i += T) psi[i] = cin ? st_psi[i] : 0ull;
+        // zero until the stream's first frame: that frame's update relies on it (psi_step)
+        for (int i = tid; i < V * NB; i += T) psi[i] = (cin && st.have_prev) ? st_psi[i] : 0ull;
         for (int i = tid; i < V * N; i += T) {
             const int ii = i & (N - 1);
             acc[i] = (cin && ii + Hs < N) ? st_acc[i + Hs] : 0.f;

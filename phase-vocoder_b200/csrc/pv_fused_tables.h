@@ -70,27 +70,32 @@ inline void build_gather_natural(int N, int V, const int32_t *a_lo, const int32_
     }
 }
 
-// Per-thread packed gather table of the corrected kernel: entry [v][u][slot] = a_lo | a_hi << 16 for the
-// synthesis bin owned by slot `slot` of thread `u` (pvfused::slot_bin).  A synthesis bin that no analysis bin maps
-// to points at the DUMMY bin NB (both halves): the kernel keeps magnitude 0 and phase difference 0 there, so the
-// slot needs no special case.  multi[v] = 1 if some bin of voice v sums more than one analysis bin (beta < 1).
+// Per-thread gather table of the corrected kernel, entry [v][u][slot] for the synthesis bin owned by slot `slot` of thread
+// `u` (pvfused::slot_bin).  A voice whose synthesis bins have at most ONE source bin each (pitch ratio >= 1) stores 8 * a_hi:
+// the byte offset of the source bin's {|X|, D} slot and, at the same time, the multiplier of the accumulator update
+// (pvfused::psi_step) -- the slot loop needs no unpacking.  A voice that sums several analysis bins into some synthesis bin
+// (pitch ratio < 1, multi[v] = 1) stores a_lo | a_hi << 16.  A synthesis bin that no analysis bin maps to points at the DUMMY
+// bin NB: the kernel keeps magnitude 0 and phase difference 0 there, so the slot needs no special case.
 inline void build_gather_table(int N, int V, const int32_t *a_lo, const int32_t *a_hi, std::vector<uint32_t> &out,
                                int32_t *multi = nullptr)
 {
     const int T = N / 16, B3 = N / 8, NB = N / 2 + 1;
-    const uint32_t dummy = (uint32_t)NB | ((uint32_t)NB << 16);
-    out.assign((size_t)V * T * 9, dummy);
+    out.assign((size_t)V * T * 9, 0u);
     for (int v = 0; v < V; v++) {
-        if (multi) multi[v] = 0;
+        bool mv = false;
+        for (int s = 0; s < NB; s++) mv = mv || a_hi[(size_t)v * NB + s] > a_lo[(size_t)v * NB + s];
+        if (multi) multi[v] = mv ? 1 : 0;
+        const uint32_t dummy = mv ? (uint32_t)NB | ((uint32_t)NB << 16) : 8u * (uint32_t)NB;
         for (int u = 0; u < T; u++)
             for (int sl = 0; sl < 9; sl++) {
+                uint32_t &e = out[((size_t)v * T + u) * 9 + sl];
+                e = dummy;
                 if (sl == 8 && u != 0) continue;                                   // slot not used
                 const int j = sl & 3;
                 const int bin = (sl == 8) ? 4 * B3 : (sl < 4 ? u + B3 * j : (u == 0 ? B3 / 2 : B3 - u) + B3 * j);
                 const size_t i = (size_t)v * NB + bin;
                 if (a_lo[i] > a_hi[i]) continue;                                   // empty range
-                if (multi && a_hi[i] > a_lo[i]) multi[v] = 1;
-                out[((size_t)v * T + u) * 9 + sl] = (uint32_t)a_lo[i] | ((uint32_t)a_hi[i] << 16);
+                e = mv ? (uint32_t)a_lo[i] | ((uint32_t)a_hi[i] << 16) : 8u * (uint32_t)a_hi[i];
             }
     }
 }
