@@ -144,6 +144,21 @@ PV_DEV void dft16_half(const float2 (&a)[16], float2 (&o)[8])
     dft8<DIR>(o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
 }
 
+// The same with the analysis window folded into the first stage: inputs x[n] * w(n), the products of the upper half
+// contracted into the fold (one FMUL2 + one FFMA2 per output instead of two FMUL2 + one FADD2).
+template <int DIR, bool ODD, class W>
+PV_DEV void dft16_half_win(const float2 (&x)[16], W w, float2 (&o)[8])
+{
+#pragma unroll
+    for (int n = 0; n < 8; n++) o[n] = f2fma(x[n + 8], ODD ? f2neg(w(n + 8)) : w(n + 8), f2mul(x[n], w(n)));
+    if constexpr (ODD) {
+        o[1] = twid16<1, DIR>(o[1]); o[2] = twid16<2, DIR>(o[2]); o[3] = twid16<3, DIR>(o[3]);
+        o[4] = twid16<4, DIR>(o[4]); o[5] = twid16<5, DIR>(o[5]); o[6] = twid16<6, DIR>(o[6]);
+        o[7] = twid16<7, DIR>(o[7]);
+    }
+    dft8<DIR>(o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+}
+
 // ---- radix-32 pieces for window 4096 (pv_fused_core.cuh, Shape<12>: R2 = 32) ----
 // cos(2 pi k / 32) for any integer k, compile time
 PV_HD constexpr float pv_cos32(int k)

@@ -467,7 +467,9 @@ struct TableTw2 {      // default source of the inverse pass-2 twiddles: the glo
     PV_DEV float2 operator()(int /*q*/, int m2, int n3) const { return PV_LDG(itw2 + (m2 - 1) * R2 + n3); }
 };
 
-template <int LOG2N, class Sync, class PreLast, class Tw2 = TableTw2>
+// UNIT_SCALE: the caller has already scaled the spectrum (the corrected kernel folds gain / N into the 1/2 of its real-FFT
+// split, where it costs nothing); `scale` is ignored then.
+template <int LOG2N, class Sync, class PreLast, class Tw2 = TableTw2, bool UNIT_SCALE = false>
 PV_DEV void inverse_23_ola(int tid, const Tables &tb, float2 *bufA, float2 *bufB, float *acc, int pos0, int Hs,
                            bool zero_frame, float scale, Sync sync, PreLast pre_last_sync,
                            Tw2 tw2 = TableTw2{nullptr, 0})
@@ -488,7 +490,8 @@ PV_DEV void inverse_23_ola(int tid, const Tables &tb, float2 *bufA, float2 *bufB
         // cudaDivVec kernel.cu:130-138 (x/N == x*(1/N) exactly, N a power of two) and cudaWindow :75-81.
         // One window table serves analysis and synthesis: with 4 CTAs x 51 KB of shared memory only ~24 KB
         // of L1 remain per SM, and a second (pre-scaled) 8 KB table measurably thrashes it.
-        const float2 w = f2mul(PV_LDG(reinterpret_cast<const float2 *>(tb.win + i)), f2bc(scale));
+        float2 w = PV_LDG(reinterpret_cast<const float2 *>(tb.win + i));
+        if constexpr (!UNIT_SCALE) w = f2mul(w, f2bc(scale));
         float2 *slot = reinterpret_cast<float2 *>(acc + ((pos0 + i) & (N - 1)));
         *slot = f2fma(v, w, *slot);                    // cudaOverlapAdd kernel.cu:111-119
     };

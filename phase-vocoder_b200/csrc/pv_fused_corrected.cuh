@@ -214,10 +214,11 @@ PV_DEV float2 cis_turns64(unsigned long long psi)
 }
 
 // X[k] and X[M-k] of the N-point real spectrum (M = N/2) from a = C[k], b = C[M-k], w = W_N^k
-PV_DEV void split_both(float2 a, float2 b, float2 w, float2 &xk, float2 &xm)
+// h = 1/2 times whatever the caller wants the spectrum scaled by (the output gain: linear all the way to the overlap-add)
+PV_DEV void split_both(float2 a, float2 b, float2 w, float h, float2 &xk, float2 &xm)
 {
-    const float2 e = f2mul(f2add(a, cconj(b)), f2bc(0.5f));
-    const float2 o = f2mul(f2add(mul_mj(a), f2swap(b)), f2bc(0.5f));       // (a.y + b.y, b.x - a.x) / 2
+    const float2 e = f2mul(f2add(a, cconj(b)), f2bc(h));
+    const float2 o = f2mul(f2add(mul_mj(a), f2swap(b)), f2bc(h));          // (a.y + b.y, b.x - a.x) * h
     const float2 t = cmul(w, o);
     xk = f2add(e, t);
     xm = f2add(cconj(e), make_float2(-t.x, t.y));                          // conj(e - t)
@@ -286,7 +287,10 @@ PV_DEV CThreadTw load_cthread_tw(int tid, const CTables &tb)
 }
 
 struct CState {             // per-thread registers carried across the frames of a stream
-    uint32_t Pprev[9];
+    // EXPECTED phase of the next frame per slot: previous phase + nomA[bin], nomA[bin] = (bin * Ha * 2^32 / N) mod 2^32
+    // (see pv_capi.cu); 0 before the first frame.  The phase difference of a frame is then one subtraction, D = P - Pexp, and
+    // the first frame's D = P (the phase itself, pv_oracle.c) needs no special case.
+    uint32_t Pexp[9];
     int have_prev;
 };
 
@@ -299,6 +303,29 @@ PV_DEV int slot_bin(int u, int sl)
     const int j = sl & 3;
     if (sl < 4) return (u == 0 ? 0 : u) + B3 * j;
     return (u == 0 ? B3 / 2 : B3 - u) + B3 * j;
+}
+
+// nomA of the bin of a slot (cold paths: carried state in and out)
+template <int LOG2N>
+PV_DEV uint32_t slot_nomA(int u, int sl, int Ha)
+{
+    return ((uint32_t)slot_bin<CShape<LOG2N>::B3>(u, sl) * (uint32_t)Ha) << (32 - LOG2N);
+}
+
+// The same for all slots of a thread from two products: bins u + B3 j and (B3 - u) + B3 j step by (B3 * Ha) << (32 - LOG2N)
+// = Ha << 29 (B3 = N / 8)
+struct SlotNomA {
+    uint32_t p0, q0, step;
+    PV_DEV uint32_t operator()(int sl) const { return sl == 8 ? step << 2 : (sl < 4 ? p0 : q0) + (uint32_t)(sl & 3) * step; }
+};
+template <int LOG2N>
+PV_DEV SlotNomA slot_nomA_all(int u, int Ha)
+{
+    SlotNomA n;
+    n.step = (uint32_t)Ha << 29;
+    n.p0 = ((uint32_t)u * (uint32_t)Ha) << (32 - LOG2N);
+    n.q0 = u ? n.step - n.p0 : (uint32_t)Ha << 28;       // bin B3 - u; thread 0: bin B3 / 2
+    return n;
 }
 
 // Forward transform of one frame: X[slot] = spectrum at the bins owned by this thread, wp[j] = W_N^bin of
@@ -314,7 +341,10 @@ PV_DEV void cforward(int tid, const FrameIO &io, const CTables &tb, const CThrea
     // Loads the R windowed sample pairs of one pass-1 butterfly.  The ring / global choice is made ONCE per
     // butterfly, not per pair: the hot (ring) path stays one straight run of instructions instead of sixteen
     // short ones separated by the bounds-checked global fallback, which the instruction cache pays for.
-    auto ld_block = [&](auto &v, int t1) {
+    auto win_pair = [&](int n1, int t1) {
+        return PV_LDG(reinterpret_cast<const float2 *>(tb.win + ((N / 2 + 2 * (n1 * S1 + t1)) & (N - 1))));
+    };
+    auto ld_block = [&](auto &v, int t1, auto windowed) {
         constexpr int R = (int)(sizeof(v) / sizeof(v[0]));
         if (ring != nullptr) {
 #pragma unroll
@@ -333,10 +363,9 @@ PV_DEV void cforward(int tid, const FrameIO &io, const CTables &tb, const CThrea
                 v[n1] = x;
             }
         }
+        if constexpr (decltype(windowed)::value) {
 #pragma unroll
-        for (int n1 = 0; n1 < R; n1++) {
-            const int i = (N / 2 + 2 * (n1 * S1 + t1)) & (N - 1);
-            v[n1] = f2mul(v[n1], PV_LDG(reinterpret_cast<const float2 *>(tb.win + i)));
+            for (int n1 = 0; n1 < R; n1++) v[n1] = f2mul(v[n1], win_pair(n1, t1));
         }
     };
 
@@ -344,9 +373,10 @@ PV_DEV void cforward(int tid, const FrameIO &io, const CTables &tb, const CThrea
     if constexpr (2 * C::C1 == T) {
         const int t1 = tid % C::C1, half = tid / C::C1;
         float2 v[16], o[8];
-        ld_block(v, t1);
-        if (half == 0) dft16_half<-1, false>(v, o);
-        else dft16_half<-1, true>(v, o);
+        ld_block(v, t1, std::false_type{});                     // the window goes into the butterfly's first stage
+        auto w = [&](int n1) { return win_pair(n1, t1); };
+        if (half == 0) dft16_half_win<-1, false>(v, w, o);
+        else dft16_half_win<-1, true>(v, w, o);
         float2 e[8];
         constexpr bool TWREG1 = TWREG || (2 * C::C1 == T);      // window 4096: pass 1 is a split radix 16 too
         if constexpr (TWREG1) tw_expand(tt.p1, e);
@@ -361,7 +391,7 @@ PV_DEV void cforward(int tid, const FrameIO &io, const CTables &tb, const CThrea
 #pragma unroll
         for (int t1 = tid; t1 < C::C1; t1 += T) {
             float2 v[R1];
-            ld_block(v, t1);
+            ld_block(v, t1, std::true_type{});
             dft<R1, -1>(v);
             bufA[t1] = v[0];
 #pragma unroll
@@ -437,15 +467,18 @@ PV_DEV void cforward(int tid, const FrameIO &io, const CTables &tb, const CThrea
         // Thread 0 (columns 0 and B3/2): (P0,P0) -> bins 0, N/2; (P1,P3); (P2,P2); (Q0,Q3); (Q1,Q2).
         const bool u0 = (u == 0);
         auto sel = [&](float2 a, float2 b) { return u0 ? a : b; };
+        // the spectrum leaves the split scaled by gain / N: magnitudes carry the output scale from here on (phases do not
+        // care), and the overlap-add multiplies by the bare window
+        const float h = 0.5f * tb.scale;
         // W_N^{u + B3 j} = W_N^u * exp(-2 pi i j/8)
         wp[0] = tt.wN; wp[1] = twid16<2, -1>(tt.wN); wp[2] = twid16<4, -1>(tt.wN); wp[3] = twid16<6, -1>(tt.wN);
         float2 xk0, xm0, xk1, xm1, xk2, xm2, xk3, xm3;
-        split_both(P[0], sel(P[0], Q[3]), wp[0], xk0, xm0);
-        split_both(P[1], sel(P[3], Q[2]), wp[1], xk1, xm1);
-        split_both(P[2], sel(P[2], Q[1]), wp[2], xk2, xm2);
-        split_both(sel(Q[0], P[3]), sel(Q[3], Q[0]), sel(tt.q1, wp[3]), xk3, xm3);
+        split_both(P[0], sel(P[0], Q[3]), wp[0], h, xk0, xm0);
+        split_both(P[1], sel(P[3], Q[2]), wp[1], h, xk1, xm1);
+        split_both(P[2], sel(P[2], Q[1]), wp[2], h, xk2, xm2);
+        split_both(sel(Q[0], P[3]), sel(Q[3], Q[0]), sel(tt.q1, wp[3]), h, xk3, xm3);
         float2 xke = make_float2(0.f, 0.f), xme = xke;
-        if (u0) split_both(Q[1], Q[2], twid16<2, -1>(tt.q1), xke, xme);       // W_N^{3 B3/2}
+        if (u0) split_both(Q[1], Q[2], twid16<2, -1>(tt.q1), h, xke, xme);       // W_N^{3 B3/2}
         X[0] = xk0; X[1] = xk1; X[2] = xk2;
         X[3] = sel(xm1, xk3);
         X[4] = sel(xk3, xm3);
@@ -483,6 +516,7 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
     cforward<LOG2N, TWREG>(tid, io, tb, tt, ring, bufA, bufB, sync, hook, X, wp);
     // ---- analysis: magnitude, phase (turns*2^32), unwrapped phase difference ----
     const bool first = st.have_prev == 0;
+    const SlotNomA nomA = slot_nomA_all<LOG2N>(u, tb.Ha);
     if (agg.on) {
         uint32_t Pn[9];
 #pragma unroll
@@ -494,16 +528,15 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
             if (sl == 8 && u != 0) break;
             const int bin = slot_bin<B3>(u, sl);
             const uint32_t Pc = Pn[sl];
-            const uint32_t nomA = ((uint32_t)bin * (uint32_t)tb.Ha) << (32 - LOG2N);
             // branch-free in the common case (see the synthesis slot loop): a first frame adds 0
-            agg.sum[bin] += first ? 0ll : (long long)(int32_t)(Pc - st.Pprev[sl] - nomA);
-            st.Pprev[sl] = Pc;
+            agg.sum[bin] += first ? 0ll : (long long)(int32_t)(Pc - st.Pexp[sl]);
+            st.Pexp[sl] = Pc + nomA(sl);
         }
         if (first && agg.P_first) {          // once per segment, outside the slot loop
 #pragma unroll
             for (int sl = 0; sl < 9; sl++) {
                 if (sl == 8 && u != 0) break;
-                agg.P_first[slot_bin<B3>(u, sl)] = st.Pprev[sl];
+                agg.P_first[slot_bin<B3>(u, sl)] = Pn[sl];
             }
         }
         st.have_prev = 1;
@@ -520,13 +553,11 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
         const int bin = slot_bin<B3>(u, sl);
         const float2 x = X[sl];
         const uint32_t Pc = Pn[sl];
-        // nomA[bin] = (bin*Ha*2^32/N) mod 2^32 (see pv_capi.cu): two integer ops instead of a table load
-        const uint32_t nomA = ((uint32_t)bin * (uint32_t)tb.Ha) << (32 - LOG2N);
-        const int32_t dd = first ? (int32_t)Pc : (int32_t)(Pc - st.Pprev[sl] - nomA);
+        const int32_t dd = (int32_t)(Pc - st.Pexp[sl]);
         // {|X|, D} of a bin side by side: one 8-byte store here, and ONE 8-byte load per synthesis bin in the common case of a
         // single source bin (pitch ratio >= 1)
         mdS[bin] = make_float2(fast_sqrt(x.x * x.x + x.y * x.y), __int_as_float(dd));
-        st.Pprev[sl] = Pc;
+        st.Pexp[sl] = Pc + nomA(sl);
     }
     st.have_prev = 1;
     sync();
@@ -593,14 +624,15 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
             Zq[3] = herm_pack(Y[7], sel(Y[4], Y[0]), cconj(twid16<8, -1>(q1c)));
         }
         Tables itb{nullptr, nullptr, tb.tw2n, tb.itw1, tb.itw2, tb.win};
+        auto last = [&]() { if (v + 1 == tb.V) pre_last_sync(); };
         {
             // exp(+2 pi i m1 u/(N/2)) = conj(W_N^{2 m1 u}); for t1 = B3-u_q: j^m1 * W_N^{2 m1 u_q}
             const float2 w6 = cmul(tt.w2, tt.w4), q6 = cmul(tt.q2, tt.q4);
             inverse_1_tw<LOG2N>(tP, cconj(tt.w2), cconj(tt.w4), cconj(w6), Zp, bufA);
             inverse_1_tw<LOG2N>(tQ, mul_pj(tt.q2), make_float2(-tt.q4.x, -tt.q4.y), mul_mj(q6), Zq, bufA);
         }
-        inverse_23_ola<LOG2N>(tid, itb, bufA, bufB, acc + (size_t)v * N, pos0, Hs, false, tb.scale, sync,
-                              [&]() { if (v + 1 == tb.V) pre_last_sync(); });
+        inverse_23_ola<LOG2N, Sync, decltype(last), TableTw2, true>(tid, itb, bufA, bufB, acc + (size_t)v * N, pos0, Hs, false, 1.f,
+                                                                    sync, last);
         (void)S::T;
     }
     (void)M;

@@ -102,13 +102,13 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
     CState st;
     st.have_prev = 0;
 #pragma unroll
-    for (int sl = 0; sl < 9; sl++) st.Pprev[sl] = 0;
+    for (int sl = 0; sl < 9; sl++) st.Pexp[sl] = 0;
     const bool cin = seg.carry_in && state;
     if (cin) {
         st.have_prev = (int)st_hdr[0];
 #pragma unroll
         for (int sl = 0; sl < 9; sl++)
-            if (sl < 8 || tid == 0) st.Pprev[sl] = st_P[slot_bin<B3>(tid, sl)];
+            if ((sl < 8 || tid == 0) && st.have_prev) st.Pexp[sl] = st_P[slot_bin<B3>(tid, sl)] + slot_nomA<LOG2N>(tid, sl, d.Ha);
     }
     if (agg_mode) {
         const bool carried = seg.carry_in && ag.P_prev != nullptr &&
@@ -118,7 +118,7 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
         for (int sl = 0; sl < 9; sl++) {
             if (sl == 8 && tid != 0) break;
             const int bin = slot_bin<B3>(tid, sl);
-            st.Pprev[sl] = carried ? ag.P_prev[(long long)seg.stream * ag.P_prev_stride + bin] : 0u;
+            st.Pexp[sl] = carried ? ag.P_prev[(long long)seg.stream * ag.P_prev_stride + bin] + slot_nomA<LOG2N>(tid, sl, d.Ha) : 0u;
             sumS[bin] = 0;
             sumH[bin] = 0;
             if (agg_pf) agg_pf[bin] = 0u;
@@ -199,7 +199,7 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
             const long long o = (long long)seg_idx * NB + bin;
             ag.S[o] = sumS[bin];
             if (ag.H) ag.H[o] = sumH[bin];
-            if (ag.P_last) ag.P_last[o] = st.Pprev[sl];
+            if (ag.P_last) ag.P_last[o] = st.have_prev ? st.Pexp[sl] - slot_nomA<LOG2N>(tid, sl, d.Ha) : 0u;
         }
         return;
     }
@@ -211,7 +211,8 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
             if (tid == 0) { st_hdr[0] = (uint32_t)st.have_prev; st_hdr[1] = 0; }
 #pragma unroll
             for (int sl = 0; sl < 9; sl++)
-                if (sl < 8 || tid == 0) st_P[slot_bin<B3>(tid, sl)] = st.Pprev[sl];
+                if (sl < 8 || tid == 0)
+                    st_P[slot_bin<B3>(tid, sl)] = st.have_prev ? st.Pexp[sl] - slot_nomA<LOG2N>(tid, sl, d.Ha) : 0u;
         }
         for (int i = tid; i < V * NB; i += T) st_psi[i] = psi[i];
         for (int i = tid; i < V * N; i += T) st_acc[i] = acc[(i & ~(N - 1)) + ((plast + i) & (N - 1))];

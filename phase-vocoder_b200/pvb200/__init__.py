@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_DIR, "libpv_b200.so")
+# PV_B200_LIB: another build of the same library (kernel A/B experiments, tools/ab_variants.sh); still no fallback
+LIB_PATH = os.environ.get("PV_B200_LIB") or os.path.join(_DIR, "libpv_b200.so")
 
 MODE_COMPAT, MODE_CORRECTED = 0, 1
 WIN_HAMMING, WIN_HANN_SYM, WIN_HANN_PERIODIC = 0, 1, 2
