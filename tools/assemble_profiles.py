@@ -43,7 +43,7 @@ out += ["",
         "corrected mode), then the analysis pass (~30 %).",
         "",
         "Same runs, the headline batch (independent streams per rank, no collective): device-resident "
-        f"{rows[0][1]['value']/1e6:.0f} / {rows[1][1]['value']/1e6:.0f} / {rows[2][1]['value']/1e6:.0f} M frames/s on 2 / 4 / 8 GPUs (1 GPU: 109 M); end to end "
+        f"{rows[0][1]['value']/1e6:.0f} / {rows[1][1]['value']/1e6:.0f} / {rows[2][1]['value']/1e6:.0f} M frames/s on 2 / 4 / 8 GPUs (1 GPU in the same state of the code: 109 M; the phase-path trims at the end of the round, DESIGN.md 4.2, brought one GPU to 116 M after these runs); end to end "
         f"{rows[0][1]['e2e']['value']/1e6:.1f} / {rows[1][1]['e2e']['value']/1e6:.1f} / {rows[2][1]['e2e']['value']/1e6:.1f} M frames/s = "
         f"{rows[0][1]['e2e']['copy_ceiling']['frac_achieved']:.2f} / {rows[1][1]['e2e']['copy_ceiling']['frac_achieved']:.2f} / "
         f"{rows[2][1]['e2e']['copy_ceiling']['frac_achieved']:.2f} of the copy ceiling measured in the same run (`profiles/r02_pcie_probe.md`)."]
@@ -73,12 +73,13 @@ copied in both directions at once with no kernel (`e2e.copy_ceiling`):
 | GPUs | e2e through pv_process_host (float) | copy-only ceiling, same buffers | e2e / ceiling |
 |---|---|---|---|
 {erows}
-(Ratios slightly above 1 are run-to-run variation of the copies.)  The 16-bit PCM leg (`pv_process_host_pcm16`, half the bytes) on one GPU:
+(Ratios slightly above 1 are run-to-run variation of the copies.  Every row is its own `gpurun` call on a freshly assigned box; the copy
+engines of the boxes differ -- 41 to 56 GB/s each way for one GPU alone -- which is why the ceiling is measured inside every run.)  The 16-bit PCM leg (`pv_process_host_pcm16`, half the bytes) on one GPU:
 {one['e2e']['pcm16']['value']/1e6:.1f} M frames/s = {one['e2e']['pcm16']['copy_ceiling']['frac_achieved']:.2f} of ITS copy ceiling ({one['e2e']['pcm16']['copy_ceiling']['value']/1e6:.1f} M frames/s); VERDICT r01's
 60 M frames/s target for it is above what this box's PCIe moves.
 
 The pipelined host path (chunks of frames on three streams, state carried on the device) therefore sits ON the copy ceiling at every
-GPU count; the kernels behind it scale linearly (109 -> 871 M frames/s).  The end-to-end number of this box cannot scale past what its
+GPU count; the kernels behind it scale linearly (109 -> 871 M frames/s at the time of the multi-GPU runs; one GPU is at 116 M now).  The end-to-end number of this box cannot scale past what its
 host memory system feeds.
 """)
 
@@ -130,4 +131,15 @@ open(os.path.join(P, "r02_voices.md"), "w").write("""# Cost of extra voices (rou
 voices run as launches of two voices each (`DESIGN.md` 4.2); round 1: V = 4 cost 3.8x (window 256) / 4.1x (window 2048) of one voice.
 
 """ + rd("r02_voices.md"))
+open(os.path.join(P, "r02_exchange_micro.md"), "w").write("""# One FFT exchange: shared memory against warp shuffles (round 2)
+
+`tools/micro/exchange_shfl.cu` on one B200 (`tools/refresh_profiles.sh`), the launch shape of the corrected kernel (128 threads per CTA,
+four CTAs per SM, 51 KB of shared memory per CTA).  Every thread hands on 16 complex values per exchange, as in every pass of the fused
+kernels.  VERDICT r01 #7 asked for the `north_star`'s "warp-shuffle FFT" to be built or refused by measurement:
+
+""" + rd("r02_exchange_micro.md") + """
+The shuffle variant is the CHEAPEST pattern shuffles offer (lane-xor butterflies, no dynamic register indexing) and still costs 1.3x the
+shared-memory exchange while reaching 16 lanes instead of the 128 - 256 threads every pass of a 1024- or 2048-point transform needs
+(`DESIGN.md` 4.6).  Not used.
+""")
 print("ok")

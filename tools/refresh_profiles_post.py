@@ -37,6 +37,11 @@ for mode, kern in (("corrected", "corrected_fused"), ("compat", "compat_fused"))
     hot = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_hotmap.py"), rep, "512"], capture_output=True, text=True).stdout
     with open(md, "a") as f:
         f.write("\n## Hot/cold layout of the code (tools/ncu_hotmap.py; instruction-cache view)\n\n```\n" + hot + "```\n")
+    mix = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_opmix.py"), rep, str(FRAMES)], capture_output=True, text=True).stdout
+    lines = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, str(FRAMES), "40"], capture_output=True, text=True).stdout
+    with open(md, "a") as f:
+        f.write("\n## Executed instructions by opcode (tools/ncu_opmix.py)\n\n" + mix)
+        f.write("\n## Executed instructions by source line, every instruction once (tools/ncu_lines.py; top 40)\n\n```\n" + lines + "```\n")
     m = raw_metrics(rep)
     traffic[mode] = {"bytes_per_launch": num(m, "dram__bytes_read.sum") + num(m, "dram__bytes_write.sum"),
                      "frames_per_launch": FRAMES,
