@@ -249,6 +249,15 @@ int pv_process_host_pcm16(pv_handle *h, const int16_t *in, int64_t n_streams, in
                           int64_t out_stream_stride, int64_t out_voice_stride, void *state,
                           int32_t flags);
 
+/* Same with packed 24-bit PCM host buffers (three little-endian bytes per sample, as in the `data` chunk of the
+ * reference's testtones/MAT_ZO_24_bit.wav): sign-extend and /8388608 on load (src/AudioFile.h:508-518), the low
+ * three bytes of (int32)(x*8388608) on save (:755-766; AudioFile does not clamp there and neither does this).
+ * Strides and counts are in SAMPLES.  Three quarters of the bytes of the float call cross PCIe.              */
+int pv_process_host_pcm24(pv_handle *h, const uint8_t *in, int64_t n_streams, int64_t in_stride,
+                          int64_t n_in, int64_t n_analysed, int64_t n_frames, uint8_t *out,
+                          int64_t out_stream_stride, int64_t out_voice_stride, void *state,
+                          int32_t flags);
+
 /* ------------------------------------------------------------------------------------------
  * Real-time block server: the reference's unfinished RtAudio path (src/main.cpp:45-59 `callback`,
  * README.md:44-50, img/Realtime.png).  Its contract: every time the audio buffer is full the

@@ -65,6 +65,26 @@ def float_to_s16(x: np.ndarray) -> np.ndarray:
     return np.trunc(x.astype(np.float64) * 32767.0).astype(np.int16)
 
 
+def s24_to_bytes(v: np.ndarray) -> np.ndarray:
+    """int32 sample values (24 significant bits, sign-extended) -> [..., 3] little-endian bytes as stored in a WAV."""
+    u = np.asarray(v, np.int64) & 0xFFFFFF
+    return np.stack([u & 0xFF, (u >> 8) & 0xFF, (u >> 16) & 0xFF], axis=-1).astype(np.uint8)
+
+
+def bytes_to_s24(b: np.ndarray) -> np.ndarray:
+    """[..., 3] little-endian bytes -> sign-extended int32 (AudioFile.h:508-515)."""
+    b = np.asarray(b, np.uint8).astype(np.int32)
+    v = b[..., 0] | (b[..., 1] << 8) | (b[..., 2] << 16)
+    return np.where(v & 0x800000, v | ~0xFFFFFF, v).astype(np.int32)
+
+
+def float_to_s24(x: np.ndarray) -> np.ndarray:
+    """The 24-bit branch of AudioFile::saveToWaveFile (AudioFile.h:755-757): (int32)(x * 8388608.), NO clamp; the three low
+    bytes are what reaches the file.  Returns the int32 values (callers take `s24_to_bytes`)."""
+    x = np.asarray(x, np.float32)
+    return np.trunc(x.astype(np.float64) * 8388608.0).astype(np.int64).astype(np.int32)
+
+
 def encode_wav16(samples: np.ndarray, rate: int = 44100) -> bytes:
     """samples [channels, n] float -> bytes exactly as AudioFile::saveToWaveFile, 16-bit."""
     ch, n = samples.shape

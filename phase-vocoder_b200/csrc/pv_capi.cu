@@ -1056,10 +1056,11 @@ int pv_shard_finish(pv_handle *h, const float *in, int64_t in_first_frame, int64
 
 }  // extern "C"
 
-// Shared body of the host entry points.  PCM16: the host buffers hold 16-bit PCM and the conversions of the
-// reference's AudioFile (s/32768 in, trunc(clamp(x,-1,1)*32767) out; src/AudioFile.h:1038-1049) run on the
-// device, which halves the bytes crossing PCIe in both directions.
-template <bool PCM16>
+// Shared body of the host entry points.  PCM = 2 / 3: the host buffers hold 16-bit / packed 24-bit PCM and the conversions
+// of the reference's AudioFile (16 bit: s/32768 in, trunc(clamp(x,-1,1)*32767) out, src/AudioFile.h:1038-1049; 24 bit:
+// sign-extend, /8388608 in, (int32)(x*8388608) out, :508-518, :755-766) run on the device, which halves / cuts by a quarter
+// the bytes crossing PCIe in both directions.  PCM = 0: float samples.
+template <int PCM>
 static int process_host_impl(pv_handle *h, const void *in_v, int64_t n_streams, int64_t in_stride, int64_t n_in,
                              int64_t n_analysed, int64_t n_frames, void *out_v, int64_t out_stream_stride,
                              int64_t out_voice_stride, void *state, int32_t flags)
@@ -1080,13 +1081,14 @@ static int process_host_impl(pv_handle *h, const void *in_v, int64_t n_streams, 
         return fail(PV_ERR_PARAM, "pv_process_host: carry requested without a state buffer");
     DeviceGuard guard(h->device);
     const int64_t V = h->p.n_voices, n_out = n_frames * h->p.hop_out;
-    const size_t esz = PCM16 ? 2 : 4;
+    constexpr bool PCM16 = PCM != 0;          // any integer sample type: staged in d_in16 / d_out16 and converted on the device
+    const size_t esz = PCM ? (size_t)PCM : 4;
     // device rows are padded to 4 samples so that the kernels keep their 16-byte aligned fast paths
     const int64_t n_in_p = (n_in + 3) & ~int64_t(3);
     int rc = ensure(&h->d_in, &h->in_cap, std::max<size_t>(4, (size_t)(n_streams * n_in_p)));   // n_in == 0: all-zero input, not a null pointer
     if (rc == PV_OK) rc = ensure(&h->d_out, &h->out_cap, (size_t)(n_streams * V * n_out));
-    if (rc == PV_OK && PCM16) rc = ensure(&h->d_in16, &h->in16_cap, (size_t)(n_streams * n_in_p) / 2);
-    if (rc == PV_OK && PCM16) rc = ensure(&h->d_out16, &h->out16_cap, (size_t)(n_streams * V * n_out + 1) / 2);
+    if (rc == PV_OK && PCM16) rc = ensure(&h->d_in16, &h->in16_cap, ((size_t)(n_streams * n_in_p) * esz + 3) / 4);
+    if (rc == PV_OK && PCM16) rc = ensure(&h->d_out16, &h->out16_cap, ((size_t)(n_streams * V * n_out) * esz + 3) / 4);
     if (rc != PV_OK) return rc;
     for (auto &ps : h->pipe)
         if (!ps) PV_CUDA(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
@@ -1132,7 +1134,7 @@ static int process_host_impl(pv_handle *h, const void *in_v, int64_t n_streams, 
     }
     const unsigned char *in = (const unsigned char *)in_v;
     unsigned char *out = (unsigned char *)out_v;
-    int16_t *d16 = reinterpret_cast<int16_t *>(h->d_in16), *o16 = reinterpret_cast<int16_t *>(h->d_out16);
+    unsigned char *d16 = reinterpret_cast<unsigned char *>(h->d_in16), *o16 = reinterpret_cast<unsigned char *>(h->d_out16);
     int64_t e0 = 0;                                       // input samples already on the device
     // inside the pipeline a failed call must not return before the streams have drained: the caller's buffers are
     // still the source / target of copies in flight
@@ -1150,8 +1152,8 @@ static int process_host_impl(pv_handle *h, const void *in_v, int64_t n_streams, 
         cudaEvent_t ev_in = h->pipe_events[(size_t)(2 * c)], ev_k = h->pipe_events[(size_t)(2 * c + 1)];
         if (e1 > e0) {
             if (PCM16)
-                PIPE_CUDA(cudaMemcpy2DAsync(d16 + e0, 2 * n_in_p, in + (size_t)e0 * 2, 2 * in_stride, 2 * (size_t)(e1 - e0),
-                                          (size_t)n_streams, cudaMemcpyHostToDevice, s_in));
+                PIPE_CUDA(cudaMemcpy2DAsync(d16 + (size_t)e0 * esz, esz * n_in_p, in + (size_t)e0 * esz, esz * in_stride,
+                                          esz * (size_t)(e1 - e0), (size_t)n_streams, cudaMemcpyHostToDevice, s_in));
             else
                 PIPE_CUDA(cudaMemcpy2DAsync(h->d_in + e0, 4 * n_in_p, in + (size_t)e0 * 4, 4 * in_stride, 4 * (size_t)(e1 - e0),
                                           (size_t)n_streams, cudaMemcpyHostToDevice, s_in));
@@ -1159,7 +1161,11 @@ static int process_host_impl(pv_handle *h, const void *in_v, int64_t n_streams, 
         PIPE_CUDA(cudaEventRecord(ev_in, s_in));
         PIPE_CUDA(cudaStreamWaitEvent(s_k, ev_in, 0));
         if (PCM16 && e1 > e0) {
-            PIPE_CUDA(pv_launch_pcm16_to_float(d16, h->d_in, n_streams, n_in_p, e0 & ~int64_t(3), e1, n_in, s_k));
+            if (PCM == 2)
+                PIPE_CUDA(pv_launch_pcm16_to_float(reinterpret_cast<const int16_t *>(d16), h->d_in, n_streams, n_in_p,
+                                                   e0 & ~int64_t(3), e1, n_in, s_k));
+            else
+                PIPE_CUDA(pv_launch_pcm24_to_float(d16, h->d_in, n_streams, n_in_p, e0 & ~int64_t(3), e1, n_in, s_k));
             h->launches++;
         }
         e0 = e1;
@@ -1168,7 +1174,10 @@ static int process_host_impl(pv_handle *h, const void *in_v, int64_t n_streams, 
                           h->d_out + k0 * Hs, V * n_out, n_out, use_state ? h->d_state : nullptr, cflags, s_k);
         if (rc != PV_OK) goto drain;
         if (PCM16) {
-            PIPE_CUDA(pv_launch_float_to_pcm16(h->d_out, o16, n_streams * V, n_out, k0 * Hs, k1 * Hs, s_k));
+            if (PCM == 2)
+                PIPE_CUDA(pv_launch_float_to_pcm16(h->d_out, reinterpret_cast<int16_t *>(o16), n_streams * V, n_out, k0 * Hs, k1 * Hs, s_k));
+            else
+                PIPE_CUDA(pv_launch_float_to_pcm24(h->d_out, o16, n_streams * V, n_out, k0 * Hs, k1 * Hs, s_k));
             h->launches++;
         }
         PIPE_CUDA(cudaEventRecord(ev_k, s_k));
@@ -1176,8 +1185,8 @@ static int process_host_impl(pv_handle *h, const void *in_v, int64_t n_streams, 
         const size_t w = (size_t)(k1 - k0) * Hs;
         for (int64_t v = 0; v < V; v++) {
             if (PCM16)
-                PIPE_CUDA(cudaMemcpy2DAsync(out + ((size_t)v * out_voice_stride + (size_t)k0 * Hs) * 2, 2 * out_stream_stride,
-                                          o16 + v * n_out + k0 * Hs, 2 * V * n_out, 2 * w, (size_t)n_streams,
+                PIPE_CUDA(cudaMemcpy2DAsync(out + ((size_t)v * out_voice_stride + (size_t)k0 * Hs) * esz, esz * out_stream_stride,
+                                          o16 + (size_t)(v * n_out + k0 * Hs) * esz, esz * V * n_out, esz * w, (size_t)n_streams,
                                           cudaMemcpyDeviceToHost, s_out));
             else
                 PIPE_CUDA(cudaMemcpy2DAsync(out + ((size_t)v * out_voice_stride + (size_t)k0 * Hs) * 4, 4 * out_stream_stride,
@@ -1202,7 +1211,7 @@ int pv_process_host(pv_handle *h, const float *in, int64_t n_streams, int64_t in
                     int64_t n_analysed, int64_t n_frames, float *out, int64_t out_stream_stride,
                     int64_t out_voice_stride, void *state, int32_t flags)
 {
-    return process_host_impl<false>(h, in, n_streams, in_stride, n_in, n_analysed, n_frames, out, out_stream_stride,
+    return process_host_impl<0>(h, in, n_streams, in_stride, n_in, n_analysed, n_frames, out, out_stream_stride,
                                     out_voice_stride, state, flags);
 }
 
@@ -1210,8 +1219,16 @@ int pv_process_host_pcm16(pv_handle *h, const int16_t *in, int64_t n_streams, in
                           int64_t n_analysed, int64_t n_frames, int16_t *out, int64_t out_stream_stride,
                           int64_t out_voice_stride, void *state, int32_t flags)
 {
-    return process_host_impl<true>(h, in, n_streams, in_stride, n_in, n_analysed, n_frames, out, out_stream_stride,
+    return process_host_impl<2>(h, in, n_streams, in_stride, n_in, n_analysed, n_frames, out, out_stream_stride,
                                    out_voice_stride, state, flags);
+}
+
+int pv_process_host_pcm24(pv_handle *h, const uint8_t *in, int64_t n_streams, int64_t in_stride, int64_t n_in,
+                          int64_t n_analysed, int64_t n_frames, uint8_t *out, int64_t out_stream_stride,
+                          int64_t out_voice_stride, void *state, int32_t flags)
+{
+    return process_host_impl<3>(h, in, n_streams, in_stride, n_in, n_analysed, n_frames, out, out_stream_stride,
+                                out_voice_stride, state, flags);
 }
 
 }  // extern "C"

@@ -1074,6 +1074,86 @@ cudaError_t pv_launch_float_to_pcm16(const float *in, int16_t *out, int64_t rows
     return cudaGetLastError();
 }
 
+// ---- packed 24-bit PCM (three little-endian bytes per sample), AudioFile rules: sign-extend, / 8388608 in
+// (src/AudioFile.h:508-518); (int32)(x * 8388608), low three bytes out (:755-766: no clamp there -- the conversion
+// saturates here where the reference's is undefined, |x| >= 256) ----
+__global__ void pcm24_to_float_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, long long pitch,
+                                      long long c0, long long c1, long long n_valid)
+{
+    const long long r = blockIdx.y;
+    const long long c = c0 + 4 * (blockIdx.x * (long long)blockDim.x + threadIdx.x);   // c0 and pitch: multiples of 4
+    if (c >= c1) return;
+    // four samples = 12 bytes = three aligned words (rows are `pitch` samples = 3 * pitch bytes, pitch % 4 == 0)
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(in + (r * pitch + c) * 3);
+    const uint32_t w0 = src[0], w1 = src[1], w2 = src[2];
+    const int32_t s0 = (int32_t)(w0 << 8) >> 8;
+    const int32_t s1 = (int32_t)(((w0 >> 24) | (w1 << 8)) << 8) >> 8;
+    const int32_t s2 = (int32_t)(((w1 >> 16) | (w2 << 16)) << 8) >> 8;
+    const int32_t s3 = (int32_t)w2 >> 8;
+    float4 v;
+    v.x = c + 0 < n_valid ? (float)s0 / 8388608.0f : 0.f;
+    v.y = c + 1 < n_valid ? (float)s1 / 8388608.0f : 0.f;
+    v.z = c + 2 < n_valid ? (float)s2 / 8388608.0f : 0.f;
+    v.w = c + 3 < n_valid ? (float)s3 / 8388608.0f : 0.f;
+    *reinterpret_cast<float4 *>(out + r * pitch + c) = v;
+}
+
+__device__ __forceinline__ uint32_t to_pcm24(float x)
+{
+    // x * 2^23 is exact in fp32 (a power of two), the cast truncates toward zero like the reference's
+    return (uint32_t)__float2int_rz(x * 8388608.0f) & 0xffffffu;
+}
+
+__global__ void float_to_pcm24_kernel(const float *__restrict__ in, uint8_t *__restrict__ out, long long pitch,
+                                      long long c0, long long c1, int vec)
+{
+    const long long r = blockIdx.y;
+    const long long c = c0 + 4 * (blockIdx.x * (long long)blockDim.x + threadIdx.x);
+    if (c >= c1) return;
+    const float *src = in + r * pitch + c;
+    uint8_t *dst = out + (r * pitch + c) * 3;
+    if (vec && c + 3 < c1) {
+        const float4 v = *reinterpret_cast<const float4 *>(src);
+        const uint32_t a = to_pcm24(v.x), b = to_pcm24(v.y), cc = to_pcm24(v.z), d = to_pcm24(v.w);
+        uint32_t *w = reinterpret_cast<uint32_t *>(dst);
+        w[0] = a | (b << 24);
+        w[1] = (b >> 8) | (cc << 16);
+        w[2] = (cc >> 16) | (d << 8);
+    } else {
+        for (int j = 0; j < 4 && c + j < c1; j++) {
+            const uint32_t a = to_pcm24(src[j]);
+            dst[3 * j] = (uint8_t)a; dst[3 * j + 1] = (uint8_t)(a >> 8); dst[3 * j + 2] = (uint8_t)(a >> 16);
+        }
+    }
+}
+
+// same contracts as the 16-bit launchers; `in` / `out` are byte pointers, pitch and columns count SAMPLES
+cudaError_t pv_launch_pcm24_to_float(const uint8_t *in, float *out, int64_t rows, int64_t pitch, int64_t c0, int64_t c1,
+                                     int64_t n_valid, cudaStream_t st)
+{
+    if (rows <= 0 || c1 <= c0) return cudaSuccess;
+    if ((pitch & 3) || (c0 & 3) || (reinterpret_cast<uintptr_t>(in) & 3)) return cudaErrorInvalidValue;
+    for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+        const int64_t nr = std::min<int64_t>(65535, rows - r0);
+        const dim3 grid((unsigned)(((c1 - c0 + 3) / 4 + 255) / 256), (unsigned)nr);
+        pcm24_to_float_kernel<<<grid, 256, 0, st>>>(in + r0 * pitch * 3, out + r0 * pitch, pitch, c0, c1, n_valid);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t pv_launch_float_to_pcm24(const float *in, uint8_t *out, int64_t rows, int64_t pitch, int64_t c0, int64_t c1,
+                                     cudaStream_t st)
+{
+    if (rows <= 0 || c1 <= c0) return cudaSuccess;
+    const int vec = !((pitch | c0) & 3) && !(reinterpret_cast<uintptr_t>(out) & 3);
+    for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+        const int64_t nr = std::min<int64_t>(65535, rows - r0);
+        const dim3 grid((unsigned)(((c1 - c0 + 3) / 4 + 255) / 256), (unsigned)nr);
+        float_to_pcm24_kernel<<<grid, 256, 0, st>>>(in + r0 * pitch, out + r0 * pitch * 3, pitch, c0, c1, vec);
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t pv_launch_corrected_generic(const PvDev &d, const PvProcessArgs &a, cudaStream_t st)
 {
     if (a.n_segs <= 0) return cudaSuccess;

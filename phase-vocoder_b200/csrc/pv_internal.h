@@ -140,3 +140,8 @@ cudaError_t pv_launch_pcm16_to_float(const int16_t *in, float *out, int64_t rows
                                      int64_t n_valid, cudaStream_t st);
 cudaError_t pv_launch_float_to_pcm16(const float *in, int16_t *out, int64_t rows, int64_t pitch, int64_t c0, int64_t c1,
                                      cudaStream_t st);
+// packed 24-bit PCM (3 bytes per sample); pitch and columns in samples
+cudaError_t pv_launch_pcm24_to_float(const uint8_t *in, float *out, int64_t rows, int64_t pitch, int64_t c0, int64_t c1,
+                                     int64_t n_valid, cudaStream_t st);
+cudaError_t pv_launch_float_to_pcm24(const float *in, uint8_t *out, int64_t rows, int64_t pitch, int64_t c0, int64_t c1,
+                                     cudaStream_t st);

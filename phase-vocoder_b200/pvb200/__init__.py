@@ -27,6 +27,7 @@ EXPORTS = [
     "pv_reference_schedule", "pv_analysis", "pv_resynthesis", "pv_test_overlap_add", "pv_analysis_batch",
     "pv_resynthesis_batch", "pv_state_bytes", "pv_process_device", "pv_process_device_ex", "pv_process_host",
     "pv_process_host_pcm16",
+    "pv_process_host_pcm24",
     "pv_corrected_aggregate", "pv_corrected_state_from_carry", "pv_launch_count", "pv_timing_enable", "pv_timing_read",
     "pv_rt_open", "pv_rt_close", "pv_rt_reset", "pv_rt_latency_samples", "pv_rt_input", "pv_rt_output", "pv_rt_step",
     "pv_rt_callback", "pv_fft_batch", "pv_corrected_split_aggregate",
@@ -80,6 +81,7 @@ def load():
     L.pv_process_device.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, i64, i64, vp, i32, vp]
     L.pv_process_host.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, i64, i64, vp, i32]
     L.pv_process_host_pcm16.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, i64, i64, vp, i32]
+    L.pv_process_host_pcm24.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, i64, i64, vp, i32]
     L.pv_process_device_ex.argtypes = [vp, vp, i64, i64, i64, i64, i64, i64, vp, i64, i64, vp, i32, vp]
     L.pv_corrected_aggregate.argtypes = [vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp]
     L.pv_corrected_state_from_carry.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp]
@@ -331,6 +333,19 @@ class PhaseVocoder:
             in_stride, os_, ov = x.stride(0), out.stride(0), out.stride(1)
         _check(load().pv_process_host_pcm16(self._h, _ptr(x), S, in_stride, n_in, na, n_frames, _ptr(out), os_, ov,
                                             _ptr(state), flags))
+        return out
+
+    def process_host_pcm24(self, x, n_frames, n_analysed=None, out=None, state=None, flags=0):
+        """Packed 24-bit PCM in and out: x uint8 [streams, n_in, 3] (little-endian bytes of each sample, numpy) ->
+        out uint8 [streams, V, n_frames*Hs, 3]; AudioFile's 24-bit conversions run on the device."""
+        S, n_in, three = x.shape
+        assert three == 3 and x.dtype == np.uint8 and x.strides[1] == 3 and x.strides[2] == 1 and x.strides[0] % 3 == 0
+        n_out = n_frames * self.outHopSize
+        if out is None:
+            out = np.empty((S, self.n_voices, n_out, 3), np.uint8)
+        na = n_frames if n_analysed is None else n_analysed
+        _check(load().pv_process_host_pcm24(self._h, _ptr(x), S, x.strides[0] // 3, n_in, na, n_frames, _ptr(out),
+                                            out.strides[0] // 3, out.strides[1] // 3, _ptr(state), flags))
         return out
 
     def fft_batch(self, x, inverse=False, out=None):

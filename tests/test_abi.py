@@ -67,6 +67,7 @@ def test_null_arguments_are_rejected_before_any_device_work():
         lambda: lib.pv_process_device_ex(None, buf, 1, 8, 8, 1, 1, 0, buf, 8, 8, None, 0, None),
         lambda: lib.pv_process_host(None, buf, 1, 8, 8, 1, 1, buf, 8, 8, None, 0),
         lambda: lib.pv_process_host_pcm16(None, buf, 1, 8, 8, 1, 1, buf, 8, 8, None, 0),
+        lambda: lib.pv_process_host_pcm24(None, buf, 1, 8, 8, 1, 1, buf, 8, 8, None, 0),
         lambda: lib.pv_corrected_aggregate(None, buf, 1, 8, 8, 1, None, buf, None, None, None),
         lambda: lib.pv_corrected_split_aggregate(None, buf, 1, 8, 8, 1, 0, None, 0, buf, None),
         lambda: lib.pv_corrected_state_from_carry(None, 1, buf, buf, 0, buf, None, None),

@@ -51,3 +51,38 @@ def test_pitch_shift_on_the_reference_wav(golden_wav, cfg, wt):
         assert r["phase_ratio"] < 1.0, r
         assert r["frac"] < 1e-3, r
         assert min(r["aligned"]) > 100, r
+
+
+def test_process_host_pcm24_applies_audiofile_rules(golden_wav):
+    """Packed 24-bit PCM in and out (C2's real samples, as stored in MAT_ZO_24_bit.wav): the conversions on the device ==
+    the float path with AudioFile's 24-bit rules applied on the host, byte for byte; both modes; chunked pipeline too."""
+    import wav_oracle as wo
+    v = golden_wav["c2_raw"]                                 # [2, n] int32, 24 significant bits
+    raw = wo.s24_to_bytes(v)                                   # [2, n, 3] uint8, the file's bytes
+    assert np.array_equal(wo.bytes_to_s24(raw), v)
+    xf = (v.astype(np.float32) / np.float32(8388608))
+    N, H = 2048, 512
+    nf = (v.shape[1] - N) // H + 1
+    for mode, pitch in ((pvb200.MODE_COMPAT, 1.0), (pvb200.MODE_CORRECTED, 2.0 ** (7 / 12))):
+        pv = pvb200.PhaseVocoder(N, hop_in=H, hop_out=H, mode=mode, window_type=pvb200.WIN_HANN_PERIODIC, pitch=[pitch])
+        got = pv.process_host_pcm24(raw, nf)
+        assert got.dtype == np.uint8 and got.shape == (2, 1, nf * H, 3)
+        ref = pv.process_host(xf, nf)
+        assert np.array_equal(got, wo.s24_to_bytes(wo.float_to_s24(ref)))
+        # odd row length (device rows are padded to 4 samples) and an output length that is not a multiple of 4
+        pv2 = pvb200.PhaseVocoder(256, hop_in=64, hop_out=62, mode=mode, window_type=pvb200.WIN_HANN_PERIODIC, pitch=[pitch])
+        r2 = np.ascontiguousarray(raw[:, :256 + 30 * 64 + 3])
+        g2 = pv2.process_host_pcm24(r2, 31)
+        f2 = pv2.process_host(np.ascontiguousarray(xf[:, :r2.shape[1]]), 31)
+        assert np.array_equal(g2, wo.s24_to_bytes(wo.float_to_s24(f2)))
+
+
+def test_pcm24_host_pipeline_chunks_bit_exact(monkeypatch, golden_wav):
+    import wav_oracle as wo
+    raw = wo.s24_to_bytes(golden_wav["c2_raw"])
+    pv = pvb200.PhaseVocoder(1024, hop_in=256, hop_out=256, mode=pvb200.MODE_CORRECTED, window_type=pvb200.WIN_HANN_PERIODIC, pitch=[1.25])
+    nf = 100
+    monkeypatch.setenv("PV_HOST_CHUNKS", "1")
+    one = pv.process_host_pcm24(raw, nf)
+    monkeypatch.setenv("PV_HOST_CHUNKS", "7")
+    assert np.array_equal(one, pv.process_host_pcm24(raw, nf))
