@@ -49,13 +49,21 @@ struct NoTw { float2 w[1]; };
 // SRC_LIN / DST_LIN: linear indexing (global memory or the unpadded staging buffer), else the padded work buffer.
 // INPLACE: src == dst; every thread owns at most one butterfly (total <= blockDim), so one barrier between its
 // loads and its stores is all the ordering the autosort permutation needs.
-template <int LG_N, int R, int LG_NS, int DIR, bool SRC_LIN, bool DST_LIN, bool INPLACE, class TWF, class TW>
-__device__ __forceinline__ void stockham_pass(const float2 *src, float2 *dst, int total, const TWF &tw, const TW &rtw)
+// CT_TOTAL / CT_BLOCK > 0: `total` and blockDim.x are these compile-time constants (a full tile of the persistent batched FFT,
+// CT_TOTAL a multiple of CT_BLOCK): the butterfly loop unrolls and its index arithmetic folds into immediates.
+template <int LG_N, int R, int LG_NS, int DIR, bool SRC_LIN, bool DST_LIN, bool INPLACE, int CT_TOTAL, int CT_BLOCK, class TWF, class TW>
+__device__ __forceinline__ void stockham_pass_ct(const float2 *src, float2 *dst, int total, const TWF &tw, const TW &rtw)
 {
     constexpr int LR = Log2<R>::v, LG_PER = LG_N - LR, per = 1 << LG_PER, Ns = 1 << LG_NS;
     static_assert(SRC_LIN || per >= 16, "r*per must stay a multiple of the padding period");
-    if (INPLACE && (int)threadIdx.x >= total) __syncthreads();
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    constexpr bool CT = CT_TOTAL > 0;
+    static_assert(!CT || (CT_BLOCK > 0 && CT_TOTAL % CT_BLOCK == 0), "full tiles only");
+    if (!CT && INPLACE && (int)threadIdx.x >= total) __syncthreads();
+    const int step = CT ? CT_BLOCK : (int)blockDim.x;
+    constexpr int TRIPS = CT ? CT_TOTAL / (CT_BLOCK > 0 ? CT_BLOCK : 1) : 0;
+#pragma unroll(CT ? 16 : 1)
+    for (int it = 0; CT ? it < TRIPS : (int)threadIdx.x + it * step < total; it++) {
+        const int i = (int)threadIdx.x + it * step;
         const int g = i >> LG_PER, idx = i & (per - 1), k = idx & (Ns - 1);
         const int base = g << LG_N;
         float2 v[R];
@@ -113,6 +121,12 @@ __device__ __forceinline__ void stockham_pass(const float2 *src, float2 *dst, in
     }
 }
 
+template <int LG_N, int R, int LG_NS, int DIR, bool SRC_LIN, bool DST_LIN, bool INPLACE, class TWF, class TW>
+__device__ __forceinline__ void stockham_pass(const float2 *src, float2 *dst, int total, const TWF &tw, const TW &rtw)
+{
+    stockham_pass_ct<LG_N, R, LG_NS, DIR, SRC_LIN, DST_LIN, INPLACE, 0, 0>(src, dst, total, tw, rtw);
+}
+
 // A pass that hands its outputs to `sink(n, value)` (n = index within the transform, natural order after the last
 // pass) instead of storing them: lets the consumer of a transform work straight from the butterfly's registers.
 // Source: the padded work buffer.  Twiddles by table lookup (any Ns > 1).
@@ -159,24 +173,33 @@ struct SecondRadix { static constexpr int v = (LG_N - 4 >= 4) ? 16 : (1 << (LG_N
 
 // Passes after the first one, for n = 2^LG_N >= 32: radix 16 with Ns = 16, 256 in place while more than 16 points
 // per butterfly column remain, then one pass of radix n / Ns straight to global memory.
-template <int LG_N, int DIR, class TWF, class TW2>
-__device__ __forceinline__ void remaining_passes(float2 *work, float2 *dst, int tot16, const TWF &tw, const TW2 &tw2)
+// TOT16 / BLOCK > 0: a full tile with a compile-time butterfly count and block size (stockham_pass_ct).
+template <int LG_N, int DIR, int TOT16, int BLOCK, class TWF, class TW2>
+__device__ __forceinline__ void remaining_passes_ct(float2 *work, float2 *dst, int tot16, const TWF &tw, const TW2 &tw2)
 {
     NoTw none;
     constexpr int REST = LG_N - 4;            // log2 of what is left after the first pass
     if constexpr (REST <= 4) {
-        stockham_pass<LG_N, (1 << REST), 4, DIR, false, true, false>(work, dst, tot16 * (16 >> REST), tw, tw2);
+        stockham_pass_ct<LG_N, (1 << REST), 4, DIR, false, true, false, TOT16 * (16 >> REST), BLOCK>(work, dst, tot16 * (16 >> REST), tw, tw2);
     } else {
-        stockham_pass<LG_N, 16, 4, DIR, false, false, true>(work, work, tot16, tw, tw2);
+        stockham_pass_ct<LG_N, 16, 4, DIR, false, false, true, TOT16, BLOCK>(work, work, tot16, tw, tw2);
         __syncthreads();
         if constexpr (REST <= 8) {
-            stockham_pass<LG_N, (1 << (REST - 4)), 8, DIR, false, true, false>(work, dst, tot16 * (16 >> (REST - 4)), tw, none);
+            stockham_pass_ct<LG_N, (1 << (REST - 4)), 8, DIR, false, true, false, TOT16 * (16 >> (REST - 4)), BLOCK>(
+                work, dst, tot16 * (16 >> (REST - 4)), tw, none);
         } else {
-            stockham_pass<LG_N, 16, 8, DIR, false, false, true>(work, work, tot16, tw, none);
+            stockham_pass_ct<LG_N, 16, 8, DIR, false, false, true, TOT16, BLOCK>(work, work, tot16, tw, none);
             __syncthreads();
-            stockham_pass<LG_N, (1 << (REST - 8)), 12, DIR, false, true, false>(work, dst, tot16 * (16 >> (REST - 8)), tw, none);
+            stockham_pass_ct<LG_N, (1 << (REST - 8)), 12, DIR, false, true, false, TOT16 * (16 >> (REST - 8)), BLOCK>(
+                work, dst, tot16 * (16 >> (REST - 8)), tw, none);
         }
     }
+}
+
+template <int LG_N, int DIR, class TWF, class TW2>
+__device__ __forceinline__ void remaining_passes(float2 *work, float2 *dst, int tot16, const TWF &tw, const TW2 &tw2)
+{
+    remaining_passes_ct<LG_N, DIR, 0, 0>(work, dst, tot16, tw, tw2);
 }
 
 }  // namespace pvsmem
