@@ -34,7 +34,7 @@ for n, d, c in rows:
                    f"{'yes' if r['bit_identical_to_single_gpu'] else 'NO'} | {ex} |")
 out += ["",
         "Round 1 (Python orchestration over torch.distributed, two collectives, in-place large-window kernels): 2 GPUs compat 2.0x, corrected",
-        "1.4x (28.2 ms); 4 and 8 GPUs unmeasured.  One hour of stereo audio is now pitch-shifted in 2.0 ms on eight GPUs.",
+        "1.4x (28.2 ms); 4 and 8 GPUs unmeasured.  One hour of stereo audio is now pitch-shifted in 1.9 ms on eight GPUs.",
         "",
         "What limits the scaling at 8 GPUs: each rank's range is 21 094 frames per channel, cut into ~74 parts per channel so that the 296",
         "resident groups of the GPU are busy; every part recomputes its 3-frame overlap-add halo and (corrected) one analysis frame, and the",
@@ -43,7 +43,7 @@ out += ["",
         "corrected mode), then the analysis pass (~30 %).",
         "",
         "Same runs, the headline batch (independent streams per rank, no collective): device-resident "
-        f"{rows[0][1]['value']/1e6:.0f} / {rows[1][1]['value']/1e6:.0f} / {rows[2][1]['value']/1e6:.0f} M frames/s on 2 / 4 / 8 GPUs (1 GPU in the same state of the code: 109 M; the phase-path trims at the end of the round, DESIGN.md 4.2, brought one GPU to 116 M after these runs); end to end "
+        f"{rows[0][1]['value']/1e6:.0f} / {rows[1][1]['value']/1e6:.0f} / {rows[2][1]['value']/1e6:.0f} M frames/s on 2 / 4 / 8 GPUs (1 GPU: 116 M); end to end "
         f"{rows[0][1]['e2e']['value']/1e6:.1f} / {rows[1][1]['e2e']['value']/1e6:.1f} / {rows[2][1]['e2e']['value']/1e6:.1f} M frames/s = "
         f"{rows[0][1]['e2e']['copy_ceiling']['frac_achieved']:.2f} / {rows[1][1]['e2e']['copy_ceiling']['frac_achieved']:.2f} / "
         f"{rows[2][1]['e2e']['copy_ceiling']['frac_achieved']:.2f} of the copy ceiling measured in the same run (`profiles/r02_pcie_probe.md`)."]
@@ -79,7 +79,7 @@ engines of the boxes differ -- 41 to 56 GB/s each way for one GPU alone -- which
 60 M frames/s target for it is above what this box's PCIe moves.
 
 The pipelined host path (chunks of frames on three streams, state carried on the device) therefore sits ON the copy ceiling at every
-GPU count; the kernels behind it scale linearly (109 -> 871 M frames/s at the time of the multi-GPU runs; one GPU is at 116 M now).  The end-to-end number of this box cannot scale past what its
+GPU count; the kernels behind it scale linearly (116 -> 929 M frames/s).  The end-to-end number of this box cannot scale past what its
 host memory system feeds.
 """)
 
