@@ -43,6 +43,12 @@ struct pv_handle {
     size_t carry_cap = 0;
     unsigned char *d_slots = nullptr;
     size_t slots_cap = 0;
+    // Stored analysis of a frame-range split (PvAggArgs::md): {|X|, D} of every frame, [stream][frame][N/2 + 2] float2.  The
+    // analysis pass writes it, the processing pass reads it back instead of repeating the forward transform.
+    float2 *d_md = nullptr;
+    size_t md_cap = 0;                      // float2 elements
+    const void *md_valid_for = nullptr;     // plan whose analysis is in d_md (set and checked together with agg_valid_for)
+    bool env_no_md = false;                 // PV_NO_MD_STORE: always recompute (test / A-B knob, read once at pv_create)
     // Segment tables, cached by shape.  Every entry owns its device tables, so a plan that queued launches
     // still read is never overwritten by the next shape (the pipelined host path alternates between plans).
     struct Plan {
@@ -319,13 +325,35 @@ int plan_corrected_split(pv_handle *h, int64_t n_streams, int64_t n_frames, int3
 // one resident group needs for one full frame.  Segments run in waves of `capacity` resident groups; a split adds the
 // analysis-only aggregate pass (measured ~0.45 of a full frame per frame), the recomputed overlap-add halo of every part
 // and two more launches.  p = 1 is the plain one-segment-per-stream launch.
+// Can a split of n streams x F frames keep its analysis ({|X|, D} per frame and bin) in device memory?  Up to 16 GB of scratch.
+bool md_fits(const pv_handle *h, int64_t n, int64_t F)
+{
+    if (h->env_no_md || !h->fused || h->env_force_generic) return false;
+    // measured (tools/md_ab.py, split runs, stored / recomputing): window 256 3.3 / 3.1 ms at one voice and 10.9 / 8.5 ms at four
+    // (a 1 KB row per frame and 16-thread group: the copies cost more than the forward transform they save); 1024: 0.78 / 0.94;
+    // 2048: 2.8 / 3.6; 4096: 8.7 / 11.6
+    if (h->p.window < 1024) return false;
+    return (double)n * (double)F * (double)(h->p.window / 2 + 2) * 8.0 <= 16.0 * 1073741824.0;
+}
+
 double split_cost(const pv_handle *h, int64_t n, int64_t F, int64_t p)
 {
     const int64_t cap = std::max(1, h->capacity), halo = (h->p.window - 1) / h->p.hop_out;
     const int64_t L = (F + p - 1) / p;
     const double waves = (double)((n * p + cap - 1) / cap);
     if (p <= 1) return waves * (double)F;
-    return waves * ((double)(L + halo) + 0.45 * (double)(L + 1)) + 3.0;
+    // One voice: the forward half (transform + analysis) is ~0.45 of a frame, a voice's synthesis half ~0.55.  V voices run in
+    // launches of at most two voices (pv_fused_corrected_kernels.cu), each with its own forward half.  With the analysis stored
+    // the processing pass is the synthesis halves only (+ ~0.05 per launch for reading the stored frame) and the analysis pass
+    // also stores (+ ~0.05); without, the processing pass is a full frame again.
+    const int V = std::max(1, h->p.n_voices), groups = V >= 3 ? (V + 1) / 2 : 1;
+    const double full = 0.45 * groups + 0.55 * V;
+    double proc = 1.0, agg = 0.45 / full;
+    if (md_fits(h, n, F)) {
+        proc = (0.55 * V + 0.05 * groups) / full;
+        agg = 0.50 / full;
+    }
+    return waves * (proc * (double)(L + halo) + agg * (double)(L + 1)) + 3.0;
 }
 
 // number of frame-range parts per stream for a corrected run (1 = do not split): the cheapest under split_cost.
@@ -413,6 +441,7 @@ int pv_create(const pv_params *params, pv_handle **out)
     h->sm_count = prop.multiProcessorCount;
     h->env_no_split = getenv("PV_NO_SPLIT") != nullptr;
     h->env_force_generic = getenv("PV_FORCE_GENERIC") != nullptr;
+    h->env_no_md = getenv("PV_NO_MD_STORE") != nullptr;
     make_window(p.window_type, N, h->h_win);
     std::vector<float2> tw(N);
     for (int k = 0; k < N; k++) {
@@ -514,6 +543,7 @@ void pv_destroy(pv_handle *h)
     }
     for (auto e : h->pipe_events) cudaEventDestroy(e);
     for (auto p : h->d_fft_tw) cudaFree(p);
+    cudaFree(h->d_md);
     cudaFree(h->d_S);
     cudaFree(h->d_H);
     cudaFree(h->d_Pf);
@@ -666,8 +696,9 @@ int pv_corrected_aggregate(pv_handle *h, const float *in, int64_t n_streams, int
             int rc0 = plan_corrected_split(h, n_streams, n_frames, (int32_t)parts, false, 0, &pl);
             if (rc0 != PV_OK) return rc0;
             h->agg_valid_for = nullptr;          // the shared per-part sums are about to be overwritten
+            h->md_valid_for = nullptr;           // ... and the last phases that go with a stored analysis
             const int nb = h->p.window / 2 + 1;
-            PvAggArgs ag{in, in_stride, n_in, pl->d_agg_segs, pl->n_segs, P_prev, (int64_t)nb, h->d_S, nullptr, h->d_Pf, h->d_Pl, 0};
+            PvAggArgs ag{in, in_stride, n_in, pl->d_agg_segs, pl->n_segs, P_prev, (int64_t)nb, h->d_S, nullptr, h->d_Pf, h->d_Pl, 0, nullptr, 0};
             if (h->fused && !h->env_force_generic) PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, ag, (cudaStream_t)cuda_stream));
             else PV_CUDA(pv_launch_aggregate_generic(h->dev, ag, (cudaStream_t)cuda_stream));
             PV_CUDA(pv_launch_reduce_parts(nb, n_streams, (int32_t)parts, h->d_S, h->d_Pf, h->d_Pl, sumD, P_first, P_last,
@@ -706,7 +737,7 @@ static int aggregate_plain(pv_handle *h, const float *in, int64_t n_streams, int
         pl->n_segs = (int32_t)n_streams;
         pl->kind = 2;
     }
-    PvAggArgs a{in, in_stride, n_in, pl->d_segs, (int32_t)n_streams, P_prev, P_prev_stride, sumD, nullptr, P_first, P_last, in_state};
+    PvAggArgs a{in, in_stride, n_in, pl->d_segs, (int32_t)n_streams, P_prev, P_prev_stride, sumD, nullptr, P_first, P_last, in_state, nullptr, 0};
     if (h->fused && !h->env_force_generic) PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, a, (cudaStream_t)cuda_stream));
     else PV_CUDA(pv_launch_aggregate_generic(h->dev, a, (cudaStream_t)cuda_stream));
     h->launches++;
@@ -838,11 +869,35 @@ static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_
             const int64_t sb = (int64_t)pv_state_bytes(h);
             PvAggArgs ag{in, in_stride, n_in, pl->d_agg_segs, pl->n_segs,
                          user_carry ? reinterpret_cast<const uint32_t *>((const unsigned char *)state + 8) : nullptr, sb / 4,
-                         h->d_S, h->d_H, h->d_Pf, nullptr, 1};
+                         h->d_S, h->d_H, h->d_Pf, nullptr, 1, nullptr, 0};
             // PV_PROCESS_REUSE_AGGREGATE: pv_corrected_split_aggregate has just left the per-part sums of exactly this
             // call in the handle (same plan, same input), so the analysis pass is not repeated
             const bool reuse = (flags & PV_PROCESS_REUSE_AGGREGATE) && h->agg_valid_for == pl;
             h->agg_valid_for = nullptr;
+            // Stored analysis: the analysis pass keeps {|X|, D} of every frame, the processing pass synthesises from it
+            bool use_md = reuse ? h->md_valid_for == pl : (fused_ok && md_fits(h, n_streams, n_frames));
+            h->md_valid_for = nullptr;
+            const size_t nbp = (size_t)h->p.window / 2 + 2;
+            if (use_md && !reuse) {
+                const size_t need = (size_t)n_streams * (size_t)n_frames * nbp;
+                if (need > h->md_cap) {
+                    cudaDeviceSynchronize();
+                    cudaFree(h->d_md);
+                    h->d_md = nullptr;
+                    h->md_cap = 0;
+                    if (cudaMalloc((void **)&h->d_md, need * sizeof(float2)) == cudaSuccess) h->md_cap = need;
+                    else {
+                        cudaGetLastError();          // no room for the scratch: recompute instead
+                        h->d_md = nullptr;
+                        use_md = false;
+                    }
+                }
+            }
+            if (use_md) {
+                ag.md = h->d_md;
+                ag.md_stream_stride = (int64_t)((size_t)n_frames * nbp);
+                ag.P_last = h->d_Pl;
+            }
             if (!reuse) {
                 if (fused_ok) PV_CUDA(pv_launch_corrected_aggregate(h->dev, h->ft, ag, st));
                 else PV_CUDA(pv_launch_aggregate_generic(h->dev, ag, st));
@@ -854,6 +909,7 @@ static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_
                                                nullptr, nullptr, st));
                 h->launches++;
                 h->agg_valid_for = pl;
+                h->md_valid_for = use_md ? pl : nullptr;
                 return PV_OK;
             }
             PV_CUDA(pv_launch_split_states(h->dev, n_streams, (int32_t)parts, pl->d_segs, h->d_S, h->d_H, h->d_Pf,
@@ -871,6 +927,11 @@ static int process_impl(pv_handle *h, const float *in, int64_t n_streams, int64_
             a.state_stride = sb;
             a.segs = pl->d_segs;
             a.n_segs = pl->n_segs;
+            if (use_md) {
+                a.md = h->d_md;
+                a.md_stream_stride = (int64_t)((size_t)n_frames * nbp);
+                a.P_last = h->d_Pl;
+            }
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (h->timing) {
                 PV_CUDA(cudaEventCreate(&e0));

@@ -498,13 +498,17 @@ struct AggCtx {
     bool on;                 // analysis only: no synthesis, no barriers after the forward transform
     long long *sum;          // [NB] per-bin running sum of D for this frame (shared memory, thread-private slots)
     uint32_t *P_first;       // global [NB] or null: phase of the first analysed frame of the segment
+    float2 *md_row;          // global [NB + 1] or null: {|X|, D} of this frame, kept for the processing pass (analysis store)
 };
 
-template <int LOG2N, class Sync, class Hook, class PreLast>
+// MODE 0: the normal frame (and the analysis-only mode that shares its compiled forward transform).  The two halves of the
+// stored-analysis split are kernel instantiations of their own, so that the normal one -- at the 128-register limit -- carries
+// none of them: MODE 2 = analysis-only that also STORES {|X|, D} (AggCtx::md_row), MODE 1 = processing FROM the stored values.
+template <int LOG2N, int MODE = 0, class Sync, class Hook, class PreLast>
 PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const CThreadTw &tt, const float *ring,
                             float2 *bufA, float2 *bufB, float2 *mdS, unsigned long long *psi, float *acc,
                             CState &st, int pos0, int Hs, Sync sync, Hook hook, PreLast pre_last_sync,
-                            const AggCtx agg = AggCtx{false, nullptr, nullptr})
+                            const AggCtx agg = AggCtx{false, nullptr, nullptr, nullptr})
 {
     using C = CShape<LOG2N>;
     using S = Shape<LOG2N>;
@@ -513,9 +517,17 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
     const int u = tid;
     const int tP = u, tQ = (u == 0) ? B3 / 2 : B3 - u;
     float2 X[9], wp[4];
+    const bool first = st.have_prev == 0;
+    if constexpr (MODE == 1) {
+        // Stored analysis: mdS already holds {|X|, D} of this frame (the caller's `hook` waits for its copy), so the forward
+        // transform, the analysis and two of the five barriers of a frame go.  The barrier orders the previous frame's
+        // overlap-add before the hook's emit, as the first barrier of the forward transform does otherwise.
+        sync();
+        hook();
+        wp[0] = tt.wN; wp[1] = twid16<2, -1>(tt.wN); wp[2] = twid16<4, -1>(tt.wN); wp[3] = twid16<6, -1>(tt.wN);
+    } else {
     cforward<LOG2N, TWREG>(tid, io, tb, tt, ring, bufA, bufB, sync, hook, X, wp);
     // ---- analysis: magnitude, phase (turns*2^32), unwrapped phase difference ----
-    const bool first = st.have_prev == 0;
     const SlotNomA nomA = slot_nomA_all<LOG2N>(u, tb.Ha);
     if (agg.on) {
         uint32_t Pn[9];
@@ -528,9 +540,19 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
             if (sl == 8 && u != 0) break;
             const int bin = slot_bin<B3>(u, sl);
             const uint32_t Pc = Pn[sl];
+            const int32_t dd = (int32_t)(Pc - st.Pexp[sl]);          // first frame: Pexp = 0, D = the phase itself
             // branch-free in the common case (see the synthesis slot loop): a first frame adds 0
-            agg.sum[bin] += first ? 0ll : (long long)(int32_t)(Pc - st.Pexp[sl]);
+            agg.sum[bin] += first ? 0ll : (long long)dd;
             st.Pexp[sl] = Pc + nomA(sl);
+            if constexpr (MODE == 2) {
+                if (agg.md_row) {        // uniform: the same two values the processing pass would put in shared memory
+                    const float2 x = X[sl];
+                    agg.md_row[bin] = make_float2(fast_sqrt(x.x * x.x + x.y * x.y), __int_as_float(dd));
+                }
+            }
+        }
+        if constexpr (MODE == 2) {
+            if (agg.md_row && u == 0) agg.md_row[NB] = make_float2(0.f, 0.f);      // the dummy bin
         }
         if (first && agg.P_first) {          // once per segment, outside the slot loop
 #pragma unroll
@@ -559,8 +581,9 @@ PV_DEV void frame_corrected(int tid, const FrameIO &io, const CTables &tb, const
         mdS[bin] = make_float2(fast_sqrt(x.x * x.x + x.y * x.y), __int_as_float(dd));
         st.Pexp[sl] = Pc + nomA(sl);
     }
-    st.have_prev = 1;
     sync();
+    }
+    st.have_prev = 1;
     // ---- synthesis, one voice at a time ----
     for (int v = 0; v < tb.V; v++) {
         const uint32_t *gt = tb.gather + ((size_t)v * C::T + u) * 9;

@@ -28,7 +28,10 @@ struct CLaunch {
     static size_t group_bytes(int V)
     {
         return (size_t)(C::BUF_A + C::BUF_B) * sizeof(float2) + (size_t)V * ((C::NB + 1) & ~1) * 8 +
-               (size_t)((C::NB + 3) & ~3) * 4 * 2 + (size_t)V * C::N * 4 + (size_t)C::N * 4 + 16;     // + the ring's mbarrier
+               (size_t)((C::NB + 3) & ~3) * 4 * 2 + (size_t)V * C::N * 4 + (size_t)C::N * 4 + 16 + 128;
+        // ... + the mbarrier + room behind the ring: the stored-analysis mode keeps a second {|X|, D} buffer of N/2 + 2 float2 =
+        // 4 N + 16 bytes there.  128 and not 16: two groups of a small window share a warp, and the bank phase between their
+        // bases (the group size mod 128) is part of the tuned layout -- +16 cost the two- and four-voice window-256 runs 5 %.
     }
 };
 
@@ -44,7 +47,11 @@ struct CGroupSync {
     }
 };
 
-template <int LOG2N, int MINB>
+// MODE (frame_corrected): 1 = the stored-analysis processing pass (PvProcessArgs::md), 2 = the analysis pass that stores
+// (PvAggArgs::md); both are instantiations of their own: the normal one (processing with the forward transform, and the
+// analysis-only mode that shares its compiled copy) sits at the 128-register limit and lost 2 - 5 % when the extra modes were
+// run-time branches in it.
+template <int LOG2N, int MINB, int MODE = 0>
 __global__ void __launch_bounds__(CLaunch<LOG2N>::THREADS, MINB)
 corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int vec_out_ok, int use_ring,
                        unsigned group_bytes, PvAggArgs ag)
@@ -70,6 +77,12 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(base + group_bytes - 16);
     unsigned mbar_phase = 0;
     bool bulk_pending = false;
+    // Stored-analysis mode (PvProcessArgs::md): the frames' {|X|, D} come from global memory, double-buffered in the array's
+    // own region and the (then unused) input ring, one bulk copy per frame on the ring's mbarrier
+    constexpr int NBP = NB + 1;                                 // floats2 per stored frame (even: rows stay 16-byte aligned)
+    // (nothing of this mode may stay live across the frame loop of the normal mode: the kernel sits at the 128-register limit;
+    // buffer parity = frame parity within the segment, pointers are rebuilt where they are used)
+    constexpr bool md_load = MODE == 1;
     unsigned long long *psi_v0 = psi;      // voice stride in psi is NB (kernel body) -> keep packed
     (void)psi_v0;
 
@@ -124,7 +137,7 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
             if (agg_pf) agg_pf[bin] = 0u;
         }
     } else {
-        if (tid == 0) mdS[NB] = make_float2(0.f, 0.f);     // the dummy bin behind empty gather entries (pv_fused_tables.h)
+        if (tid == 0 && !md_load) mdS[NB] = make_float2(0.f, 0.f);     // the dummy bin behind empty gather entries (pv_fused_tables.h); stored rows carry it
         // zero until the stream's first frame: that frame's update relies on it (psi_step)
         for (int i = tid; i < V * NB; i += T) psi[i] = (cin && st.have_prev) ? st_psi[i] : 0ull;
         for (int i = tid; i < V * N; i += T) {
@@ -132,7 +145,13 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
             acc[i] = (cin && ii + Hs < N) ? st_acc[i + Hs] : 0.f;
         }
     }
-    if (use_ring == 3 && tid == 0) mbar_init(mbar, 1);
+    auto md_buf = [&](long long k) { return ((k - seg.k_begin) & 1) ? reinterpret_cast<float2 *>(acc + (size_t)V * N) : mdS; };
+    auto md_fetch = [&](long long k) {           // thread 0: one bulk copy of frame k's stored row into its buffer
+        const float2 *src = a.md + seg.stream * a.md_stream_stride + k * NBP;
+        bulk_load_hop(reinterpret_cast<float *>(md_buf(k)), reinterpret_cast<const float *>(src), (unsigned)(NBP * sizeof(float2)), mbar);
+    };
+    if ((use_ring == 3 || md_load) && tid == 0) mbar_init(mbar, 1);
+    if (md_load && tid == 0) md_fetch(seg.k_begin);
     if (use_ring) {
         FrameIO io0{in, a.n_in, seg.k_begin * (long long)d.Ha, true, true};
         if (use_ring >= 2) ring_prefetch_coop16<N, T>(tid, io0, ring, 0);
@@ -166,6 +185,13 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
     for (long long k = seg.k_begin; k < seg.k_end; ++k) {
         FrameIO io{in, a.n_in, k * (long long)d.Ha, true, vec_in_ok != 0};
         auto hook = [&]() {
+            if (md_load) {
+                // this frame's copy was issued a frame ago; only then the next one (one copy in flight per mbarrier phase),
+                // into the buffer whose last readers -- the previous frame's slot loops -- are behind the frame's first barrier
+                mbar_wait(mbar, mbar_phase);
+                mbar_phase ^= 1u;
+                if (k + 1 < seg.k_end && tid == 0) md_fetch(k + 1);
+            }
             if (use_ring && k + 1 < seg.k_end) {
                 FrameIO nx{in, a.n_in, (k + 1) * (long long)d.Ha, true, true};
                 const long long g0 = nx.base + (N - d.Ha);                // first new sample of the next frame
@@ -177,9 +203,10 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
             }
             if (!agg_mode && k > seg.k_begin) emit(k - 1, (pos0 - Hs) & (N - 1), PV_ZERO_ON_EMIT);
         };
-        const AggCtx ac{agg_mode, k < seg.k_emit ? sumH : sumS, agg_pf};
-        frame_corrected<LOG2N>(tid, io, tb, tt, ring, bufA, bufB, mdS, psi, acc, st, pos0, Hs, sync, hook,
-                               [&]() { if (use_ring) cp_async_wait_all(); }, ac);
+        const AggCtx ac{agg_mode, k < seg.k_emit ? sumH : sumS, agg_pf,
+                        (MODE == 2 && k >= seg.k_emit) ? ag.md + seg.stream * ag.md_stream_stride + k * NBP : nullptr};
+        frame_corrected<LOG2N, MODE>(tid, io, tb, tt, ring, bufA, bufB, md_load ? md_buf(k) : mdS, psi, acc, st, pos0, Hs, sync, hook,
+                                       [&]() { if (use_ring) cp_async_wait_all(); }, ac);
         if (agg_mode && use_ring) {        // analysis only: no inverse passes whose last barrier would complete the refill
             cp_async_wait_all();
             sync();
@@ -211,8 +238,12 @@ corrected_fused_kernel(PvDev d, CTables tb, PvProcessArgs a, int vec_in_ok, int 
             if (tid == 0) { st_hdr[0] = (uint32_t)st.have_prev; st_hdr[1] = 0; }
 #pragma unroll
             for (int sl = 0; sl < 9; sl++)
-                if (sl < 8 || tid == 0)
-                    st_P[slot_bin<B3>(tid, sl)] = st.have_prev ? st.Pexp[sl] - slot_nomA<LOG2N>(tid, sl, d.Ha) : 0u;
+                if (sl < 8 || tid == 0) {
+                    const int bin = slot_bin<B3>(tid, sl);
+                    // stored analysis: the phases never passed through this launch; the analysis pass left the last one
+                    st_P[bin] = md_load ? a.P_last[(long long)seg_idx * NB + bin]
+                                        : (st.have_prev ? st.Pexp[sl] - slot_nomA<LOG2N>(tid, sl, d.Ha) : 0u);
+                }
         }
         for (int i = tid; i < V * NB; i += T) st_psi[i] = psi[i];
         for (int i = tid; i < V * N; i += T) st_acc[i] = acc[(i & ~(N - 1)) + ((plast + i) & (N - 1))];
@@ -251,7 +282,6 @@ template <int LOG2N, int MINB>
 cudaError_t claunch(const PvDev &d, const CTables &tb, const PvProcessArgs &a, cudaStream_t st, bool no_ring = false)
 {
     using L = CLaunch<LOG2N>;
-    auto kern = corrected_fused_kernel<LOG2N, MINB>;
     const bool in_ok = (d.Ha % 2 == 0) && (a.in_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.in) & 7) == 0);
     const bool out_ok = (d.Hs % 4 == 0) && (a.out_stream_stride % 4 == 0) && (a.out_voice_stride % 4 == 0) &&
                         ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
@@ -261,12 +291,20 @@ cudaError_t claunch(const PvDev &d, const CTables &tb, const PvProcessArgs &a, c
     static const bool ldgsts = getenv("PV_RING_LDGSTS") != nullptr;       // A/B switch, read once
     int ring = (in_ok && d.Ha <= d.N && !no_ring) ? (al16 ? 2 : 1) : 0;
     if (ring == 2 && !ldgsts && d.N % d.Ha == 0) ring = 3;
-    const size_t gb = L::group_bytes(tb.V) - (ring ? 0 : (size_t)d.N * 4);
+    if (a.md) ring = 0;                                    // stored analysis: no input is read; the ring's region holds a buffer
+    const size_t gb = L::group_bytes(tb.V) - ((ring || a.md) ? 0 : (size_t)d.N * 4);
     const size_t smem = gb * L::G;
-    cudaError_t e = pv_max_smem_once<corrected_fused_kernel<LOG2N, MINB>>();
-    if (e != cudaSuccess) return e;
     const int grid = (a.n_segs + L::G - 1) / L::G;
-    kern<<<grid, L::THREADS, smem, st>>>(d, tb, a, in_ok, out_ok, ring, (unsigned)gb, PvAggArgs{});
+    cudaError_t e;
+    if (a.md) {
+        e = pv_max_smem_once<corrected_fused_kernel<LOG2N, MINB, 1>>();
+        if (e != cudaSuccess) return e;
+        corrected_fused_kernel<LOG2N, MINB, 1><<<grid, L::THREADS, smem, st>>>(d, tb, a, in_ok, out_ok, ring, (unsigned)gb, PvAggArgs{});
+    } else {
+        e = pv_max_smem_once<corrected_fused_kernel<LOG2N, MINB>>();
+        if (e != cudaSuccess) return e;
+        corrected_fused_kernel<LOG2N, MINB><<<grid, L::THREADS, smem, st>>>(d, tb, a, in_ok, out_ok, ring, (unsigned)gb, PvAggArgs{});
+    }
     return cudaGetLastError();
 }
 
@@ -344,7 +382,7 @@ static cudaError_t agg_launch(const PvDev &d, const CTables &tb, const PvAggArgs
     const int ring = (in_ok && d.Ha <= d.N) ? (al16 ? 2 : 1) : 0;
     const size_t gb = L::group_bytes(tb.V) - (ring ? 0 : (size_t)d.N * 4);
     const size_t smem = gb * L::G;
-    cudaError_t e = pv_max_smem_once<corrected_fused_kernel<LOG2N, MINB>>();
+    cudaError_t e = ag.md ? pv_max_smem_once<corrected_fused_kernel<LOG2N, MINB, 2>>() : pv_max_smem_once<corrected_fused_kernel<LOG2N, MINB>>();
     if (e != cudaSuccess) return e;
     PvProcessArgs a{};
     a.in = ag.in;
@@ -353,7 +391,8 @@ static cudaError_t agg_launch(const PvDev &d, const CTables &tb, const PvAggArgs
     a.segs = ag.segs;
     a.n_segs = ag.n_segs;
     const int grid = (ag.n_segs + L::G - 1) / L::G;
-    kern<<<grid, L::THREADS, smem, st>>>(d, tb, a, in_ok, 0, ring, (unsigned)gb, ag);
+    if (ag.md) corrected_fused_kernel<LOG2N, MINB, 2><<<grid, L::THREADS, smem, st>>>(d, tb, a, in_ok, 0, ring, (unsigned)gb, ag);
+    else kern<<<grid, L::THREADS, smem, st>>>(d, tb, a, in_ok, 0, ring, (unsigned)gb, ag);
     return cudaGetLastError();
 }
 

@@ -48,6 +48,12 @@ struct PvProcessArgs {
     int64_t state_stride; // bytes
     const PvSegment *segs;
     int32_t n_segs;
+    // Stored analysis (fused corrected kernel; null = compute it): {|X|, D} per frame and bin as PvAggArgs::md left them; the
+    // frames are then synthesised from it -- no input samples are read.  P_last [n_segs][N/2 + 1]: the phase of each segment's
+    // last frame (from the same analysis pass), which a segment with carry_out writes into the state.
+    const float2 *md;
+    int64_t md_stream_stride;
+    const uint32_t *P_last;
 };
 
 // Device copies of the fused kernels' twiddle tables (pv_fused_tables.h).
@@ -99,6 +105,11 @@ struct PvAggArgs {
     int64_t *S, *H;
     uint32_t *P_first, *P_last;
     int32_t P_prev_in_state;  // P_prev rows sit inside state records: the have_prev word (P_prev[-2]) gates the carry
+    // Analysis store (fused kernels; null = off): the pass also writes {|X|, D} of every frame a segment OWNS (k >= k_emit) to
+    // md + stream * md_stream_stride + frame * (N/2 + 2), float2 units, so that the processing pass of a frame-range split
+    // reads them back instead of repeating the forward transform (PvProcessArgs::md).
+    float2 *md;
+    int64_t md_stream_stride;
 };
 cudaError_t pv_launch_corrected_aggregate(const PvDev &d, const PvFusedTables &t, const PvAggArgs &a, cudaStream_t st);
 cudaError_t pv_launch_state_from_carry(const PvDev &d, const PvFusedTables &t, int64_t n_streams, const uint32_t *P_first,

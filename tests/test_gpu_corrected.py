@@ -227,6 +227,31 @@ def test_corrected_intra_gpu_split_is_bit_exact(monkeypatch, N, Ha, Hs, betas, n
     assert torch.equal(st_a, st_b)
 
 
+@pytest.mark.parametrize("N,Ha,Hs,betas,nf,S", [(1024, 256, 256, [0.8, SEMI7], 4000, 1), (2048, 512, 384, [0.75], 2500, 2),
+                                                (4096, 1024, 1024, [1.0, 0.9, SEMI7], 1500, 1)])
+def test_stored_analysis_split_equals_recomputing_split(monkeypatch, N, Ha, Hs, betas, nf, S):
+    """A frame-range split keeps {|X|, D} of every frame from its analysis pass and synthesises from them (PvAggArgs::md /
+    PvProcessArgs::md: no second forward transform).  PV_NO_MD_STORE=1 makes the processing pass repeat the forward transform,
+    PV_NO_SPLIT=1 runs the streams sequentially: all three bit-identical, output and carried state -- with pitch ratios < 1
+    (multi-source bins), several voices and the voice-group launches."""
+    x = torch.from_numpy(np.stack([multitone(N + nf * Ha, seed=90 + s, noise=1e-3) for s in range(S)])).cuda()
+
+    def run():
+        pv = make(N, Ha, Hs, betas)
+        st = torch.zeros((S, pv.state_bytes()), dtype=torch.uint8, device="cuda")
+        y = pv.process(x, nf, state=st, flags=pvb200.CARRY_OUT).cpu().numpy()
+        return y, st.cpu().numpy(), pv.launch_count()
+
+    stored = run()
+    monkeypatch.setenv("PV_NO_MD_STORE", "1")
+    recomputed = run()
+    monkeypatch.setenv("PV_NO_SPLIT", "1")
+    sequential = run()
+    assert stored[2] >= 3 and recomputed[2] >= 3            # both were split
+    assert np.array_equal(stored[0], recomputed[0]) and np.array_equal(stored[1], recomputed[1])
+    assert np.array_equal(stored[0], sequential[0]) and np.array_equal(stored[1], sequential[1])
+
+
 def test_corrected_split_with_carry_in_and_skip_is_bit_exact(monkeypatch):
     """The on-GPU split also starts from a carried-in state and honours skip_frames (what a frame-range rank
     of a multi-GPU run does); and the public aggregate is split the same way.  All bit-identical to sequential."""
