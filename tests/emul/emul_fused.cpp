@@ -17,6 +17,11 @@ using namespace pvfused;
 // one, so the barrier phases stay aligned).  -1 = run normally.  ThreadSanitizer must then report a race.
 static int g_drop_barrier = -1;
 extern "C" void emul_drop_barrier(int k) { g_drop_barrier = k; }
+// Stored-analysis split (frame_corrected MODE 2 then MODE 1): emul_corrected runs the analysis-only pass over the whole stream,
+// keeping {|X|, D} of every frame, and then the processing pass that synthesises from the stored rows (double-buffered, the next
+// row copied by thread 0 where the kernel issues its bulk copy).  Same output as the normal frame, bit for bit.
+static int g_stored = 0;
+extern "C" void emul_stored_analysis(int on) { g_stored = on; }
 
 template <int LOG2N>
 static int run(const float *x, long n_in, int Ha, int Hs, const float *win, long n_analysed, long n_frames,
@@ -123,6 +128,65 @@ static int run_corrected(const float *x, long n_in, int Ha, int Hs, const float 
     std::barrier bar(T);
     const bool use_ring = (Ha % 2) == 0 && Ha <= N;
     float *ring = use_ring ? ringbuf.data() : nullptr;
+    constexpr int NBP = NB + 1;
+    std::vector<float2> md_all(g_stored ? (size_t)n_frames * NBP : 0), md_alt(NBP);
+    std::vector<long long> sums(NB, 0);
+    auto body_stored = [&](int tid) {
+        int nbar = 0;
+        auto sync = [&]() { if (nbar++ != g_drop_barrier) bar.arrive_and_wait(); };
+        const CThreadTw tt = load_cthread_tw<LOG2N>(tid, tb);
+        {   // pass 1: analysis only, storing
+            CState st{};
+            if (use_ring) {
+                FrameIO io0{x, n_in, 0, true, true};
+                ring_prefetch_coop<N, T>(tid, io0, ring, 0);
+                cp_async_wait_all();
+            }
+            sync();
+            for (long k = 0; k < n_frames; k++) {
+                FrameIO io{x, n_in, k * (long long)Ha, true, (Ha % 2) == 0};
+                auto hook = [&]() {
+                    if (use_ring && k + 1 < n_frames) {
+                        FrameIO nx{x, n_in, (k + 1) * (long long)Ha, true, true};
+                        ring_prefetch_coop<N, T>(tid, nx, ring, N - Ha);
+                    }
+                };
+                const AggCtx ac{true, sums.data(), nullptr, md_all.data() + (size_t)k * NBP};
+                frame_corrected<LOG2N, 2>(tid, io, tb, tt, ring, bufA.data(), bufB.data(), mdS.data(), psi.data(), acc.data(), st, 0,
+                                          Hs, sync, hook, [&]() { cp_async_wait_all(); }, ac);
+                if (use_ring) { cp_async_wait_all(); sync(); }
+            }
+            sync();
+        }
+        // pass 2: processing from the stored rows
+        CState st{};
+        int pos0 = 0;
+        auto md_buf = [&](long k) { return (k & 1) ? md_alt.data() : mdS.data(); };
+        if (tid == 0) std::memcpy(md_buf(0), md_all.data(), sizeof(float2) * NBP);
+        sync();
+        for (long k = 0; k < n_frames; k++) {
+            FrameIO io{x, n_in, k * (long long)Ha, true, (Ha % 2) == 0};
+            auto hook = [&]() {
+                if (k + 1 < n_frames && tid == 0) std::memcpy(md_buf(k + 1), md_all.data() + (size_t)(k + 1) * NBP, sizeof(float2) * NBP);
+                if (k > 0) {
+                    const int pp = (pos0 - Hs) & (N - 1);
+                    for (int v = 0; v < V; v++)
+                        for (int j = tid; j < Hs; j += T) {
+                            out[v * out_stride + (k - 1) * (long)Hs + j] = acc[(size_t)v * N + ((pp + j) & (N - 1))];
+                            acc[(size_t)v * N + ((pp + j) & (N - 1))] = 0.f;
+                        }
+                }
+            };
+            frame_corrected<LOG2N, 1>(tid, io, tb, tt, nullptr, bufA.data(), bufB.data(), md_buf(k), psi.data(), acc.data(), st, pos0, Hs,
+                                      sync, hook, []() {});
+            pos0 = (pos0 + Hs) & (N - 1);
+        }
+        sync();
+        const int pp = (pos0 - Hs) & (N - 1);
+        for (int v = 0; v < V; v++)
+            for (int j = tid; j < Hs; j += T)
+                out[v * out_stride + (n_frames - 1) * (long)Hs + j] = acc[(size_t)v * N + ((pp + j) & (N - 1))];
+    };
     auto body = [&](int tid) {
         int nbar = 0;
         auto sync = [&]() { if (nbar++ != g_drop_barrier) bar.arrive_and_wait(); };
@@ -162,7 +226,10 @@ static int run_corrected(const float *x, long n_in, int Ha, int Hs, const float 
                 out[v * out_stride + (n_frames - 1) * (long)Hs + j] = acc[(size_t)v * N + ((pp + j) & (N - 1))];
     };
     std::vector<std::thread> th;
-    for (int t = 0; t < T; t++) th.emplace_back(body, t);
+    for (int t = 0; t < T; t++) {
+        if (g_stored) th.emplace_back(body_stored, t);
+        else th.emplace_back(body, t);
+    }
     for (auto &t : th) t.join();
     return 0;
 }

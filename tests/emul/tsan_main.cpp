@@ -40,7 +40,13 @@ int main(int argc, char **argv)
         rc |= emul_corrected(lg, x.data(), n_in, H, H, win.data(), V, nomA.data(), alo.data(), ahi.data(),
                              (const unsigned long long *)nomS.data(), (const unsigned long long *)Rq,
                              (const unsigned long long *)bq, pvo_corrected_gain(win.data(), N, H), nf, out.data(), (long)nf * H);
-        printf("window %d: compat + corrected (2 voices) x %d frames emulated with %d threads, rc=%d\n", N, nf, N / 16, rc);
+        // the stored-analysis split: analysis pass that stores, then the processing pass with its own barrier structure
+        emul_stored_analysis(1);
+        rc |= emul_corrected(lg, x.data(), n_in, H, H, win.data(), V, nomA.data(), alo.data(), ahi.data(),
+                             (const unsigned long long *)nomS.data(), (const unsigned long long *)Rq,
+                             (const unsigned long long *)bq, pvo_corrected_gain(win.data(), N, H), nf, out.data(), (long)nf * H);
+        emul_stored_analysis(0);
+        printf("window %d: compat + corrected (2 voices) + stored-analysis split x %d frames emulated with %d threads, rc=%d\n", N, nf, N / 16, rc);
     }
     return rc;
 }

@@ -74,3 +74,14 @@ def test_corrected_body_matches_oracle(emul, N, Ha, Hs, betas, nf):
     want, _ = po.process_corrected(x, N, Ha, Hs, win, betas, nf)
     for v in range(V):
         assert snr_db(want[v], out[v]) > 100, (v, snr_db(want[v], out[v]))
+    # the stored-analysis split (analysis pass keeps {|X|, D} of every frame, processing pass synthesises from the stored rows:
+    # frame_corrected MODE 2 then MODE 1, three barriers per frame) gives the same samples bit for bit
+    out2 = np.zeros_like(out)
+    emul.emul_stored_analysis(1)
+    try:
+        rc = emul.emul_corrected(int(np.log2(N)), x.ctypes.data_as(fp), n_in, Ha, Hs, win.ctypes.data_as(fp), V,
+                                 nomA.ctypes.data, a_lo.ctypes.data, a_hi.ctypes.data, nomS.ctypes.data, Rq.ctypes.data,
+                                 bq.ctypes.data, po.corrected_gain(win, Hs), nf, out2.ctypes.data_as(fp), nf * Hs)
+    finally:
+        emul.emul_stored_analysis(0)
+    assert rc == 0 and np.array_equal(out, out2)
