@@ -19,7 +19,7 @@ out = ["# C5 (one long file, frame-range sharded) on 2 / 4 / 8 x B200 (round 2)\
        "`python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 bench.py --gpus G` prints this as the",
        "`c5_sharded` record of its JSON line (full lines: `profiles/r02_bench_{2,4,8}gpu.json`).  Workload: BASELINE.json config 5, a synthetic",
        "1-hour 48 kHz stereo file, window 4096, hop 1024 (2 x 168 750 frames).  The sharding runs **behind the C ABI**: `pv_shard_begin`",
-       "(analysis of the rank's range) -> ONE NCCL all-gather of the packed carry record (49 184 bytes per rank for the two channels: per-bin",
+       "(analysis of the rank's range, which keeps {|X|, D} of every frame) -> ONE NCCL all-gather of the packed carry record (49 184 bytes per rank for the two channels: per-bin",
        "int64 sums + rank 0's phase of frame 0) -> `pv_shard_finish` (state from the carry, processing; the analysis pass is reused, not",
        "repeated).  Every rank hands the library only its own view of the input: its frame range, the overlap-add halo and one more frame.",
        "Timing: CUDA events around three calls after two warm-ups, max over ranks; rank 0 gathers the ranges, runs the whole file alone and",
@@ -34,7 +34,7 @@ for n, d, c in rows:
                    f"{'yes' if r['bit_identical_to_single_gpu'] else 'NO'} | {ex} |")
 out += ["",
         "Round 1 (Python orchestration over torch.distributed, two collectives, in-place large-window kernels): 2 GPUs compat 2.0x, corrected",
-        "1.4x (28.2 ms); 4 and 8 GPUs unmeasured.  One hour of stereo audio is now pitch-shifted in 1.9 ms on eight GPUs.",
+        "1.4x (28.2 ms); 4 and 8 GPUs unmeasured.  One hour of stereo audio is now pitch-shifted in 1.6 ms on eight GPUs (8.8 ms on one: the single-GPU time fell by a quarter when the split began to keep its analysis, DESIGN.md 4.2, which is why the ratios are lower than the 1.86x / 3.49x / 6.15x measured against the recomputing split earlier in the round).",
         "",
         "What limits the scaling at 8 GPUs: each rank's range is 21 094 frames per channel, cut into ~74 parts per channel so that the 296",
         "resident groups of the GPU are busy; every part recomputes its 3-frame overlap-add halo and (corrected) one analysis frame, and the",
@@ -79,7 +79,7 @@ engines of the boxes differ -- 41 to 56 GB/s each way for one GPU alone -- which
 60 M frames/s target for it is above what this box's PCIe moves.
 
 The pipelined host path (chunks of frames on three streams, state carried on the device) therefore sits ON the copy ceiling at every
-GPU count; the kernels behind it scale linearly (116 -> 929 M frames/s).  The end-to-end number of this box cannot scale past what its
+GPU count; the kernels behind it scale linearly (116 -> 931 M frames/s).  The end-to-end number of this box cannot scale past what its
 host memory system feeds.
 """)
 
@@ -94,13 +94,13 @@ Round 1 (same tool, at the start of this round): 300 / 592 / 600 / 740 / 900 str
 1184-stream rate (fewer than two waves of streams were ALWAYS cut into frame-range parts, which costs an extra analysis pass), and
 1200 / 1300 / 1500 / 1800 at 0.84 / 0.90 / 0.93 / 0.92 (ragged last wave).
 
-Now: (1) a cost model decides the number of parts (`split_cost` in `csrc/pv_capi.cu`: waves x (frames + halo) + 0.45 x analysis
-frames + launches) and splits only when that is clearly cheaper; (2) a batch with a ragged last wave runs its full waves unsplit and
+Now: (1) a cost model decides the number of parts (`split_cost` in `csrc/pv_capi.cu`: waves x (processing share x (frames + halo) +
+analysis share x frames) + launches, by number of voices and by whether the analysis is stored) and splits only when that is clearly cheaper; (2) a batch with a ragged last wave runs its full waves unsplit and
 hands the remaining streams to a second call that is free to split them.
 
 """ + rd("r02_stream_sweep_body.md") + """
-Corrected mode stays within 0.85 - 1.02 of the 1184-stream rate from 592 to 2400 streams (worst: 900 streams = 1.52 waves; a partial wave
-of a latency-bound kernel costs almost a full wave, and cutting ALL streams in two would cost the analysis pass).  300 streams use half
+Corrected mode stays within 0.92 - 1.02 of the 1184-stream rate from 592 to 2400 streams (worst: 900 streams = 1.52 waves; before the
+split kept its analysis -- DESIGN.md 4.2, stored analysis -- the worst point was 0.85 and 300 streams ran at 0.61).  300 streams use half
 the machine by construction.  Compat mode cuts every stream into segments (frames are independent) and is flat.
 """)
 open(os.path.join(P, "r02_configs.md"), "w").write("""# All five BASELINE.json configs on one B200 (round 2)
