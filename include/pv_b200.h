@@ -147,7 +147,12 @@ size_t pv_state_bytes(const pv_handle *h);
  *               (flags & PV_PROCESS_CARRY_OUT).  An all-zero state is a fresh start, so a block-by-block
  *               caller may zero it once and pass both flags on every call.
  * Long streams are split into frame-range segments processed concurrently (the (N-Hs) OLA
- * halo is recomputed, so the result does not depend on the split).                            */
+ * halo is recomputed, so the result does not depend on the split).  Corrected mode: a split runs an
+ * analysis pass first (per-bin phase carries); for windows >= 1024 that pass keeps magnitude and
+ * phase difference of every frame in device scratch owned by the handle -- (N/2 + 2) * 8 bytes per
+ * frame and stream, at most 16 GB, freed by pv_destroy -- and the processing pass synthesises from it
+ * instead of repeating the forward transform; a call whose scratch would not fit (or cannot be
+ * allocated) recomputes.  Either way the result is bit-identical to the unsplit run.              */
 enum { PV_PROCESS_CARRY_IN = 1, PV_PROCESS_CARRY_OUT = 2, PV_PROCESS_REUSE_AGGREGATE = 4 };
 
 int pv_process_device(pv_handle *h, const float *in, int64_t n_streams, int64_t in_stride,

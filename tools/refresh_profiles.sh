@@ -23,5 +23,6 @@ python tools/run_configs.py --sweep > $O/${R}_sweep_body.md 2> $O/sweep.err
 python tools/stream_sweep.py > $O/${R}_stream_sweep_body.md 2> $O/ssweep.err
 python tools/fft_bench.py > $O/${R}_fft_bench.md 2> $O/fft.err
 python tools/voices_probe.py > $O/${R}_voices.md 2> $O/voices.err
+[ -x tools/micro/exchange_shfl ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/micro/exchange_shfl tools/micro/exchange_shfl.cu
 tools/micro/exchange_shfl > $O/${R}_exchange_micro.md 2> $O/micro.err
 for f in ncu1 ncu2 ncu3 ncu4; do tail -n 2 $O/$f.log; done; tail -c 300 $O/${R}_bench.json; tail -3 $O/${R}_configs_body.md
