@@ -148,7 +148,7 @@ size_t pv_state_bytes(const pv_handle *h);
  *               caller may zero it once and pass both flags on every call.
  * Long streams are split into frame-range segments processed concurrently (the (N-Hs) OLA
  * halo is recomputed, so the result does not depend on the split).  Corrected mode: a split runs an
- * analysis pass first (per-bin phase carries); for windows >= 1024 that pass keeps magnitude and
+ * analysis pass first (per-bin phase carries); for windows >= 512 that pass keeps magnitude and
  * phase difference of every frame in device scratch owned by the handle -- (N/2 + 2) * 8 bytes per
  * frame and stream, at most 16 GB, freed by pv_destroy -- and the processing pass synthesises from it
  * instead of repeating the forward transform; a call whose scratch would not fit (or cannot be

@@ -49,6 +49,7 @@ struct pv_handle {
     size_t md_cap = 0;                      // float2 elements
     const void *md_valid_for = nullptr;     // plan whose analysis is in d_md (set and checked together with agg_valid_for)
     bool env_no_md = false;                 // PV_NO_MD_STORE: always recompute (test / A-B knob, read once at pv_create)
+    int md_min_window = 512;                // PV_MD_MIN_WINDOW overrides (A-B knob): smallest window that stores its analysis
     // Segment tables, cached by shape.  Every entry owns its device tables, so a plan that queued launches
     // still read is never overwritten by the next shape (the pipelined host path alternates between plans).
     struct Plan {
@@ -330,9 +331,9 @@ bool md_fits(const pv_handle *h, int64_t n, int64_t F)
 {
     if (h->env_no_md || !h->fused || h->env_force_generic) return false;
     // measured (tools/md_ab.py, split runs, stored / recomputing): window 256 3.3 / 3.1 ms at one voice and 10.9 / 8.5 ms at four
-    // (a 1 KB row per frame and 16-thread group: the copies cost more than the forward transform they save); 1024: 0.78 / 0.94;
-    // 2048: 2.8 / 3.6; 4096: 8.7 / 11.6
-    if (h->p.window < 1024) return false;
+    // (a 1 KB row per frame and 16-thread group: the copies cost more than the forward transform they save); 512: 1.7 / 2.2;
+    // 1024: 0.78 / 0.94; 2048: 2.8 / 3.6; 4096: 8.7 / 11.6
+    if (h->p.window < h->md_min_window) return false;
     return (double)n * (double)F * (double)(h->p.window / 2 + 2) * 8.0 <= 16.0 * 1073741824.0;
 }
 
@@ -442,6 +443,7 @@ int pv_create(const pv_params *params, pv_handle **out)
     h->env_no_split = getenv("PV_NO_SPLIT") != nullptr;
     h->env_force_generic = getenv("PV_FORCE_GENERIC") != nullptr;
     h->env_no_md = getenv("PV_NO_MD_STORE") != nullptr;
+    if (const char *e = getenv("PV_MD_MIN_WINDOW")) h->md_min_window = std::max(256, atoi(e));
     make_window(p.window_type, N, h->h_win);
     std::vector<float2> tw(N);
     for (int k = 0; k < N; k++) {

@@ -227,7 +227,7 @@ def test_corrected_intra_gpu_split_is_bit_exact(monkeypatch, N, Ha, Hs, betas, n
     assert torch.equal(st_a, st_b)
 
 
-@pytest.mark.parametrize("N,Ha,Hs,betas,nf,S", [(1024, 256, 256, [0.8, SEMI7], 4000, 1), (2048, 512, 384, [0.75], 2500, 2),
+@pytest.mark.parametrize("N,Ha,Hs,betas,nf,S", [(512, 128, 128, [0.8, SEMI7], 4000, 1), (1024, 256, 256, [1.0], 3000, 2), (2048, 512, 384, [0.75], 2500, 2),
                                                 (4096, 1024, 1024, [1.0, 0.9, SEMI7], 1500, 1)])
 def test_stored_analysis_split_equals_recomputing_split(monkeypatch, N, Ha, Hs, betas, nf, S):
     """A frame-range split keeps {|X|, D} of every frame from its analysis pass and synthesises from them (PvAggArgs::md /
