@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=FRAMES_PER_STREAM)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-c5", action="store_true", help="skip the frame-range-sharded long file (config 5) at --gpus > 1")
+    ap.add_argument("--no-c5", action="store_true", help="skip the long file of config 5 (one GPU: record `c5`; --gpus > 1: frame-range sharded, record `c5_sharded`)")
     return ap.parse_args()
 
 
@@ -292,17 +292,14 @@ def bind_to_gpu_numa_node(index):
         return None
 
 
-def c5_sharded(torch, dist, pvb200, world, rank, local, seconds=3600.0):
-    """BASELINE.json config 5: a synthetic 1-hour 48 kHz stereo file, window 4096 / hop 1024 (2 x 168 750 frames), frame-range
-    sharded over the ranks behind the C ABI (pv_shard_begin -> ONE NCCL all-gather of the carry records -> pv_shard_finish).
-    Every rank hands the library only its own view (range + overlap-add halo + one frame).  Timing: CUDA events, max over
-    ranks; rank 0 also runs the whole file alone for the speed-up and checks the gathered result bit for bit."""
-    from pvb200 import sharding
+def c5_file(torch, seconds=3600.0):
+    """BASELINE.json config 5's input: a synthetic 48 kHz stereo file (three tones per channel + noise, seed 0), window 4096,
+    hop 1024.  Returns (x [2, n] on the GPU, n_frames)."""
     N, H, fs = 4096, 1024, 48000.0
     nf = int(seconds * fs) // H
     n = N + (nf - 1) * H
     g = torch.Generator(device="cuda")
-    g.manual_seed(0)                                  # the same file on every rank
+    g.manual_seed(0)
     t = torch.arange(n, device="cuda", dtype=torch.float64)
     x = torch.empty((2, n), device="cuda", dtype=torch.float32)
     for c in range(2):
@@ -312,7 +309,49 @@ def c5_sharded(torch, dist, pvb200, world, rank, local, seconds=3600.0):
         for i in range(3):
             acc += (a[i] * torch.sin(6.283185307179586 * f[i] / fs * t)).float()
         x[c] = acc + torch.randn(n, generator=g, device="cuda") * 1e-3
-    del t
+    return x, nf
+
+
+def c5_single(torch, pvb200, local, seconds=3600.0):
+    """Config 5 on ONE GPU (the record `c5` of the N = 1 line): the two channels are cut into frame-range parts on the device
+    (analysis pass that keeps {|X|, D} of every frame -> per-part phase carry -> processing from the stored analysis; compat:
+    independent segments).  Device-resident, CUDA events, 3 calls after 2 warm-ups."""
+    N, H = 4096, 1024
+    x, nf = c5_file(torch, seconds)
+    rec = {"workload": f"synthetic {seconds / 3600:g} h 48 kHz stereo file, window {N}, hop {H}: 2 x {nf} frames, one GPU"}
+    for mode in ("corrected", "compat"):
+        corr = mode == "corrected"
+        pv = pvb200.PhaseVocoder(N, hop_in=H, hop_out=H, device=local, mode=pvb200.MODE_CORRECTED if corr else pvb200.MODE_COMPAT,
+                                 window_type=pvb200.WIN_HANN_PERIODIC if corr else pvb200.WIN_HAMMING, pitch=(SEMITONES_7,))
+        out = torch.empty((2, 1, nf * H), device="cuda")
+        for _ in range(2):
+            pv.process(x, nf, out=out)
+        torch.cuda.synchronize()
+        n0 = pv.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            pv.process(x, nf, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        rec[mode] = {"ms": ms, "frames_per_s": 2 * nf / (ms * 1e-3), "audio_s_per_s": 2 * seconds / (ms * 1e-3),
+                     "launches_per_call": (pv.launch_count() - n0) // 3, "checksum": float(out[0, 0, :4096].double().abs().sum())}
+        pv.close()
+        del out
+        torch.cuda.empty_cache()
+    return rec
+
+
+def c5_sharded(torch, dist, pvb200, world, rank, local, seconds=3600.0):
+    """BASELINE.json config 5: a synthetic 1-hour 48 kHz stereo file, window 4096 / hop 1024 (2 x 168 750 frames), frame-range
+    sharded over the ranks behind the C ABI (pv_shard_begin -> ONE NCCL all-gather of the carry records -> pv_shard_finish).
+    Every rank hands the library only its own view (range + overlap-add halo + one frame).  Timing: CUDA events, max over
+    ranks; rank 0 also runs the whole file alone for the speed-up and checks the gathered result bit for bit."""
+    from pvb200 import sharding
+    N, H = 4096, 1024
+    x, nf = c5_file(torch, seconds)                   # the same file on every rank (seeded)
+    n = x.shape[1]
     comm = sharding.TorchComm()
     rec = {"workload": f"synthetic {seconds / 3600:g} h 48 kHz stereo file, window {N}, hop {H}: 2 x {nf} frames, frame ranges over "
                        f"{world} GPUs", "exchange": "one all_gather of pv_shard_carry_elems() int64 per channel and rank (corrected); "
@@ -543,13 +582,13 @@ def run_ours(args):
                  "corrected = phase-unwrap/pitch pipeline the north star names (+7 semitones)"}
         pv2.close()
 
-    # ---- BASELINE config 5 when several GPUs are given: ONE long stereo file, frame-range sharded over the ranks ----
+    # ---- BASELINE config 5: ONE long stereo file -- on one GPU (record `c5`), or frame-range sharded over the ranks (`c5_sharded`) ----
     c5 = None
-    if world > 1 and not args.no_c5:
+    if not args.no_c5:
         del x, out
         torch.cuda.empty_cache()
         try:
-            c5 = c5_sharded(torch, dist, pvb200, world, rank, local)
+            c5 = c5_sharded(torch, dist, pvb200, world, rank, local) if world > 1 else c5_single(torch, pvb200, local)
         except Exception as e:          # noqa: BLE001 -- a side record: never lose the headline line over it
             c5 = {"error": f"{type(e).__name__}: {e}"}
 
@@ -599,7 +638,7 @@ def run_ours(args):
         }
         line["other_mode"] = other
         if c5 is not None:
-            line["c5_sharded"] = c5
+            line["c5_sharded" if world > 1 else "c5"] = c5
         if world == 1:
             line["reference_gpu_build"] = reference_gpu_build()
         if world == 1 and not args.no_cpu_baseline:
