@@ -290,8 +290,9 @@ cudaError_t claunch(const PvDev &d, const CTables &tb, const PvProcessArgs &a, c
     // 3: bulk asynchronous hop copies (needs the hop to divide the window so that a hop never wraps in the ring)
     static const bool ldgsts = getenv("PV_RING_LDGSTS") != nullptr;       // A/B switch, read once
     int ring = (in_ok && d.Ha <= d.N && !no_ring) ? (al16 ? 2 : 1) : 0;
-    // (window 256: two 16-thread groups share a warp and wait on different mbarriers; measured 908 M frames/s with the bulk
-    // ring, 924 M with the 16-byte cp.async ring -- and the stored analysis, which waits the same way, loses there, pv_capi.cu)
+    // (window 256: a bulk request per 256-byte hop and 16-thread group does not pay -- measured 908 M frames/s with the bulk ring,
+    // 924 M with the 16-byte cp.async ring, also with a retry loop the two groups of a warp reconverge behind; the stored
+    // analysis, 1 KB per request, loses there as well, pv_capi.cu)
     if (ring == 2 && !ldgsts && d.N % d.Ha == 0 && LOG2N >= 9) ring = 3;
     if (a.md) ring = 0;                                    // stored analysis: no input is read; the ring's region holds a buffer
     const size_t gb = L::group_bytes(tb.V) - ((ring || a.md) ? 0 : (size_t)d.N * 4);
