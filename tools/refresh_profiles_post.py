@@ -82,8 +82,10 @@ for n in ("bench.json", "bench_reference.json", "bench_under_profile_config.json
 # SASS of the two headline kernels
 so = os.path.join(ROOT, "phase-vocoder_b200", "libpv_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-for name, key in (("corrected_fused_n2048", "corrected_fused_kernelILi11ELi4"), ("compat_fused_n2048", "compat_fused_kernelILi11ELi5ELi2"),
-                  ("corrected_fused_n4096", "corrected_fused_kernelILi12ELi2"), ("compat_fused_n4096", "compat_fused_kernelILi12ELi2ELi3")):
+# (corrected: ...ELi0E = the normal instantiation, ...ELi1E = processing from the stored analysis)
+for name, key in (("corrected_fused_n2048", "corrected_fused_kernelILi11ELi4ELi0E"), ("compat_fused_n2048", "compat_fused_kernelILi11ELi5ELi2"),
+                  ("corrected_fused_n4096", "corrected_fused_kernelILi12ELi2ELi0E"), ("compat_fused_n4096", "compat_fused_kernelILi12ELi2ELi3"),
+                  ("corrected_stored_n4096", "corrected_fused_kernelILi12ELi2ELi1E")):
     parts = sass.split("\t\tFunction : ")
     body = [p for p in parts if p.startswith("_Z") and key in p.split("\n")[0]]
     open(os.path.join(P, f"{R}_sass_{name}.txt"), "w").write("Function : " + body[0] if body else "not found\n")
