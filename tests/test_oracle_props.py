@@ -202,3 +202,28 @@ def test_decision_aligned_parity_between_the_f32_and_f64_oracle(N, H, beta, nf, 
     assert r["frac"] < 1e-3, r                # flips are rare among the bins that carry energy
     assert min(r["aligned"]) > 100, r         # and nothing else differs
     assert min(r["direct"]) > 60, r
+
+
+def test_24_bit_sample_rules_round_trip_and_match_the_wav_decoder():
+    """The checker side of pv_process_host_pcm24 (oracle/wav_oracle.py): bytes <-> sign-extended ints round trip, the encode rule
+    is AudioFile's `(int32)(x * 8388608.)` (truncation toward zero, no clamp, low three bytes), and the helper decodes a 24-bit
+    WAV `data` chunk exactly like decode_wav (AudioFile.h:508-518)."""
+    import struct
+
+    import wav_oracle as wo
+    rng = np.random.default_rng(3)
+    v = np.concatenate([rng.integers(-(1 << 23), 1 << 23, size=4000), [-(1 << 23), (1 << 23) - 1, -1, 0, 1]]).astype(np.int32)
+    b = wo.s24_to_bytes(v)
+    assert b.shape == (len(v), 3) and b.dtype == np.uint8
+    assert np.array_equal(wo.bytes_to_s24(b), v)
+    x = v.astype(np.float32) / np.float32(8388608)                     # the decode rule; exact in fp32
+    assert np.array_equal(wo.float_to_s24(x), v)                       # ... so encoding gives the integers back
+    assert wo.float_to_s24(np.float32([0.9999999, -0.9999999, 0.5 / 8388608, -0.5 / 8388608])).tolist() == [8388607, -8388607, 0, 0]
+    over = wo.float_to_s24(np.float32([1.0, 1.5]))                     # no clamp: the low three bytes wrap
+    assert wo.bytes_to_s24(wo.s24_to_bytes(over)).tolist() == [-(1 << 23), -(1 << 22)]
+    # a mono 24-bit WAV around the same bytes
+    pcm = b.tobytes()
+    hdr = b"RIFF" + struct.pack("<i", 36 + len(pcm)) + b"WAVE" + b"fmt " + struct.pack("<ihhiihh", 16, 1, 1, 44100, 3 * 44100, 3, 24) + \
+        b"data" + struct.pack("<i", len(pcm))
+    s, rate, bits = wo.decode_wav(hdr + pcm)
+    assert bits == 24 and rate == 44100 and np.array_equal(s[0], x)
